@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Generate golden vectors by running the UNMODIFIED reference (needs /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+It imports the reference's own modules (lib.model.rie, lib.model.Model, lib.camera.camera,
+lib.train_val.trainer.eval_data_prepare), loads seeded synthetic weights
+(ray3d_b200.synth, numpy PCG64 => reproducible on any box) with load_state_dict(strict=True)
+and stores inputs plus fp32 / fp64 outputs as small .npz fixtures beside this script.
+Weights are NOT stored (80-200 MB each); each fixture carries a float64 digest of the state
+dicts so tests can prove the regenerated weights are the ones the reference saw.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("RAY3D_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from ray3d_b200.spec import NetSpec  # noqa: E402
+from ray3d_b200 import synth  # noqa: E402
+
+from lib.model.rie import RIEModel, RIETrajectoryModel  # noqa: E402  (reference)
+from lib.camera.camera import CameraInfoPacket, normalize_screen_coordinates  # noqa: E402  (reference)
+
+CASES = {
+    # name: (spec kwargs, batch, resolution, uv kind)
+    "h36m_s1_t27": (dict(num_joints=17, in_features=3, filter_widths=(3, 3, 3), stage=1), 3, 1000, "smooth"),
+    "h36m_s3_t9": (dict(num_joints=17, in_features=3, filter_widths=(3, 3), stage=3), 4, 1000, "smooth"),
+    "humaneva_s1_t9": (dict(num_joints=15, in_features=3, filter_widths=(3, 3), stage=1), 3, 1000, "uniform"),
+    "h36mcross_s2_t9": (dict(num_joints=14, in_features=3, filter_widths=(3, 3), stage=2), 3, 1000, "smooth"),
+    "rie_s1_t9_noembed": (dict(num_joints=17, in_features=2, filter_widths=(3, 3), stage=1, extrinsic_dim=0,
+                               embed_dim=0), 3, 1000, "smooth"),
+    "rie15_s3_t27": (dict(num_joints=15, in_features=2, filter_widths=(3, 3, 3), stage=3, extrinsic_dim=0,
+                          embed_dim=0), 2, 1000, "smooth"),
+    "h36m_s1_t81": (dict(num_joints=17, in_features=3, filter_widths=(3, 3, 3, 3), stage=1), 2, 1000, "smooth"),
+    "h36m_s1_t243": (dict(num_joints=17, in_features=3, filter_widths=(3, 3, 3, 3, 3), stage=1), 2, 1000, "smooth"),
+    "3dhp_s3_t243": (dict(num_joints=17, in_features=3, filter_widths=(3, 3, 3, 3, 3), stage=3), 2, 2048, "smooth"),
+}
+
+
+def build_reference(spec: NetSpec, sd_pos, sd_trj, dtype):
+    kw = dict(filter_widths=list(spec.filter_widths), causal=False, dropout=0.2, latten_features=spec.latent,
+              channels=spec.channels, dense=False, is_train=False, Optimize1f=True, stage=spec.stage,
+              extrinsic_dim=spec.extrinsic_dim, embedd_dim=spec.embed_dim)
+    pos = RIEModel(spec.num_joints, spec.in_features, spec.num_joints, **kw)
+    trj = RIETrajectoryModel(spec.num_joints, spec.in_features, spec.num_joints, **kw)
+    pos.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd_pos.items()}, strict=True)
+    trj.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd_trj.items()}, strict=True)
+    return pos.to(dtype).eval(), trj.to(dtype).eval()
+
+
+def encode_with_reference(uv, cam, res):
+    """Ray-encode every sequence with the reference's CameraInfoPacket (undistort=False)."""
+    out = np.empty(uv.shape[:-1] + (3,), dtype=np.float64)
+    for b in range(uv.shape[0]):
+        fx, fy, cx, cy, pitch, height = (float(v) for v in cam[b])
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=np.float64)
+        c, s = np.cos(pitch), np.sin(pitch)
+        # A camera pitched by `pitch` about x looking along world +y, z up: Rw2c rows = cam axes in world.
+        R = np.array([[1, 0, 0], [0, -s, -c], [0, c, -s]], dtype=np.float64)
+        t = -R @ np.array([[0.0], [0.0], [height]])
+        pkt = CameraInfoPacket(P=None, K=K, R=R, t=t, dist_coeff=None, res_w=res, res_h=res, undistort=False)
+        # replace the derived pitch by the table's pitch so both sides encode with the same angle
+        pkt.cam_pitch_rad = pitch
+        pkt.Rc2n, pkt.Tc2n = pkt.get_norm_coord_config()
+        out[b] = pkt.get_cam_ray_given_uv(uv[b].astype(np.float64))
+    return out
+
+
+def main():
+    torch.manual_seed(14)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    meta = {}
+    for idx, (name, (kw, batch, res, kind)) in enumerate(CASES.items()):
+        spec = NetSpec(**kw)
+        sd_pos, sd_trj = synth.make_state_dicts(spec)
+        uv, cam = synth.make_inputs(spec, batch, seed=1234 + idx, res=res, kind=kind)
+        if spec.in_features == 3:
+            x64 = encode_with_reference(uv, cam, res)
+        else:
+            x64 = normalize_screen_coordinates(uv.astype(np.float64), w=res, h=res)
+        x = x64.astype(np.float32)                                     # trainer.py:298
+        param = np.ascontiguousarray(cam[:, [5, 4]]) if spec.camera_embedding else np.zeros((batch, 2), np.float32)
+        out = {}
+        for tag, dtype in (("32", torch.float32), ("64", torch.float64)):
+            pos, trj = build_reference(spec, sd_pos, sd_trj, dtype)
+            with torch.no_grad():
+                xt = torch.from_numpy(x).to(dtype)
+                pt = torch.from_numpy(param).to(dtype)
+                out["pos" + tag] = pos(xt, pt).numpy()
+                out["trj" + tag] = trj(xt, pt).numpy()
+            if tag == "32":
+                keys_pos = [(k, list(v.shape)) for k, v in pos.state_dict().items()]
+                keys_trj = [(k, list(v.shape)) for k, v in trj.state_dict().items()]
+                named_pos = [k for k, _ in pos.named_parameters()]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), uv=uv, cam=cam, x64=x64, x=x, param=param,
+                            digest=np.array([synth.state_digest(sd_pos), synth.state_digest(sd_trj)]), **out)
+        meta[name] = dict(spec=dict(kw, filter_widths=list(kw["filter_widths"])), batch=batch, res=res, kind=kind,
+                          seed=1234 + idx, keys_pos=keys_pos, keys_trj=keys_trj, named_params_pos=named_pos,
+                          receptive_field=pos.receptive_field())
+        err = np.linalg.norm(out["pos32"] - out["pos64"]) / np.linalg.norm(out["pos64"])
+        print(f"{name:22s} pos {out['pos32'].shape} trj {out['trj32'].shape} fp32-vs-fp64 relerr {err:.2e}")
+
+    # camera fixtures: real-looking extrinsics through the reference class (pitch/height derivation)
+    rng = np.random.Generator(np.random.PCG64(77))
+    cams = []
+    for i in range(6):
+        ang = rng.uniform(-1.0, 1.0, size=3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+        Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+        Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+        R = Rx @ Ry @ Rz
+        t = rng.uniform(-3.0, 3.0, size=(3, 1))
+        fx, fy = rng.uniform(1000, 1500, size=2)
+        cx, cy = rng.uniform(450, 600, size=2)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]])
+        pkt = CameraInfoPacket(P=None, K=K, R=R, t=t, dist_coeff=None, res_w=1000, res_h=1002, undistort=False)
+        uv = rng.uniform(0, 1000, size=(5, 17, 2))
+        cams.append(dict(K=K, R=R, t=t, uv=uv, ray=pkt.get_cam_ray_given_uv(uv), pitch=pkt.cam_pitch_rad,
+                         height=float((-pkt.Rw2c.T @ pkt.Tw2c)[2][0]), Rc2n=pkt.Rc2n,
+                         enc=pkt.encode_uv_with_intrinsic(uv),
+                         norm=normalize_screen_coordinates(uv, w=1000, h=1002)))
+    np.savez_compressed(os.path.join(HERE, "camera.npz"),
+                        **{f"{k}{i}": np.asarray(c[k]) for i, c in enumerate(cams) for k in c})
+
+    # sliding-window materialisation (trainer.py:47-58) -- imported lazily, it pulls in lib.loss etc.
+    try:
+        from lib.train_val.trainer import Trainer  # noqa: E402  (reference)
+        seq = torch.from_numpy(rng.standard_normal(size=(1, 40, 17, 3)).astype(np.float32))
+        win, _ = Trainer.eval_data_prepare(27, seq, None)
+        np.savez_compressed(os.path.join(HERE, "windows.npz"), seq=seq.numpy(), win=win.numpy())
+    except Exception as e:  # pragma: no cover
+        print("eval_data_prepare fixture skipped:", e)
+
+    with open(os.path.join(HERE, "meta.json"), "w") as f:
+        json.dump(meta, f, indent=0)
+    print("wrote", len(CASES), "cases to", HERE)
+
+
+if __name__ == "__main__":
+    main()
