@@ -1,0 +1,171 @@
+/*
+ * ray3d_b200.h -- C ABI of the B200-native Ray3D lifting forward pass.
+ *
+ * One shared library (libray3d_b200.so, hand-written sm_100a CUDA) replaces, for eval-mode
+ * inference, the PyTorch module graph the reference dispatches for its 2D->3D lifting path.
+ * Every entry point names the reference interface it stands in for (paths are relative to the
+ * reference checkout, YxZhxn/Ray3D @ aff4b9f).  No torch types cross this boundary: plain
+ * pointers, sizes and a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative r3d_status; r3d_last_error() gives the
+ *     message for the calling thread.  Nothing throws across the ABI.
+ *   - "_dev" pointers are device pointers on the plan's device; "_host" pointers are host memory.
+ *   - forward calls are asynchronous on `stream` (the caller's current stream) and do no host
+ *     allocation; the *_host variants copy in/out themselves and synchronise before returning.
+ *   - outputs are always freshly written caller-owned buffers (the reference's callers mutate
+ *     the returned tensors in place, lib/train_val/trainer.py:215,340,353).
+ */
+#ifndef RAY3D_B200_H_
+#define RAY3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define R3D_API __attribute__((visibility("default")))
+#else
+#define R3D_API
+#endif
+
+#define R3D_ABI_VERSION 1
+#define R3D_MAX_WIDTHS 8
+
+typedef enum {
+  R3D_OK = 0,
+  R3D_ERR_BAD_ARG = -1,        /* null pointer, bad shape; mirrors the asserts at lib/model/rie.py:285-287 */
+  R3D_ERR_UNSUPPORTED = -2,    /* config outside what the reference itself supports */
+  R3D_ERR_MISSING_WEIGHT = -3, /* finalize() before every state_dict tensor was supplied */
+  R3D_ERR_CUDA = -4,           /* a CUDA runtime/driver call failed */
+  R3D_ERR_STATE = -5,          /* call order violated (e.g. forward before upload) */
+  R3D_ERR_NO_DEVICE = -6       /* no usable sm_100 device: the product path never falls back to CPU */
+} r3d_status;
+
+/* Arithmetic used for the conv/linear contractions. */
+typedef enum {
+  R3D_PREC_FP32 = 0,   /* FP32 FFMA everywhere (bit-for-bit fp32 operands, fp32 accumulate) */
+  R3D_PREC_BF16X3 = 1, /* tcgen05 tensor cores, operands split hi+lo bf16, 3 products, fp32 accumulate
+                          (~1e-5 normwise vs fp64; meets the 1e-4 fp32 parity bar) */
+  R3D_PREC_BF16 = 2    /* tcgen05, single bf16 product (BASELINE config 3; ~3e-3 normwise) */
+} r3d_precision;
+
+/* Which of the reference's two nn.Modules a plan computes. */
+#define R3D_NET_POS 1 /* RIEModel            lib/model/rie.py:172-434 */
+#define R3D_NET_TRJ 2 /* RIETrajectoryModel  lib/model/rie.py:437-559 */
+
+/* Mirrors the constructor arguments lib/model/__init__.py:11-46 derives from cfg_*.model_config
+ * (NUM_KPTS, INPUT_DIM, ARCHITECTURE, CHANNELS, LATENT_FEATURES_DIM, STAGE, EXTRINSIC_DIM,
+ * EMBEDD_DIM; CAUSAL/DENSE/DISABLE_OPTIMIZATIONS must be False -- the only combination that runs in
+ * the reference). */
+typedef struct {
+  int32_t num_joints;               /* 17, 15 or 14 */
+  int32_t in_features;              /* 3 (ray encoding) or 2 (cfg_rie_*) */
+  int32_t n_widths;                 /* len(ARCHITECTURE) */
+  int32_t widths[R3D_MAX_WIDTHS];   /* odd filter widths; receptive field = product */
+  int32_t channels;                 /* CHANNELS (multiple of 64) */
+  int32_t latent;                   /* LATENT_FEATURES_DIM (multiple of 64) */
+  int32_t stage;                    /* 1, or !=1 for FuseBlocks */
+  int32_t extrinsic_dim;            /* 0 disables the camera embedding */
+  int32_t embed_dim;
+  int32_t nets;                     /* R3D_NET_POS | R3D_NET_TRJ */
+  int32_t precision;                /* r3d_precision */
+} r3d_config;
+
+typedef struct r3d_plan r3d_plan;
+
+R3D_API int r3d_abi_version(void);
+R3D_API const char* r3d_last_error(void);
+
+/* --- plan lifecycle: replaces Model(model_config, ...) + load_state_dict ------------------------
+ * r3d_plan_create    <- RIEModel.__init__ / RIETrajectoryModel.__init__ (rie.py:178-253, 443-494).
+ *                       Host only, no CUDA call.
+ * r3d_plan_set_tensor<- one state_dict entry, by the reference's own key (e.g.
+ *                       "LocalLayer_Torso.expand_conv.weight"; a leading "module." from
+ *                       nn.DataParallel checkpoints is accepted, trainer.py:232-240).  `net` is
+ *                       R3D_NET_POS or R3D_NET_TRJ.  Shape-checked: unlike lib/utils/utils.py:208-218
+ *                       (load_weight silently drops mismatches) an unknown key or wrong shape is an error.
+ * r3d_plan_finalize  <- folds eval-mode BatchNorm (running stats, eps 1e-5) into the preceding
+ *                       conv/linear in float64, repacks to the kernels' K-major layout and splits to
+ *                       bf16 hi/lo for the tensor-core precisions.  Host only.
+ * r3d_plan_upload    <- .cuda() (lib/model/__init__.py:51-53): copies packed weights to `device`.
+ */
+R3D_API int r3d_plan_create(const r3d_config* cfg, r3d_plan** out);
+R3D_API int r3d_plan_set_tensor(r3d_plan* plan, int net, const char* name, const float* data_host,
+                        const int64_t* shape, int ndim);
+R3D_API int r3d_plan_finalize(r3d_plan* plan);
+R3D_API int r3d_plan_upload(r3d_plan* plan, int device);
+R3D_API void r3d_plan_destroy(r3d_plan* plan);
+
+/* Introspection used by the CPU test-suite (no GPU needed): packed, BN-folded fp32 weights of one
+ * layer.  `layer` is the reference module path, e.g. "LocalLayer_LArm.layers_conv.0" or
+ * "GlobalInfo.fc_1".  Returns rows/cols of the K-major matrix [n_pad][k_pad]; copies
+ * min(cap, n_pad*k_pad) weights and min(cap_b, n_pad) biases. */
+R3D_API int r3d_plan_packed_layer(const r3d_plan* plan, int net, const char* layer, int32_t* n_pad, int32_t* k_pad,
+                          float* w_out, int64_t cap, float* b_out, int64_t cap_b);
+/* JSON description of the launch graph (activation buffers, grouped GEMM ops and their bindings, input-stage
+ * gather tables, output slots).  Writes at most cap bytes (NUL terminated) and the required size to *needed.
+ * Used by the CPU tests to replay the wiring with numpy; host only. */
+R3D_API int r3d_plan_describe(const r3d_plan* plan, char* out, int64_t cap, int64_t* needed);
+R3D_API int64_t r3d_plan_weight_bytes(const r3d_plan* plan);     /* device bytes of packed weights */
+R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* plan);  /* device bytes of activations at current capacity */
+R3D_API int r3d_plan_receptive_field(const r3d_plan* plan);       /* rie.py:278-282 */
+R3D_API int r3d_plan_kernel_launches(const r3d_plan* plan);       /* kernels one forward enqueues */
+
+/* --- forward: replaces nn.Module.forward(x, param) ------------------------------------------------
+ * x_dev     (B, T, J, Cin) float32 contiguous, T == receptive field (rie.py:284-304; the reference
+ *           only works for T == RF).
+ * param_dev (B, extrinsic_dim) float32 = [height_m, pitch_rad] (trainer.py:297,324); ignored (may be
+ *           NULL) when the camera embedding is off.
+ * pos_dev   (B, 1, J, 3) float32 or NULL   <- RIEModel.forward            rie.py:284-434
+ * trj_dev   (B, 1, 1, 3) float32 or NULL   <- RIETrajectoryModel.forward  rie.py:518-559
+ * sum_dev   (B, 1, J, 3) float32 or NULL   <- predicted_3d_pos += predicted_3d_trj, trainer.py:353
+ */
+R3D_API int r3d_forward_rays(r3d_plan* plan, const float* x_dev, const float* param_dev, float* pos_dev,
+                     float* trj_dev, float* sum_dev, int32_t batch, void* stream);
+
+/* Same, but starting from pixel keypoints: fuses CameraInfoPacket.get_cam_ray_given_uv
+ * (lib/camera/camera.py:423-441, 460-471; undistort=False) into the input stage.
+ * uv_dev  (B, T, J, 2) float32 pixels;  cam_dev (B, 6) float32 = [fx, fy, cx, cy, pitch_rad, height_m].
+ * The encode runs in float64 and rounds to float32 exactly like trainer.py:298. in_features must be 3. */
+R3D_API int r3d_forward_uv(r3d_plan* plan, const float* uv_dev, const float* cam_dev, float* pos_dev,
+                   float* trj_dev, float* sum_dev, int32_t batch, void* stream);
+
+/* Host-buffer variants (the end-to-end call: H2D of inputs, forward, D2H of results, chunked and
+ * double-buffered on internal streams; returns after the results are in host memory).
+ * Stand in for trainer.py:329-356 (.cuda() ... forward ... .cpu()). */
+R3D_API int r3d_forward_rays_host(r3d_plan* plan, const float* x_host, const float* param_host, float* pos_host,
+                          float* trj_host, float* sum_host, int32_t batch);
+R3D_API int r3d_forward_uv_host(r3d_plan* plan, const float* uv_host, const float* cam_host, float* pos_host,
+                        float* trj_host, float* sum_host, int32_t batch);
+
+/* Sliding-window evaluation of one video without materialising windows:
+ * replaces Trainer.eval_data_prepare + np.tile(cam_param) + forward (trainer.py:47-58, 323-337).
+ * seq_dev (F + RF - 1, J, Cin) float32 (already edge-padded like generators.py:209-234);
+ * param_dev (extrinsic_dim) float32 shared by all windows; outputs have F rows. */
+R3D_API int r3d_forward_video(r3d_plan* plan, const float* seq_dev, const float* param_dev, float* pos_dev,
+                      float* trj_dev, float* sum_dev, int32_t frames_out, void* stream);
+
+/* --- standalone camera encode: CameraInfoPacket.get_cam_ray_given_uv in float64 ------------------
+ * uv_dev (n_points, 2) float64 -> ray_dev (n_points, 3) float64; one camera (fx, fy, ppx, ppy) and
+ * cos/sin of the pitch computed by the caller with libm (math.cos/math.sin, camera.py:333-338) so the
+ * result is bit-identical to the reference's numpy arithmetic. */
+R3D_API int r3d_ray_encode_f64(const double* uv_dev, double* ray_dev, int64_t n_points, double fx, double fy,
+                       double ppx, double ppy, double cos_pitch, double sin_pitch, void* stream);
+
+/* normalize_screen_coordinates (lib/camera/camera.py:11-18) in float64 for the cfg_rie_* (in_features == 2)
+ * input encoding: out = xy / w * 2 - [1, h / w].  xy_dev/out_dev (n_points, 2) float64; may alias. */
+R3D_API int r3d_normalize_screen_f64(const double* xy_dev, double* out_dev, int64_t n_points, double w, double h,
+                                     void* stream);
+
+/* --- self tests (used by tests/ and smoke(); run on the device, compare the tensor-core GEMM with
+ * the FP32 FFMA GEMM on seeded data).  Returns max |tc - ffma| / max|ffma| in *rel_err. */
+R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
+                      double* rel_err, double* ms_tc, double* ms_ffma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAY3D_B200_H_ */

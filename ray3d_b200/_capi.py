@@ -1,0 +1,211 @@
+"""ctypes binding of libray3d_b200.so (include/ray3d_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or no sm_100 device is
+visible, every compute entry point raises.  Nothing in this package computes the lifting path on
+the CPU or through PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Iterable, Mapping, Optional, Tuple
+
+import numpy as np
+
+from .spec import NetSpec
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libray3d_b200.so")
+_lib = None
+_lock = threading.Lock()
+
+NET_POS, NET_TRJ = 1, 2
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_MISSING_WEIGHT, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
+
+
+class R3DConfig(C.Structure):
+    _fields_ = [("num_joints", C.c_int32), ("in_features", C.c_int32), ("n_widths", C.c_int32),
+                ("widths", C.c_int32 * 8), ("channels", C.c_int32), ("latent", C.c_int32), ("stage", C.c_int32),
+                ("extrinsic_dim", C.c_int32), ("embed_dim", C.c_int32), ("nets", C.c_int32),
+                ("precision", C.c_int32)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "r3d_abi_version": (C.c_int, []),
+    "r3d_last_error": (C.c_char_p, []),
+    "r3d_plan_create": (C.c_int, [C.POINTER(R3DConfig), C.POINTER(C.c_void_p)]),
+    "r3d_plan_set_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "r3d_plan_finalize": (C.c_int, [C.c_void_p]),
+    "r3d_plan_upload": (C.c_int, [C.c_void_p, C.c_int]),
+    "r3d_plan_destroy": (None, [C.c_void_p]),
+    "r3d_plan_packed_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "r3d_plan_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "r3d_plan_weight_bytes": (C.c_int64, [C.c_void_p]),
+    "r3d_plan_workspace_bytes": (C.c_int64, [C.c_void_p]),
+    "r3d_plan_receptive_field": (C.c_int, [C.c_void_p]),
+    "r3d_plan_kernel_launches": (C.c_int, [C.c_void_p]),
+    "r3d_forward_rays": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "r3d_forward_uv": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "r3d_forward_rays_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
+    "r3d_forward_uv_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
+    "r3d_forward_video": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "r3d_ray_encode_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_double] * 6 + [C.c_void_p]),
+    "r3d_normalize_screen_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
+    "r3d_selftest_gemm": (C.c_int, [C.c_int32] * 6 + [C.POINTER(C.c_double)] * 3),
+}
+
+
+class R3DError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ray3d_b200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(_LIB_PATH):
+                raise RuntimeError(
+                    f"{_LIB_PATH} is missing: build it with `python -m ray3d_b200.build` (needs nvcc). "
+                    "ray3d_b200 has no CPU/PyTorch fallback for the lifting path.")
+            handle = C.CDLL(_LIB_PATH)
+            for name, (res, args) in EXPORTS.items():
+                fn = getattr(handle, name)     # AttributeError if the .so does not export it
+                fn.restype = res
+                fn.argtypes = args
+            if handle.r3d_abi_version() != 1:
+                raise RuntimeError("libray3d_b200.so ABI version mismatch; rebuild it")
+            _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise R3DError(rc, lib().r3d_last_error().decode("utf-8", "replace"))
+
+
+def make_config(spec: NetSpec, nets: int, precision: str) -> R3DConfig:
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    cfg = R3DConfig()
+    cfg.num_joints, cfg.in_features = spec.num_joints, spec.in_features
+    cfg.n_widths = len(spec.filter_widths)
+    if cfg.n_widths > 8:
+        raise ValueError("at most 8 filter widths")
+    for i, w in enumerate(spec.filter_widths):
+        cfg.widths[i] = w
+    cfg.channels, cfg.latent, cfg.stage = spec.channels, spec.latent, spec.stage
+    cfg.extrinsic_dim, cfg.embed_dim = spec.extrinsic_dim, spec.embed_dim
+    cfg.nets, cfg.precision = nets, PRECISIONS[precision]
+    return cfg
+
+
+class Plan:
+    """Owns one native r3d_plan.  Host-side construction needs no GPU; upload()/forward do."""
+
+    def __init__(self, spec: NetSpec, nets: int = NET_POS | NET_TRJ, precision: str = "fp32"):
+        self.spec, self.nets, self.precision = spec, nets, precision
+        self._h = C.c_void_p()
+        cfg = make_config(spec, nets, precision)
+        check(lib().r3d_plan_create(C.byref(cfg), C.byref(self._h)))
+        self.device: Optional[int] = None
+
+    def close(self) -> None:
+        if self._h:
+            lib().r3d_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights -----------------------------------------------------------------------------
+    def set_tensor(self, net: int, name: str, arr: np.ndarray) -> None:
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+        check(lib().r3d_plan_set_tensor(self._h, net, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim))
+
+    def load_state(self, net: int, state: Mapping[str, object]) -> None:
+        """state: name -> numpy array or torch tensor (any device); integer buffers are skipped."""
+        for k, v in state.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            if hasattr(v, "detach"):
+                v = v.detach().to("cpu").float().numpy()
+            self.set_tensor(net, k, np.asarray(v))
+
+    def finalize(self) -> None:
+        check(lib().r3d_plan_finalize(self._h))
+
+    def upload(self, device: int = 0) -> None:
+        check(lib().r3d_plan_upload(self._h, int(device)))
+        self.device = int(device)
+
+    def packed_layer(self, net: int, layer: str) -> Tuple[np.ndarray, np.ndarray]:
+        n, k = C.c_int32(), C.c_int32()
+        check(lib().r3d_plan_packed_layer(self._h, net, layer.encode(), C.byref(n), C.byref(k), None, 0, None, 0))
+        w = np.empty((n.value, k.value), np.float32)
+        b = np.empty((n.value,), np.float32)
+        check(lib().r3d_plan_packed_layer(self._h, net, layer.encode(), C.byref(n), C.byref(k),
+                                          w.ctypes.data_as(C.c_void_p), w.size, b.ctypes.data_as(C.c_void_p), b.size))
+        return w, b
+
+    def describe(self) -> dict:
+        import json
+        need = C.c_int64()
+        check(lib().r3d_plan_describe(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib().r3d_plan_describe(self._h, buf, need.value, C.byref(need)))
+        return json.loads(buf.value.decode())
+
+    @property
+    def weight_bytes(self) -> int:
+        return int(lib().r3d_plan_weight_bytes(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(lib().r3d_plan_workspace_bytes(self._h))
+
+    @property
+    def receptive_field(self) -> int:
+        return int(lib().r3d_plan_receptive_field(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().r3d_plan_kernel_launches(self._h))
+
+    # -- forward (raw pointers; torch-facing wrappers live in lifter.py / model.py) ------------------
+    def forward_rays(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> None:
+        check(lib().r3d_forward_rays(self._h, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch, stream))
+
+    def forward_uv(self, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> None:
+        check(lib().r3d_forward_uv(self._h, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch, stream))
+
+    def forward_video(self, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out: int, stream: int) -> None:
+        check(lib().r3d_forward_video(self._h, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out, stream))
+
+    def forward_rays_host(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int) -> None:
+        check(lib().r3d_forward_rays_host(self._h, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch))
+
+    def forward_uv_host(self, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int) -> None:
+        check(lib().r3d_forward_uv_host(self._h, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch))
+
+
+def selftest_gemm(m: int, n: int, k: int, nprob: int = 1, precision: str = "bf16x3", device: int = 0):
+    err, t_tc, t_ff = C.c_double(), C.c_double(), C.c_double()
+    check(lib().r3d_selftest_gemm(m, n, k, nprob, PRECISIONS[precision], device, C.byref(err), C.byref(t_tc), C.byref(t_ff)))
+    return err.value, t_tc.value, t_ff.value

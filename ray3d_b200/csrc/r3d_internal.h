@@ -1,0 +1,116 @@
+// Internal types shared by the host plan builder and the sm_100a kernels.
+// Vocabulary: a "problem" is one independent GEMM of a grouped launch (one joint group's
+// temporal block, or one FC head); a "level" is one stride-w stage of the temporal tree.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "ray3d_b200.h"
+
+namespace r3d {
+
+constexpr int kMaxProb = 6;    // 5 joint groups (pose net) + 1 trajectory net
+constexpr int kMaxDst = 6;     // an epilogue may scatter one tile into up to 6 feature buffers
+constexpr int kKAlign = 64;    // every GEMM K (and every activation row pitch) is a multiple of 64
+
+// Activation matrix in HBM, row-major [rows][ld].
+//   FP32 precision  : p0 = float*
+//   BF16X3 precision: p0 = bf16 "hi" plane, p1 = bf16 "lo" plane (value = hi + lo)
+//   BF16 precision  : p0 = bf16 plane
+struct Mat {
+  void* p0;
+  void* p1;
+  int32_t ld;
+  int32_t _pad;
+};
+
+struct Dst {
+  Mat m;
+  int32_t col;    // first column written inside m
+  int32_t f32;    // 1: p0 is float* regardless of the plan precision (network outputs)
+};
+
+struct GemmProb {
+  Mat a;                 // [M][K] (row pitch a.ld >= K)
+  const void* w0;        // packed weights [n_pad][K] K-major: float (FP32) or bf16 hi
+  const void* w1;        // bf16 lo plane (BF16X3) or null
+  const float* bias;     // [n_pad] BN-folded bias
+  Mat res;               // optional residual, same row index; null p0 => none
+  int32_t res_col;
+  int32_t K;             // multiple of 64
+  int32_t N;             // valid output columns
+  int32_t n_pad;         // rows of the packed weight matrix (multiple of the op's n tile)
+  int32_t ndst;
+  Dst dst[kMaxDst];
+};
+
+struct GemmOpDev {
+  int32_t nprob;
+  int32_t rows_per_seq;  // M = batch * rows_per_seq
+  float slope;           // LeakyReLU slope; 1.0f = linear
+  int32_t n_tile;
+  GemmProb prob[kMaxProb];
+};
+
+// ---- input stage --------------------------------------------------------------------------------
+// tab entry for column kk of a problem's first-layer A matrix:
+//   bits 0..7 source channel (j*Cin+c), 8..9 part (0 x, 1 x-root, 2 x-x[tc]), 10..15 tap k,
+//   16..17 coordinate c (root channel); -1 => zero padding column.
+struct PrologueProb {
+  Mat a0;
+  const int32_t* tab;
+  int32_t k_pad;
+  int32_t _pad;
+};
+
+struct EmbedDev {
+  const float* w1;   // [mid][ext]  BN folded
+  const float* b1;   // [mid]
+  const float* w2;   // [emb][mid]  BN folded
+  const float* b2;   // [emb]
+  int32_t ndst;
+  int32_t _pad;
+  Dst dst[kMaxDst];
+};
+
+struct PrologueDev {
+  int32_t T, J, Cin, JC, tc, w0, L0;
+  int32_t nprob;
+  PrologueProb prob[kMaxProb];
+  Mat inc;               // in_current, [B][roundup(J*Cin,64)]
+  int32_t n_embed, ext_dim, emb_mid, emb_dim;
+  EmbedDev embed[2];
+};
+
+struct AssembleDev {
+  const float* heads[kMaxProb];   // [B][16] fp32 per problem; index 5 = trajectory head
+  int32_t head_ld;
+  int32_t J;
+  int32_t has_pos, has_trj;
+  int16_t slot_prob[32];          // output joint slot -> problem index
+  int16_t slot_joint[32];         // output joint slot -> joint index inside that head
+};
+
+// ---- kernel launchers (defined in the .cu files) ----------------------------------------------
+cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h_desc, int precision, const void* src,
+                            int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
+                            int64_t param_stride, int batch, cudaStream_t s);
+cudaError_t launch_assemble(const AssembleDev* d_desc, const AssembleDev& h_desc, float* pos, float* trj, float* sum,
+                            int batch, cudaStream_t s);
+cudaError_t launch_gemm_ffma(const GemmOpDev* d_op, const GemmOpDev& h_op, int M, cudaStream_t s);
+cudaError_t launch_ray_encode_f64(const double* uv, double* ray, int64_t n, double fx, double fy, double ppx,
+                                  double ppy, double c, double s, cudaStream_t st);
+cudaError_t launch_normalize_screen_f64(const double* xy, double* out, int64_t n, double w, double h, cudaStream_t st);
+cudaError_t prologue_configure(int max_smem_bytes);
+
+// tensor-core path (r3d_gemm_tc.cu)
+struct TcOpHost;   // per-op TMA descriptors etc.
+cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h_op, const void* d_tmaps, int M, int precision,
+                           cudaStream_t s);
+int tc_build_tmaps(const GemmOpDev& h_op, int precision, int64_t cap_rows, void* h_tmaps_out /* kMaxProb*4 maps */);
+cudaError_t tc_configure();
+constexpr int kTmapsPerProb = 4;     // A hi, A lo, W hi, W lo
+constexpr int kTmapBytes = 128;
+
+}  // namespace r3d

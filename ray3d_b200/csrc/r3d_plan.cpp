@@ -1,0 +1,1133 @@
+// Host side of the C ABI: plan construction, BatchNorm folding + weight packing, workspace layout,
+// and the launch sequence of one forward pass.  See include/ray3d_b200.h for the contract and the
+// reference interfaces each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "r3d_internal.h"
+
+using namespace r3d;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(R3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                         \
+  } while (0)
+
+extern "C" R3D_API const char* r3d_last_error(void) { return g_err.c_str(); }
+extern "C" R3D_API int r3d_abi_version(void) { return R3D_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// static network description (mirrors ray3d_b200/spec.py; reference lines cited there)
+// ------------------------------------------------------------------------------------------------
+static const char* kGroupNames[5] = {"Torso", "LArm", "RArm", "LLeg", "RLeg"};
+
+struct GroupTable {
+  std::vector<int> joints[5];
+  std::vector<std::pair<int, int>> slots;   // output slot -> (group, joint in head)
+};
+
+static bool group_table(int J, GroupTable& g) {
+  auto set = [&](int i, std::initializer_list<int> l) { g.joints[i] = l; };
+  struct Seg { int grp, first, n; };
+  std::vector<Seg> order;
+  if (J == 17) {   // lib/model/rie.py:308-315, 426-427
+    set(0, {0, 7, 8, 9, 10}); set(1, {14, 15, 16}); set(2, {11, 12, 13}); set(3, {1, 2, 3}); set(4, {4, 5, 6});
+    order = {{0, 0, 1}, {3, 0, 3}, {4, 0, 3}, {0, 1, 4}, {2, 0, 3}, {1, 0, 3}};
+  } else if (J == 15) {   // rie.py:316-323, 428-429
+    set(0, {0, 1, 14}); set(1, {2, 3, 4}); set(2, {5, 6, 7}); set(3, {8, 9, 10}); set(4, {11, 12, 13});
+    order = {{0, 0, 2}, {3, 0, 3}, {4, 0, 3}, {2, 0, 3}, {1, 0, 3}, {0, 2, 1}};
+  } else if (J == 14) {   // rie.py:324-331, 430-431
+    set(0, {0, 7}); set(1, {8, 9, 10}); set(2, {11, 12, 13}); set(3, {4, 5, 6}); set(4, {1, 2, 3});
+    order = {{0, 0, 1}, {3, 0, 3}, {4, 0, 3}, {2, 0, 3}, {1, 0, 3}, {0, 1, 1}};
+  } else {
+    return false;
+  }
+  g.slots.clear();
+  for (auto& s : order)
+    for (int i = 0; i < s.n; ++i) g.slots.push_back({s.grp, s.first + i});
+  return (int)g.slots.size() == J;
+}
+
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+static constexpr int kFcWidth = 1024;   // rie.py:226,232,245-253,483,494
+static constexpr int kEmbedMid = 32;    // embedding.py:5
+static constexpr double kBnEps = 1e-5;
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct TensorEntry {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool set = false;
+};
+
+struct PackedLayer {
+  int n = 0, k = 0, n_pad = 0, k_pad = 0;
+  std::vector<float> w, b;        // [n_pad][k_pad], [n_pad]  BN folded, fp32
+  size_t off_w0 = 0, off_w1 = 0, off_b = 0;   // offsets in the device weight slab
+  bool plain = false;             // embedder matrices: no padding, fp32 only
+};
+
+struct MatReq {          // one activation matrix in the workspace slab
+  int rows_per_seq;
+  int ld;
+  bool f32;
+  size_t off0 = 0, off1 = 0;
+};
+
+struct OpHost {
+  GemmOpDev dev;                         // pointers filled by bind_workspace()
+  std::string name;
+  // symbolic bindings resolved to pointers once the slabs exist
+  struct Bind { int a = -1, a_ld = 0, res = -1, res_ld = 0, res_col = 0; std::string layer;
+                std::vector<std::pair<int, int>> dst; std::vector<int> dst_f32; };
+  Bind bind[kMaxProb];
+};
+
+struct r3d_plan {
+  r3d_config cfg{};
+  GroupTable groups;
+  int J = 0, Cin = 0, JC = 0, C = 0, L = 0, T = 0, tc = 0, E = 0, ext = 0;
+  bool embed = false, has_pos = false, has_trj = false;
+  std::vector<int> widths, lens;
+  int feat_pos = 0, feat_trj = 0;
+
+  std::map<std::string, TensorEntry> tensors[2];     // expected entries per net (0 pos, 1 trj)
+  std::map<std::string, PackedLayer> layers;         // key "<net>:<module path>"
+  bool finalized = false;
+
+  // temporal-block problems of this plan
+  struct TB { int net; std::string prefix; std::vector<int> joints; int head; int group; };
+  std::vector<TB> tbs;
+
+  // device state
+  int device = -1;
+  bool uploaded = false;
+  char* d_weights = nullptr;
+  size_t weight_bytes = 0;
+  char* d_ws = nullptr;
+  size_t ws_bytes = 0;
+  int cap = 0;                                        // sequences the workspace holds
+  std::vector<MatReq> mats;
+  std::vector<OpHost> ops;
+  PrologueDev pro{};
+  AssembleDev asmb{};
+  std::vector<std::vector<int32_t>> tabs;
+  std::vector<size_t> tab_off;
+  char* d_desc = nullptr;                             // ops + prologue + assemble + tmaps
+  size_t off_ops = 0, off_pro = 0, off_asm = 0, off_tmaps = 0;
+  // symbolic ids used while building
+  int m_inc = -1, m_heads[kMaxProb] = {-1, -1, -1, -1, -1, -1};
+  struct EmbBind { int net; std::vector<std::pair<int, int>> dst; };
+  std::vector<EmbBind> emb_binds;
+  std::vector<int> m_a0;
+  // host-call staging
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  char* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  std::mutex mu;
+};
+
+
+// ---- expected state_dict entries ---------------------------------------------------------------
+static void expect(r3d_plan* p, int net, const std::string& name, std::vector<int64_t> shape) {
+  TensorEntry e;
+  e.shape = std::move(shape);
+  p->tensors[net][name] = std::move(e);
+}
+static void expect_bn(r3d_plan* p, int net, const std::string& pre, int c) {
+  for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) expect(p, net, pre + s, {c});
+}
+static void expect_linear(r3d_plan* p, int net, const std::string& pre, int cin, int cout) {
+  expect(p, net, pre + ".weight", {cout, cin});
+  expect(p, net, pre + ".bias", {cout});
+}
+static void expect_tblock(r3d_plan* p, int net, const std::string& pre, int in_ch) {
+  const int C = p->C;
+  expect_bn(p, net, pre + ".expand_bn", C);
+  expect(p, net, pre + ".shrink.weight", {p->L, C, 1});
+  expect(p, net, pre + ".shrink.bias", {p->L});
+  expect(p, net, pre + ".expand_conv.weight", {C, in_ch, p->widths[0]});
+  for (size_t i = 1; i < p->widths.size(); ++i) {
+    const std::string a = std::to_string(2 * (i - 1)), b = std::to_string(2 * (i - 1) + 1);
+    expect(p, net, pre + ".layers_conv." + a + ".weight", {C, C, p->widths[i]});
+    expect(p, net, pre + ".layers_conv." + b + ".weight", {C, C, 1});
+    expect_bn(p, net, pre + ".layers_bn." + a, C);
+    expect_bn(p, net, pre + ".layers_bn." + b, C);
+  }
+}
+static void expect_fcblock(r3d_plan* p, int net, const std::string& pre, int cin, int cout, int nblocks) {
+  expect_linear(p, net, pre + ".fc_1", cin, kFcWidth);
+  expect_bn(p, net, pre + ".bn_1", kFcWidth);
+  expect_linear(p, net, pre + ".fc_2", kFcWidth, cout);
+  for (int i = 0; i < nblocks; ++i) {
+    const std::string q = pre + ".layers." + std::to_string(i);
+    expect_linear(p, net, q + ".w1", kFcWidth, kFcWidth);
+    expect_bn(p, net, q + ".batch_norm1", kFcWidth);
+    expect_linear(p, net, q + ".w2", kFcWidth, kFcWidth);
+    expect_bn(p, net, q + ".batch_norm2", kFcWidth);
+  }
+}
+static void expect_embed(r3d_plan* p, int net) {
+  expect_linear(p, net, "embedder.w1", p->ext, kEmbedMid);
+  expect_bn(p, net, "embedder.b1", kEmbedMid);
+  expect_linear(p, net, "embedder.w2", kEmbedMid, p->E);
+  expect_bn(p, net, "embedder.b2", p->E);
+}
+
+extern "C" R3D_API int r3d_plan_create(const r3d_config* cfg, r3d_plan** out) {
+  if (!cfg || !out) return fail(R3D_ERR_BAD_ARG, "r3d_plan_create: null argument");
+  *out = nullptr;
+  std::unique_ptr<r3d_plan> p(new r3d_plan);
+  p->cfg = *cfg;
+  if (!group_table(cfg->num_joints, p->groups))
+    return fail(R3D_ERR_UNSUPPORTED, "num_joints=%d: the reference defines joint groups only for 17/15/14 (rie.py:306-357)",
+                cfg->num_joints);
+  if (cfg->in_features != 2 && cfg->in_features != 3)
+    return fail(R3D_ERR_UNSUPPORTED, "in_features=%d: must be 3 (ray) or 2 (rie.py:306,333)", cfg->in_features);
+  if (cfg->n_widths < 1 || cfg->n_widths > R3D_MAX_WIDTHS) return fail(R3D_ERR_BAD_ARG, "n_widths=%d out of range", cfg->n_widths);
+  if (cfg->channels <= 0 || cfg->channels % kKAlign || cfg->latent <= 0 || cfg->latent % kKAlign)
+    return fail(R3D_ERR_UNSUPPORTED, "channels=%d / latent=%d must be positive multiples of %d", cfg->channels, cfg->latent, kKAlign);
+  if (!(cfg->nets & (R3D_NET_POS | R3D_NET_TRJ)) || (cfg->nets & ~3)) return fail(R3D_ERR_BAD_ARG, "nets=%d", cfg->nets);
+  if (cfg->precision < R3D_PREC_FP32 || cfg->precision > R3D_PREC_BF16) return fail(R3D_ERR_BAD_ARG, "precision=%d", cfg->precision);
+  p->J = cfg->num_joints; p->Cin = cfg->in_features; p->JC = p->J * p->Cin; p->C = cfg->channels; p->L = cfg->latent;
+  p->T = 1;
+  for (int i = 0; i < cfg->n_widths; ++i) {
+    const int w = cfg->widths[i];
+    if (w < 1 || w % 2 == 0 || w > 63) return fail(R3D_ERR_UNSUPPORTED, "filter width %d must be odd and in 1..63", w);
+    p->widths.push_back(w);
+    p->T *= w;
+  }
+  int t = p->T;
+  for (int w : p->widths) { t /= w; p->lens.push_back(t); }
+  p->tc = p->T / p->Cin;                                       // rie.py:290,304
+  p->embed = cfg->extrinsic_dim > 0 && cfg->embed_dim > 0;     // rie.py:235
+  p->ext = p->embed ? cfg->extrinsic_dim : 0;
+  p->E = p->embed ? cfg->embed_dim : 0;
+  if (p->ext > 8) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim=%d > 8", p->ext);
+  p->has_pos = cfg->nets & R3D_NET_POS;
+  p->has_trj = cfg->nets & R3D_NET_TRJ;
+  p->feat_pos = p->L * (cfg->stage == 1 ? 2 : 3) + p->E;     // rie.py:241-242
+  p->feat_trj = p->L * 2 + p->E;                              // rie.py:491-492
+  if ((size_t)p->T * p->JC * 4 > 200 * 1024) return fail(R3D_ERR_UNSUPPORTED, "receptive field %d too large for the input stage", p->T);
+
+  if (p->has_pos) {
+    for (int g = 0; g < 5; ++g) {
+      r3d_plan::TB tb{0, std::string("LocalLayer_") + kGroupNames[g], p->groups.joints[g], g, g};
+      expect_tblock(p.get(), 0, tb.prefix, 3 * (int)tb.joints.size() * p->Cin);
+      p->tbs.push_back(tb);
+    }
+    expect_fcblock(p.get(), 0, "GlobalInfo", p->JC, p->L, 2);
+    if (cfg->stage != 1)
+      for (int i = 0; i < 5; ++i) expect_fcblock(p.get(), 0, "FuseBlocks." + std::to_string(i), 4 * p->L, p->L, 1);
+    if (p->embed) expect_embed(p.get(), 0);
+    for (int g = 0; g < 5; ++g)
+      expect_fcblock(p.get(), 0, std::string("Integration_") + kGroupNames[g], p->feat_pos, 3 * (int)p->groups.joints[g].size(), 1);
+  }
+  if (p->has_trj) {
+    std::vector<int> all;
+    for (int j = 0; j < p->J; ++j) all.push_back(j);
+    r3d_plan::TB tb{1, "LocalLayer", all, kMaxProb - 1, -1};
+    expect_tblock(p.get(), 1, tb.prefix, 3 * p->JC);
+    p->tbs.push_back(tb);
+    expect_fcblock(p.get(), 1, "GlobalInfo", p->JC, p->L, 2);
+    if (p->embed) expect_embed(p.get(), 1);
+    expect_fcblock(p.get(), 1, "Integration", p->feat_trj, 3, 1);
+  }
+  *out = p.release();
+  return R3D_OK;
+}
+
+extern "C" R3D_API int r3d_plan_set_tensor(r3d_plan* p, int net, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!p || !name || !data || (ndim > 0 && !shape)) return fail(R3D_ERR_BAD_ARG, "r3d_plan_set_tensor: null argument");
+  if (net != R3D_NET_POS && net != R3D_NET_TRJ) return fail(R3D_ERR_BAD_ARG, "net must be R3D_NET_POS or R3D_NET_TRJ");
+  if (!(p->cfg.nets & net)) return fail(R3D_ERR_BAD_ARG, "plan was not created for net %d", net);
+  std::string key(name);
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);   // nn.DataParallel checkpoints
+  if (key.size() > 20 && key.compare(key.size() - 20, 20, ".num_batches_tracked") == 0) return R3D_OK;
+  auto& tab = p->tensors[net == R3D_NET_POS ? 0 : 1];
+  auto it = tab.find(key);
+  if (it == tab.end()) return fail(R3D_ERR_BAD_ARG, "unknown state_dict key '%s' for this configuration", key.c_str());
+  TensorEntry& e = it->second;
+  bool same = (int)e.shape.size() == ndim;
+  int64_t n = 1;
+  for (int i = 0; same && i < ndim; ++i) { same = e.shape[i] == shape[i]; n *= shape[i]; }
+  if (!same) {
+    std::string want, got;
+    for (auto d : e.shape) want += std::to_string(d) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    return fail(R3D_ERR_BAD_ARG, "shape mismatch for '%s': expected (%s) got (%s)", key.c_str(), want.c_str(), got.c_str());
+  }
+  e.data.assign(data, data + n);
+  e.set = true;
+  p->finalized = false;
+  return R3D_OK;
+}
+
+// ---- folding + packing -----------------------------------------------------------------------------
+namespace {
+struct Folder {
+  r3d_plan* p;
+  int net;
+  const float* get(const std::string& k) const { return p->tensors[net].at(k).data.data(); }
+  // scale/shift of an eval-mode BatchNorm1d:  y = x*scale + shift   (running stats, eps 1e-5)
+  void bn(const std::string& pre, int c, std::vector<double>& scale, std::vector<double>& shift) const {
+    const float *g = get(pre + ".weight"), *b = get(pre + ".bias"), *m = get(pre + ".running_mean"), *v = get(pre + ".running_var");
+    scale.resize(c); shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+      scale[i] = (double)g[i] / std::sqrt((double)v[i] + kBnEps);
+      shift[i] = (double)b[i] - (double)m[i] * scale[i];
+    }
+  }
+  // conv weight (n, cin, w) [+ BN]  ->  [n_pad][k_pad] with column = tap*cin + c
+  PackedLayer conv(const std::string& wkey, int n, int cin, int w, const std::string& bnpre, const std::string& biaskey) const {
+    PackedLayer pl;
+    pl.n = n; pl.k = cin * w; pl.n_pad = round_up(n, 16); pl.k_pad = round_up(pl.k, kKAlign);
+    pl.w.assign((size_t)pl.n_pad * pl.k_pad, 0.f); pl.b.assign(pl.n_pad, 0.f);
+    std::vector<double> sc(n, 1.0), sh(n, 0.0);
+    if (!bnpre.empty()) bn(bnpre, n, sc, sh);
+    const float* W = get(wkey);
+    const float* B = biaskey.empty() ? nullptr : get(biaskey);
+    for (int o = 0; o < n; ++o) {
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < w; ++t)
+          pl.w[(size_t)o * pl.k_pad + t * cin + c] = (float)((double)W[((size_t)o * cin + c) * w + t] * sc[o]);
+      pl.b[o] = (float)((B ? (double)B[o] * sc[o] : 0.0) + sh[o]);
+    }
+    return pl;
+  }
+  PackedLayer linear(const std::string& pre, int n, int k, const std::string& bnpre) const {
+    return conv(pre + ".weight", n, k, 1, bnpre, pre + ".bias");
+  }
+  PackedLayer plain(const std::string& pre, int n, int k, const std::string& bnpre) const {
+    PackedLayer pl = conv(pre + ".weight", n, k, 1, bnpre, pre + ".bias");
+    PackedLayer q;
+    q.n = q.n_pad = n; q.k = q.k_pad = k; q.plain = true;
+    q.w.resize((size_t)n * k); q.b.assign(pl.b.begin(), pl.b.begin() + n);
+    for (int o = 0; o < n; ++o)
+      for (int i = 0; i < k; ++i) q.w[(size_t)o * k + i] = pl.w[(size_t)o * pl.k_pad + i];
+    return q;
+  }
+};
+}  // namespace
+
+static void pack_tblock(r3d_plan* p, int net, const std::string& pre, int in_ch) {
+  Folder f{p, net};
+  const std::string key = std::to_string(net) + ":" + pre;
+  const int C = p->C;
+  p->layers[key + ".expand_conv"] = f.conv(pre + ".expand_conv.weight", C, in_ch, p->widths[0], pre + ".expand_bn", "");
+  for (size_t i = 1; i < p->widths.size(); ++i) {
+    const std::string a = std::to_string(2 * (i - 1)), b = std::to_string(2 * (i - 1) + 1);
+    p->layers[key + ".layers_conv." + a] = f.conv(pre + ".layers_conv." + a + ".weight", C, C, p->widths[i], pre + ".layers_bn." + a, "");
+    p->layers[key + ".layers_conv." + b] = f.conv(pre + ".layers_conv." + b + ".weight", C, C, 1, pre + ".layers_bn." + b, "");
+  }
+  p->layers[key + ".shrink"] = f.conv(pre + ".shrink.weight", p->L, C, 1, "", pre + ".shrink.bias");
+}
+static void pack_fcblock(r3d_plan* p, int net, const std::string& pre, int cin, int cout, int nblocks) {
+  Folder f{p, net};
+  const std::string key = std::to_string(net) + ":" + pre;
+  p->layers[key + ".fc_1"] = f.linear(pre + ".fc_1", kFcWidth, cin, pre + ".bn_1");
+  for (int i = 0; i < nblocks; ++i) {
+    const std::string q = ".layers." + std::to_string(i);
+    p->layers[key + q + ".w1"] = f.linear(pre + q + ".w1", kFcWidth, kFcWidth, pre + q + ".batch_norm1");
+    p->layers[key + q + ".w2"] = f.linear(pre + q + ".w2", kFcWidth, kFcWidth, pre + q + ".batch_norm2");
+  }
+  p->layers[key + ".fc_2"] = f.linear(pre + ".fc_2", cout, kFcWidth, "");
+}
+static void pack_embed(r3d_plan* p, int net) {
+  Folder f{p, net};
+  const std::string key = std::to_string(net) + ":embedder";
+  p->layers[key + ".w1"] = f.plain("embedder.w1", kEmbedMid, p->ext, "embedder.b1");
+  p->layers[key + ".w2"] = f.plain("embedder.w2", p->E, kEmbedMid, "embedder.b2");
+}
+
+// ---- graph construction --------------------------------------------------------------------------
+static int add_mat(r3d_plan* p, int rows_per_seq, int ld, bool f32 = false) {
+  MatReq m;
+  m.rows_per_seq = rows_per_seq; m.ld = ld; m.f32 = f32;
+  p->mats.push_back(m);
+  return (int)p->mats.size() - 1;
+}
+
+static OpHost& add_op(r3d_plan* p, const std::string& name, int nprob, int rows_per_seq, float slope) {
+  p->ops.emplace_back();
+  OpHost& op = p->ops.back();
+  memset(&op.dev, 0, sizeof(op.dev));
+  op.name = name;
+  op.dev.nprob = nprob;
+  op.dev.rows_per_seq = rows_per_seq;
+  op.dev.slope = slope;
+  return op;
+}
+
+static void build_graph(r3d_plan* p) {
+  p->mats.clear(); p->ops.clear(); p->tabs.clear(); p->emb_binds.clear(); p->m_a0.clear();
+  const int C = p->C, L = p->L, nl = (int)p->widths.size(), ntb = (int)p->tbs.size();
+  const float act = 0.2f;   // nn.LeakyReLU(0.2), rie.py:27,113,156
+
+  // --- input stage tables + first-layer A matrices
+  for (int q = 0; q < ntb; ++q) {
+    const auto& tb = p->tbs[q];
+    const int nj = (int)tb.joints.size(), cg = 3 * nj * p->Cin, k = cg * p->widths[0], kp = round_up(k, kKAlign);
+    std::vector<int32_t> tab(kp, -1);
+    for (int kk = 0; kk < k; ++kk) {
+      const int tap = kk / cg, ch = kk % cg, part = ch / (nj * p->Cin), r = ch % (nj * p->Cin), jj = r / p->Cin, c = r % p->Cin;
+      tab[kk] = (tb.joints[jj] * p->Cin + c) | (part << 8) | (tap << 10) | (c << 16);
+    }
+    p->tabs.push_back(tab);
+    p->m_a0.push_back(add_mat(p, p->lens[0], kp));
+  }
+  p->m_inc = add_mat(p, 1, round_up(p->JC, kKAlign));
+
+  // --- feature / head buffers
+  int m_feat[kMaxProb] = {-1, -1, -1, -1, -1, -1}, m_fuse[5] = {-1, -1, -1, -1, -1};
+  for (int q = 0; q < ntb; ++q) {
+    const auto& tb = p->tbs[q];
+    m_feat[q] = add_mat(p, 1, round_up(tb.net == 0 ? p->feat_pos : p->feat_trj, kKAlign));
+    p->m_heads[tb.head] = add_mat(p, 1, 16, true);
+  }
+  const bool fuse = p->has_pos && p->cfg.stage != 1;
+  if (fuse) for (int i = 0; i < 5; ++i) m_fuse[i] = add_mat(p, 1, 4 * L);
+
+  // --- temporal tree: ping-pong X buffers, one Y scratch
+  std::vector<int> xa(ntb), xb(ntb), yb(ntb);
+  for (int q = 0; q < ntb; ++q) {
+    xa[q] = add_mat(p, p->lens[0], C);
+    xb[q] = nl > 1 ? add_mat(p, p->lens[1], C) : -1;
+    yb[q] = nl > 1 ? add_mat(p, p->lens[1], C) : -1;
+  }
+  auto lkey = [&](int q, const std::string& s) { return std::to_string(p->tbs[q].net) + ":" + p->tbs[q].prefix + s; };
+  {
+    OpHost& op = add_op(p, "expand_conv", ntb, p->lens[0], act);                       // rie.py:86
+    for (int q = 0; q < ntb; ++q) {
+      auto& b = op.bind[q];
+      b.a = p->m_a0[q]; b.a_ld = p->mats[p->m_a0[q]].ld; b.layer = lkey(q, ".expand_conv");
+      b.dst = {{xa[q], 0}};
+    }
+  }
+  std::vector<int> cur = xa, nxt = xb;
+  for (int i = 1; i < nl; ++i) {
+    const int w = p->widths[i];
+    const std::string a = std::to_string(2 * (i - 1)), bb = std::to_string(2 * (i - 1) + 1);
+    OpHost& o1 = add_op(p, "layers_conv." + a, ntb, p->lens[i], act);                  // rie.py:96
+    for (int q = 0; q < ntb; ++q) {
+      auto& b = o1.bind[q];
+      b.a = cur[q]; b.a_ld = w * C; b.layer = lkey(q, ".layers_conv." + a); b.dst = {{yb[q], 0}};
+    }
+    OpHost& o2 = add_op(p, "layers_conv." + bb, ntb, p->lens[i], act);                 // rie.py:94,97
+    for (int q = 0; q < ntb; ++q) {
+      auto& b = o2.bind[q];
+      b.a = yb[q]; b.a_ld = C; b.layer = lkey(q, ".layers_conv." + bb);
+      b.res = cur[q]; b.res_ld = w * C; b.res_col = (w / 2) * C;                          // x[:, :, w//2::w]
+      b.dst = {{nxt[q], 0}};
+    }
+    std::swap(cur, nxt);
+  }
+  {
+    OpHost& op = add_op(p, "shrink", ntb, 1, 1.0f);                                     // rie.py:99
+    for (int q = 0; q < ntb; ++q) {
+      const auto& tb = p->tbs[q];
+      auto& b = op.bind[q];
+      b.a = cur[q]; b.a_ld = C; b.layer = lkey(q, ".shrink");
+      b.dst = {{m_feat[q], 0}};
+      if (tb.net == 0 && fuse)                                                            // rie.py:392-394
+        for (int i = 0; i < 5; ++i)
+          if (i != tb.group) b.dst.push_back({m_fuse[i], (tb.group < i ? tb.group : tb.group - 1) * L});
+    }
+  }
+
+  // --- FC chains.  Hidden buffers: 3 x [B][1024] per problem slot, shared by successive chains.
+  int hb[3][kMaxProb];
+  for (int j = 0; j < 3; ++j)
+    for (int q = 0; q < kMaxProb; ++q) hb[j][q] = add_mat(p, 1, kFcWidth);
+  struct Chain { std::string key; int a; int a_ld; int nblocks; std::vector<std::pair<int, int>> dst; bool f32; };
+  auto fc_chain = [&](const std::string& name, std::vector<Chain>& ch) {
+    const int n = (int)ch.size();
+    if (!n) return;
+    {
+      OpHost& op = add_op(p, name + ".fc_1", n, 1, act);                                // rie.py:161-163
+      for (int q = 0; q < n; ++q) { auto& b = op.bind[q]; b.a = ch[q].a; b.a_ld = ch[q].a_ld; b.layer = ch[q].key + ".fc_1"; b.dst = {{hb[0][q], 0}}; }
+    }
+    int h = 0;
+    const int nb = ch[0].nblocks;
+    for (int i = 0; i < nb; ++i) {                                                      // rie.py:122-135
+      const std::string ls = ".layers." + std::to_string(i);
+      const int y = (h + 1) % 3, hn = (h + 2) % 3;
+      OpHost& o1 = add_op(p, name + ls + ".w1", n, 1, act);
+      for (int q = 0; q < n; ++q) { auto& b = o1.bind[q]; b.a = hb[h][q]; b.a_ld = kFcWidth; b.layer = ch[q].key + ls + ".w1"; b.dst = {{hb[y][q], 0}}; }
+      OpHost& o2 = add_op(p, name + ls + ".w2", n, 1, act);
+      for (int q = 0; q < n; ++q) {
+        auto& b = o2.bind[q];
+        b.a = hb[y][q]; b.a_ld = kFcWidth; b.layer = ch[q].key + ls + ".w2";
+        b.res = hb[h][q]; b.res_ld = kFcWidth; b.res_col = 0; b.dst = {{hb[hn][q], 0}};
+      }
+      h = hn;
+    }
+    OpHost& op = add_op(p, name + ".fc_2", n, 1, 1.0f);                                 // rie.py:167
+    for (int q = 0; q < n; ++q) {
+      auto& b = op.bind[q];
+      b.a = hb[h][q]; b.a_ld = kFcWidth; b.layer = ch[q].key + ".fc_2"; b.dst = ch[q].dst;
+      b.dst_f32.assign(ch[q].dst.size(), ch[q].f32 ? 1 : 0);
+    }
+  };
+
+  const int inc_ld = p->mats[p->m_inc].ld;
+  const int gcol_pos = (p->cfg.stage == 1 ? 1 : 2) * L;
+  {
+    std::vector<Chain> ch;                                                               // rie.py:362, :543
+    if (p->has_pos) {
+      Chain c{"0:GlobalInfo", p->m_inc, inc_ld, 2, {}, false};
+      for (int q = 0; q < ntb; ++q) if (p->tbs[q].net == 0) c.dst.push_back({m_feat[q], gcol_pos});
+      ch.push_back(c);
+    }
+    if (p->has_trj) {
+      Chain c{"1:GlobalInfo", p->m_inc, inc_ld, 2, {}, false};
+      for (int q = 0; q < ntb; ++q) if (p->tbs[q].net == 1) c.dst.push_back({m_feat[q], L});
+      ch.push_back(c);
+    }
+    fc_chain("GlobalInfo", ch);
+  }
+  if (fuse) {                                                                            // rie.py:388-394
+    std::vector<Chain> ch;
+    for (int i = 0; i < 5; ++i) ch.push_back({"0:FuseBlocks." + std::to_string(i), m_fuse[i], 4 * L, 1, {{m_feat[i], L}}, false});
+    fc_chain("FuseBlocks", ch);
+  }
+  {
+    std::vector<Chain> ch;                                                               // rie.py:410-414, :555
+    for (int q = 0; q < ntb; ++q) {
+      const auto& tb = p->tbs[q];
+      const std::string key = tb.net == 0 ? std::string("0:Integration_") + kGroupNames[tb.group] : std::string("1:Integration");
+      ch.push_back({key, m_feat[q], p->mats[m_feat[q]].ld, 1, {{p->m_heads[tb.head], 0}}, true});
+    }
+    fc_chain("Integration", ch);
+  }
+
+  // --- embedder destinations (rie.py:375-380, 395-401, :549-551)
+  if (p->embed) {
+    if (p->has_pos) {
+      r3d_plan::EmbBind e{0, {}};
+      for (int q = 0; q < ntb; ++q) if (p->tbs[q].net == 0) e.dst.push_back({m_feat[q], gcol_pos + L});
+      p->emb_binds.push_back(e);
+    }
+    if (p->has_trj) {
+      r3d_plan::EmbBind e{1, {}};
+      for (int q = 0; q < ntb; ++q) if (p->tbs[q].net == 1) e.dst.push_back({m_feat[q], 2 * L});
+      p->emb_binds.push_back(e);
+    }
+  }
+}
+
+static int pick_n_tile(int n_pad) {
+  for (int t : {256, 128, 64, 32, 16})
+    if (n_pad % t == 0) return t;
+  return 16;
+}
+
+extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  for (int net = 0; net < 2; ++net)
+    for (auto& kv : p->tensors[net])
+      if (!kv.second.set)
+        return fail(R3D_ERR_MISSING_WEIGHT, "state_dict entry '%s' (%s net) was never supplied", kv.first.c_str(), net ? "trj" : "pos");
+  p->layers.clear();
+  if (p->has_pos) {
+    for (int g = 0; g < 5; ++g)
+      pack_tblock(p, 0, std::string("LocalLayer_") + kGroupNames[g], 3 * (int)p->groups.joints[g].size() * p->Cin);
+    pack_fcblock(p, 0, "GlobalInfo", p->JC, p->L, 2);
+    if (p->cfg.stage != 1)
+      for (int i = 0; i < 5; ++i) pack_fcblock(p, 0, "FuseBlocks." + std::to_string(i), 4 * p->L, p->L, 1);
+    if (p->embed) pack_embed(p, 0);
+    for (int g = 0; g < 5; ++g)
+      pack_fcblock(p, 0, std::string("Integration_") + kGroupNames[g], p->feat_pos, 3 * (int)p->groups.joints[g].size(), 1);
+  }
+  if (p->has_trj) {
+    pack_tblock(p, 1, "LocalLayer", 3 * p->JC);
+    pack_fcblock(p, 1, "GlobalInfo", p->JC, p->L, 2);
+    if (p->embed) pack_embed(p, 1);
+    pack_fcblock(p, 1, "Integration", p->feat_trj, 3, 1);
+  }
+  build_graph(p);
+  // weight slab layout
+  const int prec = p->cfg.precision;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  for (auto& kv : p->layers) {
+    PackedLayer& l = kv.second;
+    const size_t ne = l.w.size();
+    if (l.plain || prec == R3D_PREC_FP32) { l.off_w0 = take(ne * 4); l.off_w1 = 0; }
+    else { l.off_w0 = take(ne * 2); l.off_w1 = prec == R3D_PREC_BF16X3 ? take(ne * 2) : 0; }
+    l.off_b = take(l.b.size() * 4);
+  }
+  p->tab_off.clear();
+  for (auto& t : p->tabs) p->tab_off.push_back(take(t.size() * 4));
+  p->weight_bytes = off;
+  p->finalized = true;
+  p->uploaded = false;
+  return R3D_OK;
+}
+
+extern "C" R3D_API int r3d_plan_packed_layer(const r3d_plan* p, int net, const char* layer, int32_t* n_pad, int32_t* k_pad,
+                                     float* w_out, int64_t cap, float* b_out, int64_t cap_b) {
+  if (!p || !layer) return fail(R3D_ERR_BAD_ARG, "null argument");
+  if (!p->finalized) return fail(R3D_ERR_STATE, "plan not finalized");
+  const std::string key = std::to_string(net == R3D_NET_POS ? 0 : 1) + ":" + layer;
+  auto it = p->layers.find(key);
+  if (it == p->layers.end()) return fail(R3D_ERR_BAD_ARG, "no packed layer '%s'", key.c_str());
+  const PackedLayer& l = it->second;
+  if (n_pad) *n_pad = l.n_pad;
+  if (k_pad) *k_pad = l.k_pad;
+  if (w_out) memcpy(w_out, l.w.data(), sizeof(float) * std::min<int64_t>(cap, (int64_t)l.w.size()));
+  if (b_out) memcpy(b_out, l.b.data(), sizeof(float) * std::min<int64_t>(cap_b, (int64_t)l.b.size()));
+  return R3D_OK;
+}
+
+// JSON description of the launch graph (buffers, ops, bindings, input-stage tables).  Lets the CPU test-suite
+// replay the exact wiring with numpy against the oracle without a GPU.
+extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t cap, int64_t* needed) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  if (!p->finalized) return fail(R3D_ERR_STATE, "plan not finalized");
+  std::string j = "{";
+  auto kv = [&](const char* k, long v) { j += std::string("\"") + k + "\":" + std::to_string(v) + ","; };
+  kv("T", p->T); kv("J", p->J); kv("Cin", p->Cin); kv("tc", p->tc); kv("w0", p->widths[0]); kv("L0", p->lens[0]);
+  kv("inc", p->m_inc); kv("ext", p->ext); kv("emb_mid", p->embed ? kEmbedMid : 0); kv("emb_dim", p->E);
+  kv("has_pos", p->has_pos); kv("has_trj", p->has_trj);
+  j += "\"mats\":[";
+  for (size_t i = 0; i < p->mats.size(); ++i)
+    j += std::string(i ? "," : "") + "[" + std::to_string(p->mats[i].rows_per_seq) + "," + std::to_string(p->mats[i].ld) + "," +
+         std::to_string((int)p->mats[i].f32) + "]";
+  j += "],\"a0\":[";
+  for (size_t i = 0; i < p->m_a0.size(); ++i) j += std::string(i ? "," : "") + std::to_string(p->m_a0[i]);
+  j += "],\"tabs\":[";
+  for (size_t i = 0; i < p->tabs.size(); ++i) {
+    j += std::string(i ? "," : "") + "[";
+    for (size_t k = 0; k < p->tabs[i].size(); ++k) j += std::string(k ? "," : "") + std::to_string(p->tabs[i][k]);
+    j += "]";
+  }
+  j += "],\"heads\":[";
+  for (int q = 0; q < kMaxProb; ++q) j += std::string(q ? "," : "") + std::to_string(p->m_heads[q]);
+  j += "],\"slots\":[";
+  for (int s2 = 0; s2 < p->J; ++s2)
+    j += std::string(s2 ? "," : "") + "[" + std::to_string(p->groups.slots[s2].first) + "," + std::to_string(p->groups.slots[s2].second) + "]";
+  j += "],\"embed\":[";
+  for (size_t e = 0; e < p->emb_binds.size(); ++e) {
+    j += std::string(e ? "," : "") + "{\"net\":" + std::to_string(p->emb_binds[e].net) + ",\"dst\":[";
+    for (size_t d = 0; d < p->emb_binds[e].dst.size(); ++d)
+      j += std::string(d ? "," : "") + "[" + std::to_string(p->emb_binds[e].dst[d].first) + "," + std::to_string(p->emb_binds[e].dst[d].second) + "]";
+    j += "]}";
+  }
+  j += "],\"ops\":[";
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const OpHost& op = p->ops[i];
+    char sl[32];
+    snprintf(sl, sizeof(sl), "%.9g", op.dev.slope);
+    j += std::string(i ? "," : "") + "{\"name\":\"" + op.name + "\",\"rows_per_seq\":" + std::to_string(op.dev.rows_per_seq) +
+         ",\"slope\":" + sl + ",\"prob\":[";
+    for (int q = 0; q < op.dev.nprob; ++q) {
+      const auto& b = op.bind[q];
+      j += std::string(q ? "," : "") + "{\"a\":" + std::to_string(b.a) + ",\"a_ld\":" + std::to_string(b.a_ld) + ",\"layer\":\"" + b.layer +
+           "\",\"res\":" + std::to_string(b.res) + ",\"res_ld\":" + std::to_string(b.res_ld) + ",\"res_col\":" + std::to_string(b.res_col) +
+           ",\"dst\":[";
+      for (size_t d = 0; d < b.dst.size(); ++d)
+        j += std::string(d ? "," : "") + "[" + std::to_string(b.dst[d].first) + "," + std::to_string(b.dst[d].second) + "]";
+      j += "]}";
+    }
+    j += "]}";
+  }
+  j += "]}";
+  if (needed) *needed = (int64_t)j.size() + 1;
+  if (out && cap > 0) {
+    const size_t n = std::min<size_t>((size_t)cap - 1, j.size());
+    memcpy(out, j.data(), n);
+    out[n] = 0;
+  }
+  return R3D_OK;
+}
+
+extern "C" R3D_API int64_t r3d_plan_weight_bytes(const r3d_plan* p) { return p ? (int64_t)p->weight_bytes : 0; }
+extern "C" R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* p) { return p ? (int64_t)p->ws_bytes : 0; }
+extern "C" R3D_API int r3d_plan_receptive_field(const r3d_plan* p) { return p ? p->T : 0; }
+extern "C" R3D_API int r3d_plan_kernel_launches(const r3d_plan* p) { return p ? (int)p->ops.size() + 2 : 0; }
+
+// ---- device upload -------------------------------------------------------------------------------
+static uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn (finite inputs)
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+static void free_device(r3d_plan* p) {
+  if (p->device < 0) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);
+  if (p->d_weights) cudaFree(p->d_weights);
+  if (p->d_ws) cudaFree(p->d_ws);
+  if (p->d_desc) cudaFree(p->d_desc);
+  if (p->d_stage) cudaFree(p->d_stage);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    p->ev_in[i] = p->ev_done[i] = nullptr;
+  }
+  if (p->s_copy) cudaStreamDestroy(p->s_copy);
+  if (p->s_comp) cudaStreamDestroy(p->s_comp);
+  p->d_weights = p->d_ws = p->d_desc = p->d_stage = nullptr;
+  p->s_copy = p->s_comp = nullptr;
+  p->ws_bytes = p->stage_bytes = 0;
+  p->cap = 0;
+  p->uploaded = false;
+  cudaSetDevice(prev);
+}
+
+extern "C" R3D_API void r3d_plan_destroy(r3d_plan* p) {
+  if (!p) return;
+  free_device(p);
+  delete p;
+}
+
+extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  if (!p->finalized) return fail(R3D_ERR_STATE, "r3d_plan_upload before r3d_plan_finalize");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(R3D_ERR_NO_DEVICE, "no CUDA device visible: ray3d_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(R3D_ERR_BAD_ARG, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(R3D_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  std::lock_guard<std::mutex> lk(p->mu);
+  free_device(p);
+  p->device = device;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(&p->d_weights, p->weight_bytes));
+  std::vector<char> slab(p->weight_bytes, 0);
+  const int prec = p->cfg.precision;
+  for (auto& kv : p->layers) {
+    PackedLayer& l = kv.second;
+    if (l.plain || prec == R3D_PREC_FP32) {
+      memcpy(slab.data() + l.off_w0, l.w.data(), l.w.size() * 4);
+    } else {
+      uint16_t* hi = reinterpret_cast<uint16_t*>(slab.data() + l.off_w0);
+      uint16_t* lo = prec == R3D_PREC_BF16X3 ? reinterpret_cast<uint16_t*>(slab.data() + l.off_w1) : nullptr;
+      for (size_t i = 0; i < l.w.size(); ++i) {
+        hi[i] = f2bf(l.w[i]);
+        if (lo) lo[i] = f2bf(l.w[i] - bf2f(hi[i]));
+      }
+    }
+    memcpy(slab.data() + l.off_b, l.b.data(), l.b.size() * 4);
+  }
+  for (size_t i = 0; i < p->tabs.size(); ++i) memcpy(slab.data() + p->tab_off[i], p->tabs[i].data(), p->tabs[i].size() * 4);
+  CUDA_TRY(cudaMemcpy(p->d_weights, slab.data(), p->weight_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(prologue_configure(200 * 1024 + 1024));
+  if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+  }
+  p->uploaded = true;
+  return R3D_OK;
+}
+
+// (re)allocate the activation workspace for `cap` sequences and resolve every symbolic binding
+static int bind_workspace(r3d_plan* p, int cap) {
+  const int prec = p->cfg.precision;
+  if (p->d_ws) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(p->d_ws)); p->d_ws = nullptr; }
+  if (p->d_desc) { CUDA_TRY(cudaFree(p->d_desc)); p->d_desc = nullptr; }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  for (auto& m : p->mats) {
+    const size_t ne = (size_t)cap * m.rows_per_seq * m.ld;
+    if (m.f32 || prec == R3D_PREC_FP32) { m.off0 = take(ne * 4); m.off1 = 0; }
+    else { m.off0 = take(ne * 2); m.off1 = prec == R3D_PREC_BF16X3 ? take(ne * 2) : 0; }
+  }
+  p->ws_bytes = off;
+  CUDA_TRY(cudaMalloc(&p->d_ws, p->ws_bytes));
+  CUDA_TRY(cudaMemset(p->d_ws, 0, p->ws_bytes));
+  p->cap = cap;
+  auto mat = [&](int id, int ld) {
+    Mat m{};
+    if (id < 0) return m;
+    const MatReq& r = p->mats[id];
+    m.p0 = p->d_ws + r.off0;
+    m.p1 = (r.f32 || prec != R3D_PREC_BF16X3) ? nullptr : p->d_ws + r.off1;
+    m.ld = ld > 0 ? ld : r.ld;
+    return m;
+  };
+  auto dsts = [&](const std::vector<std::pair<int, int>>& v, const std::vector<int>& f32, Dst* out) {
+    for (size_t i = 0; i < v.size(); ++i) {
+      out[i].m = mat(v[i].first, 0);
+      out[i].col = v[i].second;
+      out[i].f32 = (i < f32.size() && f32[i]) || p->mats[v[i].first].f32;
+    }
+    return (int)v.size();
+  };
+  for (auto& op : p->ops) {
+    int ntile = 256;
+    for (int q = 0; q < op.dev.nprob; ++q) {
+      const auto& b = op.bind[q];
+      const PackedLayer& l = p->layers.at(b.layer);
+      GemmProb& g = op.dev.prob[q];
+      g.a = mat(b.a, b.a_ld);
+      g.w0 = p->d_weights + l.off_w0;
+      g.w1 = (prec == R3D_PREC_BF16X3) ? p->d_weights + l.off_w1 : nullptr;
+      g.bias = reinterpret_cast<const float*>(p->d_weights + l.off_b);
+      g.res = mat(b.res, b.res_ld);
+      g.res_col = b.res_col;
+      g.K = l.k_pad; g.N = l.n; g.n_pad = l.n_pad;
+      g.ndst = dsts(b.dst, b.dst_f32, g.dst);
+      ntile = std::min(ntile, pick_n_tile(l.n_pad));
+    }
+    op.dev.n_tile = ntile;
+  }
+  // prologue
+  PrologueDev& pd = p->pro;
+  memset(&pd, 0, sizeof(pd));
+  pd.T = p->T; pd.J = p->J; pd.Cin = p->Cin; pd.JC = p->JC; pd.tc = p->tc; pd.w0 = p->widths[0]; pd.L0 = p->lens[0];
+  pd.nprob = (int)p->tbs.size();
+  for (int q = 0; q < pd.nprob; ++q) {
+    pd.prob[q].a0 = mat(p->m_a0[q], 0);
+    pd.prob[q].tab = reinterpret_cast<const int32_t*>(p->d_weights + p->tab_off[q]);
+    pd.prob[q].k_pad = p->mats[p->m_a0[q]].ld;
+  }
+  pd.inc = mat(p->m_inc, 0);
+  pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;
+  for (int e = 0; e < pd.n_embed; ++e) {
+    const std::string key = std::to_string(p->emb_binds[e].net) + ":embedder";
+    const PackedLayer &l1 = p->layers.at(key + ".w1"), &l2 = p->layers.at(key + ".w2");
+    pd.embed[e].w1 = reinterpret_cast<const float*>(p->d_weights + l1.off_w0);
+    pd.embed[e].b1 = reinterpret_cast<const float*>(p->d_weights + l1.off_b);
+    pd.embed[e].w2 = reinterpret_cast<const float*>(p->d_weights + l2.off_w0);
+    pd.embed[e].b2 = reinterpret_cast<const float*>(p->d_weights + l2.off_b);
+    pd.embed[e].ndst = dsts(p->emb_binds[e].dst, {}, pd.embed[e].dst);
+  }
+  // assemble
+  AssembleDev& ad = p->asmb;
+  memset(&ad, 0, sizeof(ad));
+  for (int q = 0; q < kMaxProb; ++q)
+    ad.heads[q] = p->m_heads[q] >= 0 ? reinterpret_cast<const float*>(p->d_ws + p->mats[p->m_heads[q]].off0) : nullptr;
+  ad.head_ld = 16; ad.J = p->J; ad.has_pos = p->has_pos; ad.has_trj = p->has_trj;
+  for (int s = 0; s < p->J; ++s) { ad.slot_prob[s] = (int16_t)p->groups.slots[s].first; ad.slot_joint[s] = (int16_t)p->groups.slots[s].second; }
+
+  // descriptor slab: [ops][prologue][assemble][tensor maps]
+  const size_t nops = p->ops.size();
+  off = 0;
+  p->off_ops = take(nops * sizeof(GemmOpDev));
+  p->off_pro = take(sizeof(PrologueDev));
+  p->off_asm = take(sizeof(AssembleDev));
+  p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
+  std::vector<char> h(off, 0);
+  for (size_t i = 0; i < nops; ++i) memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
+  memcpy(h.data() + p->off_pro, &pd, sizeof(pd));
+  memcpy(h.data() + p->off_asm, &ad, sizeof(ad));
+  if (prec != R3D_PREC_FP32) {
+    for (size_t i = 0; i < nops; ++i) {
+      const int rc = tc_build_tmaps(p->ops[i].dev, prec, (int64_t)cap * p->ops[i].dev.rows_per_seq,
+                                    h.data() + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes);
+      if (rc != 0) return fail(R3D_ERR_CUDA, "cuTensorMapEncodeTiled failed for op %s (code %d)", p->ops[i].name.c_str(), rc);
+    }
+  }
+  CUDA_TRY(cudaMalloc(&p->d_desc, off));
+  CUDA_TRY(cudaMemcpy(p->d_desc, h.data(), off, cudaMemcpyHostToDevice));
+  return R3D_OK;
+}
+
+static int ensure_capacity(r3d_plan* p, int batch) {
+  if (batch <= p->cap) return R3D_OK;
+  int cap = std::max(batch, 16);
+  return bind_workspace(p, cap);
+}
+
+// ---- forward -------------------------------------------------------------------------------------
+static constexpr int kMaxChunk = 8192;
+
+static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                     float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
+  const int prec = p->cfg.precision;
+  CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, src, src_stride,
+                           is_uv, prm, prm_stride, batch, s));
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const GemmOpDev* d_op = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops) + i;
+    const int M = batch * p->ops[i].dev.rows_per_seq;
+    if (prec == R3D_PREC_FP32)
+      CUDA_TRY(launch_gemm_ffma(d_op, p->ops[i].dev, M, s));
+    else
+      CUDA_TRY(launch_gemm_tc(d_op, p->ops[i].dev, p->d_desc + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes, M, prec, s));
+  }
+  CUDA_TRY(launch_assemble(reinterpret_cast<const AssembleDev*>(p->d_desc + p->off_asm), p->asmb, pos, trj, sum, batch, s));
+  return R3D_OK;
+}
+
+static int check_forward(r3d_plan* p, const void* src, float* pos, float* trj, float* sum, int batch) {
+  if (!p || !src) return fail(R3D_ERR_BAD_ARG, "forward: null plan or input");
+  if (!p->uploaded) return fail(R3D_ERR_STATE, "forward before r3d_plan_upload");
+  if (batch < 0) return fail(R3D_ERR_BAD_ARG, "batch=%d", batch);
+  if ((pos || sum) && !p->has_pos) return fail(R3D_ERR_BAD_ARG, "plan has no pose net but pos/sum output requested");
+  if (trj && !p->has_trj) return fail(R3D_ERR_BAD_ARG, "plan has no trajectory net but trj output requested");
+  if (sum && !p->has_trj) return fail(R3D_ERR_BAD_ARG, "sum output needs both nets");
+  return R3D_OK;
+}
+
+static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                       float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
+  int rc = check_forward(p, src, pos, trj, sum, batch);
+  if (rc) return rc;
+  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
+  if (batch == 0) return R3D_OK;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  rc = ensure_capacity(p, std::min(batch, kMaxChunk));
+  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += kMaxChunk) {
+    const int nb = std::min(kMaxChunk, batch - b0);
+    rc = run_chunk(p, src + (int64_t)b0 * src_stride, src_stride, is_uv, prm ? prm + (int64_t)b0 * prm_stride : nullptr, prm_stride,
+                   pos ? pos + (int64_t)b0 * p->J * 3 : nullptr, trj ? trj + (int64_t)b0 * 3 : nullptr,
+                   sum ? sum + (int64_t)b0 * p->J * 3 : nullptr, nb, s);
+  }
+  if (dev != p->device) cudaSetDevice(dev);
+  return rc;
+}
+
+extern "C" R3D_API int r3d_forward_rays(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
+                                int32_t batch, void* stream) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  return forward_dev(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, (cudaStream_t)stream);
+}
+
+extern "C" R3D_API int r3d_forward_uv(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum,
+                              int32_t batch, void* stream) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv needs in_features == 3 (ray encoding, utils.py:91-96)");
+  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv derives param=[height,pitch]: extrinsic_dim must be 2");
+  if (!cam) return fail(R3D_ERR_BAD_ARG, "cam is null");
+  return forward_dev(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, (cudaStream_t)stream);
+}
+
+extern "C" R3D_API int r3d_forward_video(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
+                                 int32_t frames_out, void* stream) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  // window f = frames [f, f+RF) of the padded video: batch stride of one frame, shared param row
+  return forward_dev(p, seq, (int64_t)p->JC, 0, param, 0, pos, trj, sum, frames_out, (cudaStream_t)stream);
+}
+
+// Host-buffer forward: chunks of the batch flow H2D (copy stream) -> compute stream -> D2H (copy stream)
+// with two staging slots so the PCIe transfer of chunk i+1 overlaps the kernels of chunk i.
+static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                        float* pos, float* trj, float* sum, int batch) {
+  int rc = check_forward(p, src, pos, trj, sum, batch);
+  if (rc) return rc;
+  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
+  if (batch == 0) return R3D_OK;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  const int chunk = std::min(batch, std::max(64, std::min(1024, (batch + 3) / 4)));
+  const size_t in_b = (size_t)chunk * src_stride * 4, prm_b = (size_t)chunk * std::max<int64_t>(prm_stride, 1) * 4;
+  const size_t out_b = (size_t)chunk * p->J * 3 * 4, trj_b = (size_t)chunk * 3 * 4;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t slot = al(in_b) + al(prm_b) + 2 * al(out_b) + al(trj_b);
+  if (p->stage_bytes < 2 * slot) {
+    if (p->d_stage) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(p->d_stage)); p->d_stage = nullptr; }
+    CUDA_TRY(cudaMalloc(&p->d_stage, 2 * slot));
+    p->stage_bytes = 2 * slot;
+  }
+  rc = ensure_capacity(p, chunk);
+  int it = 0;
+  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += chunk, ++it) {
+    const int nb = std::min(chunk, batch - b0), sl = it & 1;
+    char* base = p->d_stage + (size_t)sl * slot;
+    float* d_in = reinterpret_cast<float*>(base);
+    float* d_prm = reinterpret_cast<float*>(base + al(in_b));
+    float* d_pos = reinterpret_cast<float*>(base + al(in_b) + al(prm_b));
+    float* d_sum = reinterpret_cast<float*>(base + al(in_b) + al(prm_b) + al(out_b));
+    float* d_trj = reinterpret_cast<float*>(base + al(in_b) + al(prm_b) + 2 * al(out_b));
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(p->s_copy, p->ev_done[sl], 0));   // slot's previous results have left
+    CUDA_TRY(cudaMemcpyAsync(d_in, src + (int64_t)b0 * src_stride, (size_t)nb * src_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
+    if (prm) CUDA_TRY(cudaMemcpyAsync(d_prm, prm + (int64_t)b0 * prm_stride, (size_t)nb * prm_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
+    CUDA_TRY(cudaEventRecord(p->ev_in[sl], p->s_copy));
+    CUDA_TRY(cudaStreamWaitEvent(p->s_comp, p->ev_in[sl], 0));
+    rc = run_chunk(p, d_in, src_stride, is_uv, prm ? d_prm : nullptr, prm_stride, pos ? d_pos : nullptr, trj ? d_trj : nullptr,
+                   sum ? d_sum : nullptr, nb, p->s_comp);
+    if (rc) break;
+    if (pos) CUDA_TRY(cudaMemcpyAsync(pos + (int64_t)b0 * p->J * 3, d_pos, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, p->s_comp));
+    if (sum) CUDA_TRY(cudaMemcpyAsync(sum + (int64_t)b0 * p->J * 3, d_sum, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, p->s_comp));
+    if (trj) CUDA_TRY(cudaMemcpyAsync(trj + (int64_t)b0 * 3, d_trj, (size_t)nb * 12, cudaMemcpyDeviceToHost, p->s_comp));
+    CUDA_TRY(cudaEventRecord(p->ev_done[sl], p->s_comp));
+  }
+  if (rc == R3D_OK) {
+    CUDA_TRY(cudaStreamSynchronize(p->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(p->s_copy));
+  }
+  if (dev != p->device) cudaSetDevice(dev);
+  return rc;
+}
+
+extern "C" R3D_API int r3d_forward_rays_host(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum, int32_t batch) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  return forward_host(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch);
+}
+
+extern "C" R3D_API int r3d_forward_uv_host(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum, int32_t batch) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv_host needs in_features == 3");
+  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim must be 2");
+  if (!cam) return fail(R3D_ERR_BAD_ARG, "cam is null");
+  return forward_host(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch);
+}
+
+extern "C" R3D_API int r3d_ray_encode_f64(const double* uv, double* ray, int64_t n, double fx, double fy, double ppx, double ppy,
+                                  double c, double s, void* stream) {
+  if (!uv || !ray || n < 0) return fail(R3D_ERR_BAD_ARG, "r3d_ray_encode_f64: bad argument");
+  CUDA_TRY(launch_ray_encode_f64(uv, ray, n, fx, fy, ppx, ppy, c, s, (cudaStream_t)stream));
+  return R3D_OK;
+}
+
+extern "C" R3D_API int r3d_normalize_screen_f64(const double* xy, double* out, int64_t n, double w, double h, void* stream) {
+  if (!xy || !out || n < 0 || w == 0.0) return fail(R3D_ERR_BAD_ARG, "r3d_normalize_screen_f64: bad argument");
+  CUDA_TRY(launch_normalize_screen_f64(xy, out, n, w, h, (cudaStream_t)stream));
+  return R3D_OK;
+}
+
+// ---- on-device self test: tensor-core GEMM vs FP32 FFMA GEMM -----------------------------------------
+extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
+                                 double* rel_err, double* ms_tc, double* ms_ffma) {
+  if (m <= 0 || n <= 0 || k <= 0 || k % kKAlign || n % 16 || nprob < 1 || nprob > kMaxProb)
+    return fail(R3D_ERR_BAD_ARG, "selftest: need k%%64==0, n%%16==0, 1<=nprob<=6");
+  if (precision != R3D_PREC_BF16X3 && precision != R3D_PREC_BF16) return fail(R3D_ERR_BAD_ARG, "selftest precision");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(tc_configure());
+  const size_t na = (size_t)m * k, nw = (size_t)n * k, nc = (size_t)m * n;
+  std::vector<float> hA(na * nprob), hW(nw * nprob), hB((size_t)n * nprob), hR(nc * nprob);
+  uint32_t st = 12345u + m * 7 + n * 3 + k;
+  auto rnd = [&]() { st = st * 1664525u + 1013904223u; return ((st >> 8) & 0xffff) / 32768.0f - 1.0f; };
+  for (auto& v : hA) v = rnd();
+  for (auto& v : hW) v = rnd() * 0.05f;
+  for (auto& v : hB) v = rnd() * 0.1f;
+  for (auto& v : hR) v = rnd();
+  // device buffers: fp32 set for FFMA, bf16 planes for the tensor path
+  float *dA, *dW, *dB, *dR, *dC0, *dC1;
+  uint16_t *dAh, *dAl, *dWh, *dWl, *dRh, *dRl;
+  CUDA_TRY(cudaMalloc(&dA, na * nprob * 4)); CUDA_TRY(cudaMalloc(&dW, nw * nprob * 4)); CUDA_TRY(cudaMalloc(&dB, n * nprob * 4));
+  CUDA_TRY(cudaMalloc(&dR, nc * nprob * 4)); CUDA_TRY(cudaMalloc(&dC0, nc * nprob * 4)); CUDA_TRY(cudaMalloc(&dC1, nc * nprob * 4));
+  CUDA_TRY(cudaMalloc(&dAh, na * nprob * 2)); CUDA_TRY(cudaMalloc(&dAl, na * nprob * 2)); CUDA_TRY(cudaMalloc(&dWh, nw * nprob * 2));
+  CUDA_TRY(cudaMalloc(&dWl, nw * nprob * 2)); CUDA_TRY(cudaMalloc(&dRh, nc * nprob * 2)); CUDA_TRY(cudaMalloc(&dRl, nc * nprob * 2));
+  auto split = [&](const std::vector<float>& src, std::vector<float>& rounded, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+    hi.resize(src.size()); lo.resize(src.size()); rounded.resize(src.size());
+    for (size_t i = 0; i < src.size(); ++i) {
+      hi[i] = f2bf(src[i]);
+      lo[i] = precision == R3D_PREC_BF16X3 ? f2bf(src[i] - bf2f(hi[i])) : 0;
+      rounded[i] = bf2f(hi[i]) + bf2f(lo[i]);   // what the tensor path actually multiplies
+    }
+  };
+  std::vector<float> rA, rW, rR;
+  std::vector<uint16_t> Ah, Al, Wh, Wl, Rh, Rl;
+  split(hA, rA, Ah, Al); split(hW, rW, Wh, Wl); split(hR, rR, Rh, Rl);
+  // FFMA reference multiplies the *same rounded operands* for BF16 (single product); for BF16X3 it uses the
+  // original fp32 values, so rel_err includes the dropped lo*lo term (expected ~1e-5).
+  const std::vector<float>& fa = precision == R3D_PREC_BF16 ? rA : hA;
+  const std::vector<float>& fw = precision == R3D_PREC_BF16 ? rW : hW;
+  CUDA_TRY(cudaMemcpy(dA, fa.data(), na * nprob * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dW, fw.data(), nw * nprob * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dB, hB.data(), n * nprob * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dR, rR.data(), nc * nprob * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dAh, Ah.data(), na * nprob * 2, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dAl, Al.data(), na * nprob * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dWh, Wh.data(), nw * nprob * 2, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dWl, Wl.data(), nw * nprob * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dRh, Rh.data(), nc * nprob * 2, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dRl, Rl.data(), nc * nprob * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(dC0, 0, nc * nprob * 4)); CUDA_TRY(cudaMemset(dC1, 0, nc * nprob * 4));
+  GemmOpDev f{}, t{};
+  f.nprob = t.nprob = nprob; f.rows_per_seq = t.rows_per_seq = 1; f.slope = t.slope = 0.2f; f.n_tile = t.n_tile = pick_n_tile(n);
+  for (int q = 0; q < nprob; ++q) {
+    GemmProb& a = f.prob[q];
+    a.a = Mat{dA + q * na, nullptr, k, 0}; a.w0 = dW + q * nw; a.bias = dB + (size_t)q * n;
+    a.res = Mat{dR + q * nc, nullptr, n, 0}; a.res_col = 0; a.K = k; a.N = n; a.n_pad = n; a.ndst = 1;
+    a.dst[0] = Dst{Mat{dC0 + q * nc, nullptr, n, 0}, 0, 1};
+    GemmProb& b = t.prob[q];
+    b = a;
+    b.a = Mat{dAh + q * na, precision == R3D_PREC_BF16X3 ? dAl + q * na : nullptr, k, 0};
+    b.w0 = dWh + q * nw; b.w1 = precision == R3D_PREC_BF16X3 ? dWl + q * nw : nullptr;
+    b.res = Mat{dRh + q * nc, precision == R3D_PREC_BF16X3 ? dRl + q * nc : nullptr, n, 0};
+    b.dst[0] = Dst{Mat{dC1 + q * nc, nullptr, n, 0}, 0, 1};
+  }
+  GemmOpDev *dF, *dT;
+  void* dMaps;
+  std::vector<char> maps((size_t)kMaxProb * kTmapsPerProb * kTmapBytes, 0);
+  if (tc_build_tmaps(t, precision, m, maps.data()) != 0) return fail(R3D_ERR_CUDA, "selftest: tensor map encode failed");
+  CUDA_TRY(cudaMalloc(&dF, sizeof(f))); CUDA_TRY(cudaMalloc(&dT, sizeof(t))); CUDA_TRY(cudaMalloc(&dMaps, maps.size()));
+  CUDA_TRY(cudaMemcpy(dF, &f, sizeof(f), cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dT, &t, sizeof(t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dMaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  float ms = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    CUDA_TRY(launch_gemm_ffma(dF, f, m, 0));
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  if (ms_ffma) *ms_ffma = ms;
+  for (int rep = 0; rep < 2; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    CUDA_TRY(launch_gemm_tc(dT, t, dMaps, m, precision, 0));
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  if (ms_tc) *ms_tc = ms;
+  std::vector<float> c0(nc * nprob), c1(nc * nprob);
+  CUDA_TRY(cudaMemcpy(c0.data(), dC0, nc * nprob * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(c1.data(), dC1, nc * nprob * 4, cudaMemcpyDeviceToHost));
+  double mx = 0, md = 0;
+  for (size_t i = 0; i < c0.size(); ++i) {
+    mx = std::max(mx, (double)std::fabs(c0[i]));
+    const double d = std::fabs((double)c0[i] - (double)c1[i]);
+    md = (d != d) ? 1e30 : std::max(md, d);
+  }
+  if (rel_err) *rel_err = md / std::max(mx, 1e-30);
+  for (void* q : {(void*)dA, (void*)dW, (void*)dB, (void*)dR, (void*)dC0, (void*)dC1, (void*)dAh, (void*)dAl, (void*)dWh, (void*)dWl,
+                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps})
+    cudaFree(q);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return R3D_OK;
+}

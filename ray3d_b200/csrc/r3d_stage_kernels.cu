@@ -1,0 +1,213 @@
+// Input stage (camera-ray encode + positional/temporal differences + joint-group gather +
+// camera embedding) and output stage (joint permutation, pos + trj) of the lifting path.
+//
+// Reference behaviour restated here (paths relative to the reference checkout):
+//   ray encode ................. lib/camera/camera.py:423-441, 460-471 (undistort=False)
+//   in_current / diff / diff_t . lib/model/rie.py:289-304
+//   group gather + cat ......... lib/model/rie.py:306-357 (pose), :540 (trajectory)
+//   Embedding .................. lib/model/embedding.py:15-19 (LeakyReLU slope 0.01)
+//   output joint order ......... lib/model/rie.py:415-432; pos += trj trainer.py:353
+#include "r3d_internal.h"
+
+namespace r3d {
+
+__device__ __forceinline__ void store_act(const Mat& m, int precision, int64_t row, int col, float v) {
+  const int64_t idx = row * m.ld + col;
+  if (precision == R3D_PREC_FP32) {
+    reinterpret_cast<float*>(m.p0)[idx] = v;
+  } else {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    reinterpret_cast<__nv_bfloat16*>(m.p0)[idx] = hi;
+    if (precision == R3D_PREC_BF16X3)
+      reinterpret_cast<__nv_bfloat16*>(m.p1)[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+__device__ __forceinline__ void store_act2(const Mat& m, int precision, int64_t row, int col, float v0, float v1) {
+  const int64_t idx = row * m.ld + col;   // col even, ld even => 8-byte (fp32) / 4-byte (bf16) aligned
+  if (precision == R3D_PREC_FP32) {
+    *reinterpret_cast<float2*>(reinterpret_cast<float*>(m.p0) + idx) = make_float2(v0, v1);
+  } else {
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(m.p0) + idx) = hi;
+    if (precision == R3D_PREC_BF16X3) {
+      const float2 hf = __bfloat1622float2(hi);
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(m.p1) + idx) =
+          __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+    }
+  }
+}
+
+__device__ __forceinline__ float tab_value(int32_t e, const float* __restrict__ xs, int JC, int tc, int w0, int tq) {
+  if (e < 0) return 0.f;
+  const int src = e & 0xff, part = (e >> 8) & 3, k = (e >> 10) & 63, c = (e >> 16) & 3;
+  const float* row = xs + (tq * w0 + k) * JC;
+  float v = row[src];
+  if (part == 1) v -= row[c];                 // x - root joint (rie.py:301)
+  else if (part == 2) v -= xs[tc * JC + src]; // x - x[current frame] (rie.py:304)
+  return v;
+}
+
+// One CTA per sequence (window).  Dynamic smem: T*J*Cin floats (+ embed scratch).
+__global__ void __launch_bounds__(256) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
+                                                       const float* __restrict__ src, int64_t src_batch_stride,
+                                                       int src_is_uv, const float* __restrict__ cam_or_param,
+                                                       int64_t param_stride, int batch) {
+  extern __shared__ float smem[];
+  const PrologueDev& d = *dp;
+  const int b = blockIdx.x;
+  const int T = d.T, J = d.J, JC = d.JC;
+  float* xs = smem;                    // [T][JC]
+  float* scratch = smem + T * JC;      // [emb_mid] embed hidden
+
+  // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
+  if (src_is_uv) {
+    // camera.py:438-439,471 in float64, then .astype(float32) (trainer.py:298)
+    const float* cam = cam_or_param + (int64_t)b * param_stride;
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    double sp, cp;
+    sincos((double)cam[4], &sp, &cp);
+    const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)b * src_batch_stride);
+    for (int i = threadIdx.x; i < T * J; i += blockDim.x) {
+      const float2 p = __ldg(uv + i);
+      const double xn = __ddiv_rn(__dsub_rn((double)p.x, cx), fx);
+      const double yn = __ddiv_rn(__dsub_rn((double)p.y, cy), fy);
+      xs[i * 3 + 0] = (float)xn;
+      xs[i * 3 + 1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
+      xs[i * 3 + 2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
+    }
+  } else {
+    const float* x = src + (int64_t)b * src_batch_stride;
+    for (int i = threadIdx.x; i < T * JC; i += blockDim.x) xs[i] = __ldg(x + i);
+  }
+  __syncthreads();
+
+  // ---- 2. first-layer A matrices: row (b, tq), column kk = tap*Cg + channel --------------------
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int p = 0; p < d.nprob; ++p) {
+    const PrologueProb& pr = d.prob[p];
+    const int kp = pr.k_pad;
+    for (int tq = warp; tq < d.L0; tq += nwarp) {
+      const int64_t row = (int64_t)b * d.L0 + tq;
+      for (int kk = lane * 2; kk < kp; kk += 64) {
+        const int2 e = __ldg(reinterpret_cast<const int2*>(pr.tab + kk));
+        store_act2(pr.a0, precision, row, kk, tab_value(e.x, xs, JC, d.tc, d.w0, tq),
+                   tab_value(e.y, xs, JC, d.tc, d.w0, tq));
+      }
+    }
+  }
+
+  // ---- 3. in_current (rie.py:290-292), zero padded to the row pitch ------------------------------
+  for (int i = threadIdx.x; i < d.inc.ld; i += blockDim.x)
+    store_act(d.inc, precision, b, i, i < JC ? xs[d.tc * JC + i] : 0.f);
+
+  // ---- 4. camera embedding (embedding.py:15-19), BN folded, fp32 FFMA ----------------------------
+  for (int e = 0; e < d.n_embed; ++e) {
+    const EmbedDev& em = d.embed[e];
+    float prm[8];
+    if (src_is_uv) {   // param = [height, pitch] (trainer.py:297)
+      const float* cam = cam_or_param + (int64_t)b * param_stride;
+      prm[0] = cam[5];
+      prm[1] = cam[4];
+    } else {
+      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)b * param_stride + i];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < d.emb_mid; j += blockDim.x) {
+      float acc = em.b1[j];
+      for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(em.w1[j * d.ext_dim + i], prm[i], acc);
+      scratch[j] = acc > 0.f ? acc : 0.01f * acc;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < d.emb_dim; j += blockDim.x) {
+      float acc = em.b2[j];
+      for (int i = 0; i < d.emb_mid; ++i) acc = fmaf(em.w2[j * d.emb_mid + i], scratch[i], acc);
+      acc = acc > 0.f ? acc : 0.01f * acc;
+      for (int t = 0; t < em.ndst; ++t) store_act(em.dst[t].m, precision, b, em.dst[t].col + j, acc);
+    }
+  }
+}
+
+static int g_prologue_smem_cap = 48 * 1024;
+
+cudaError_t prologue_configure(int max_smem_bytes) {
+  cudaError_t e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  if (e == cudaSuccess) g_prologue_smem_cap = max_smem_bytes;
+  return e;
+}
+
+cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const void* src,
+                            int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
+                            int64_t param_stride, int batch, cudaStream_t s) {
+  const size_t smem = (size_t)(h.T * h.JC + h.emb_mid + 8) * sizeof(float);
+  if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
+  prologue_kernel<<<batch, 256, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
+                                           src_is_uv, cam_or_param, param_stride, batch);
+  return cudaGetLastError();
+}
+
+// ---- output stage ------------------------------------------------------------------------------
+__global__ void assemble_kernel(const AssembleDev* __restrict__ dp, float* __restrict__ pos, float* __restrict__ trj,
+                                float* __restrict__ sum, int batch) {
+  const AssembleDev& d = *dp;
+  const int per = d.J * 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)batch * per) return;
+  const int b = (int)(i / per), r = (int)(i % per), slot = r / 3, c = r % 3;
+  float t = 0.f;
+  if (d.has_trj) {
+    t = d.heads[kMaxProb - 1][(int64_t)b * d.head_ld + c];
+    if (trj != nullptr && slot == 0) trj[(int64_t)b * 3 + c] = t;
+  }
+  if (d.has_pos) {
+    const float v = d.heads[d.slot_prob[slot]][(int64_t)b * d.head_ld + d.slot_joint[slot] * 3 + c];
+    if (pos != nullptr) pos[i] = v;
+    if (sum != nullptr) sum[i] = v + t;
+  }
+}
+
+cudaError_t launch_assemble(const AssembleDev* d_desc, const AssembleDev& h, float* pos, float* trj, float* sum,
+                            int batch, cudaStream_t s) {
+  const int64_t n = (int64_t)batch * h.J * 3;
+  assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_desc, pos, trj, sum, batch);
+  return cudaGetLastError();
+}
+
+// ---- standalone float64 ray encode (CameraInfoPacket.get_cam_ray_given_uv, camera.py:460-471) ----
+__global__ void ray_encode_f64_kernel(const double2* __restrict__ uv, double* __restrict__ ray, int64_t n, double fx,
+                                      double fy, double ppx, double ppy, double c, double s) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 p = uv[i];
+  const double xn = __ddiv_rn(__dsub_rn(p.x, ppx), fx);
+  const double yn = __ddiv_rn(__dsub_rn(p.y, ppy), fy);
+  ray[i * 3 + 0] = xn;
+  ray[i * 3 + 1] = __dadd_rn(__dmul_rn(c, yn), s);     // no FMA contraction: matches numpy
+  ray[i * 3 + 2] = __dadd_rn(__dmul_rn(-s, yn), c);
+}
+
+cudaError_t launch_ray_encode_f64(const double* uv, double* ray, int64_t n, double fx, double fy, double ppx,
+                                  double ppy, double c, double s, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ray_encode_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const double2*>(uv), ray, n, fx,
+                                                                    fy, ppx, ppy, c, s);
+  return cudaGetLastError();
+}
+
+// ---- normalize_screen_coordinates (camera.py:11-18): X / w * 2 - [1, h / w], float64 ---------------
+__global__ void normalize_screen_f64_kernel(const double2* __restrict__ xy, double2* __restrict__ out, int64_t n, double w,
+                                            double hw) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 p = xy[i];
+  out[i] = make_double2(__dsub_rn(__dmul_rn(__ddiv_rn(p.x, w), 2.0), 1.0), __dsub_rn(__dmul_rn(__ddiv_rn(p.y, w), 2.0), hw));
+}
+
+cudaError_t launch_normalize_screen_f64(const double* xy, double* out, int64_t n, double w, double h, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  normalize_screen_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const double2*>(xy),
+                                                                          reinterpret_cast<double2*>(out), n, w, h / w);
+  return cudaGetLastError();
+}
+
+}  // namespace r3d

@@ -1,0 +1,154 @@
+"""Torch-facing wrapper of one native plan: tensors in, tensors out, current CUDA stream honoured.
+
+``Lifter`` is the fused entry point (ray encode + pose net + trajectory net + pos+trj in one
+launch sequence) that stands in for the reference's eval step
+(lib/train_val/trainer.py:323-353).  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+from typing import Mapping, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from .spec import NetSpec
+
+DEFAULT_PRECISION = "bf16x3"
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: ray3d_b200 has no CPU path (got device {t.device})")
+
+
+class Lifter:
+    """Both networks behind one plan.
+
+    state_pos / state_trj: state_dicts with the reference's key names (numpy arrays or tensors).
+    Pass ``state_trj=None`` for a pose-only plan or ``state_pos=None`` for trajectory-only.
+    """
+
+    def __init__(self, spec: NetSpec, state_pos: Optional[Mapping[str, object]], state_trj: Optional[Mapping[str, object]],
+                 precision: str = DEFAULT_PRECISION, device: Optional[int] = None):
+        nets = (_capi.NET_POS if state_pos is not None else 0) | (_capi.NET_TRJ if state_trj is not None else 0)
+        if nets == 0:
+            raise ValueError("need at least one state_dict")
+        self.spec = spec
+        self.has_pos, self.has_trj = state_pos is not None, state_trj is not None
+        self.plan = _capi.Plan(spec, nets, precision)
+        if state_pos is not None:
+            self.plan.load_state(_capi.NET_POS, state_pos)
+        if state_trj is not None:
+            self.plan.load_state(_capi.NET_TRJ, state_trj)
+        self.plan.finalize()
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: ray3d_b200 computes the lifting path on the GPU only")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.plan.upload(self.device)
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _outputs(self, batch: int, dev: torch.device, want_pos=True, want_trj=True, want_sum=True):
+        J = self.spec.num_joints
+        pos = torch.empty((batch, 1, J, 3), dtype=torch.float32, device=dev) if (want_pos and self.has_pos) else None
+        trj = torch.empty((batch, 1, 1, 3), dtype=torch.float32, device=dev) if (want_trj and self.has_trj) else None
+        both = torch.empty((batch, 1, J, 3), dtype=torch.float32, device=dev) if (want_sum and self.has_pos and self.has_trj) else None
+        return pos, trj, both
+
+    def _check_x(self, x: torch.Tensor) -> None:
+        # mirrors the asserts at lib/model/rie.py:285-287 (AssertionError like the reference)
+        assert len(x.shape) == 4
+        assert x.shape[-2] == self.spec.num_joints
+        assert x.shape[-1] == self.spec.in_features
+        if x.shape[1] != self.spec.receptive_field:
+            raise RuntimeError(f"sequence length {x.shape[1]} != receptive field {self.spec.receptive_field}: the reference "
+                               "model only evaluates windows of exactly one receptive field (rie.py:362-386)")
+
+    @staticmethod
+    def _stream(dev) -> int:
+        return torch.cuda.current_stream(dev).cuda_stream
+
+    # -- device entry points -------------------------------------------------------------------------
+    def forward_rays(self, x: torch.Tensor, param: Optional[torch.Tensor], want_pos=True, want_trj=True, want_sum=True):
+        """x (B,RF,J,Cin) f32 cuda, param (B,extrinsic_dim) -> (pos (B,1,J,3), trj (B,1,1,3), pos+trj)."""
+        self._check_x(x)
+        _require_cuda(x, "x")
+        x = x.contiguous().float()
+        if self.spec.camera_embedding:
+            if param is None:
+                raise RuntimeError("param is required when the camera embedding is enabled")
+            _require_cuda(param, "param")
+            param = param.contiguous().float()
+            assert param.shape == (x.shape[0], self.spec.extrinsic_dim)
+        pos, trj, both = self._outputs(x.shape[0], x.device, want_pos, want_trj, want_sum)
+        with torch.cuda.device(x.device):
+            self.plan.forward_rays(_ptr(x), _ptr(param) if self.spec.camera_embedding else None, _ptr(pos), _ptr(trj),
+                                   _ptr(both), x.shape[0], self._stream(x.device))
+        return pos, trj, both
+
+    def forward_uv(self, uv: torch.Tensor, cam: torch.Tensor, want_pos=True, want_trj=True, want_sum=True):
+        """uv (B,RF,J,2) pixels f32 cuda, cam (B,6)=[fx,fy,cx,cy,pitch,height] f32 cuda."""
+        _require_cuda(uv, "uv")
+        _require_cuda(cam, "cam")
+        assert uv.dim() == 4 and uv.shape[2] == self.spec.num_joints and uv.shape[3] == 2
+        assert uv.shape[1] == self.spec.receptive_field and cam.shape == (uv.shape[0], 6)
+        uv, cam = uv.contiguous().float(), cam.contiguous().float()
+        pos, trj, both = self._outputs(uv.shape[0], uv.device, want_pos, want_trj, want_sum)
+        with torch.cuda.device(uv.device):
+            self.plan.forward_uv(_ptr(uv), _ptr(cam), _ptr(pos), _ptr(trj), _ptr(both), uv.shape[0], self._stream(uv.device))
+        return pos, trj, both
+
+    def forward_video(self, seq: torch.Tensor, param: Optional[torch.Tensor]):
+        """seq (F+RF-1, J, Cin) f32 cuda (edge-padded video), param (extrinsic_dim,) -> F sliding-window outputs.
+        Replaces eval_data_prepare + np.tile + forward (trainer.py:47-58, 323-337) without materialising windows."""
+        _require_cuda(seq, "seq")
+        assert seq.dim() == 3 and seq.shape[1] == self.spec.num_joints and seq.shape[2] == self.spec.in_features
+        frames = seq.shape[0] - self.spec.receptive_field + 1
+        if frames <= 0:
+            raise RuntimeError("video shorter than one receptive field")
+        seq = seq.contiguous().float()
+        if self.spec.camera_embedding:
+            _require_cuda(param, "param")
+            param = param.contiguous().float().reshape(-1)
+            assert param.numel() == self.spec.extrinsic_dim
+        pos, trj, both = self._outputs(frames, seq.device)
+        with torch.cuda.device(seq.device):
+            self.plan.forward_video(_ptr(seq), _ptr(param) if self.spec.camera_embedding else None, _ptr(pos), _ptr(trj),
+                                    _ptr(both), frames, self._stream(seq.device))
+        return pos, trj, both
+
+    # -- host entry points (end-to-end: H2D + kernels + D2H inside the call) ---------------------------
+    def forward_uv_host(self, uv: torch.Tensor, cam: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uv/cam are CPU tensors (pinned for full PCIe rate); returns pos+trj (B,1,J,3) on the CPU."""
+        assert not uv.is_cuda and not cam.is_cuda and uv.dtype == torch.float32 and cam.dtype == torch.float32
+        uv, cam = uv.contiguous(), cam.contiguous()
+        B = uv.shape[0]
+        if out is None:
+            out = torch.empty((B, 1, self.spec.num_joints, 3), dtype=torch.float32, pin_memory=True)
+        with torch.cuda.device(self.device):
+            if self.has_pos and self.has_trj:
+                self.plan.forward_uv_host(_ptr(uv), _ptr(cam), None, None, _ptr(out), B)
+            elif self.has_pos:
+                self.plan.forward_uv_host(_ptr(uv), _ptr(cam), _ptr(out), None, None, B)
+            else:
+                raise RuntimeError("forward_uv_host needs the pose net")
+        return out
+
+    def forward_rays_host(self, x: torch.Tensor, param: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert not x.is_cuda and x.dtype == torch.float32
+        self._check_x(x)
+        x = x.contiguous()
+        param = param.contiguous() if param is not None else None
+        B = x.shape[0]
+        if out is None:
+            out = torch.empty((B, 1, self.spec.num_joints, 3), dtype=torch.float32, pin_memory=True)
+        with torch.cuda.device(self.device):
+            if self.has_pos and self.has_trj:
+                self.plan.forward_rays_host(_ptr(x), _ptr(param), None, None, _ptr(out), B)
+            else:
+                self.plan.forward_rays_host(_ptr(x), _ptr(param), _ptr(out), None, None, B)
+        return out

@@ -1,0 +1,145 @@
+"""CPU: host side of the C ABI -- symbols, weight folding/packing, launch-graph wiring, error behaviour."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, relerr
+from replay import replay
+from ray3d_b200 import _capi, synth
+from ray3d_b200.spec import NetSpec, BN_EPS
+
+CASES = ["h36m_s1_t27", "h36m_s3_t9", "humaneva_s1_t9", "h36mcross_s2_t9", "rie_s1_t9_noembed", "rie15_s3_t27"]
+
+
+def spec_of(meta, name):
+    kw = dict(meta[name]["spec"])
+    kw["filter_widths"] = tuple(kw["filter_widths"])
+    return NetSpec(**kw)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ray3d_b200.h")).read()
+    declared = set(re.findall(r"R3D_API[^;(]*?\b(r3d_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    lib = _capi.lib()                      # loads the .so and resolves every EXPORTS entry
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.r3d_abi_version() == 1
+
+
+def make_plan(spec, nets=3, precision="fp32"):
+    sp, st = synth.make_state_dicts(spec)
+    p = _capi.Plan(spec, nets, precision)
+    if nets & 1:
+        p.load_state(_capi.NET_POS, sp)
+    if nets & 2:
+        p.load_state(_capi.NET_TRJ, st)
+    p.finalize()
+    return p, sp, st
+
+
+def test_bn_fold_and_packing_match_numpy():
+    spec = NetSpec(filter_widths=(3, 3, 3), stage=3)
+    p, sp, st = make_plan(spec)
+
+    def fold(sd, w, bn, bias=None):
+        W = sd[w].astype(np.float64)
+        n = W.shape[0]
+        if bn:
+            s = sd[bn + ".weight"].astype(np.float64) / np.sqrt(sd[bn + ".running_var"].astype(np.float64) + BN_EPS)
+            sh = sd[bn + ".bias"].astype(np.float64) - sd[bn + ".running_mean"].astype(np.float64) * s
+        else:
+            s, sh = np.ones(n), np.zeros(n)
+        b = (sd[bias].astype(np.float64) * s if bias else 0) + sh
+        if W.ndim == 3:      # (out, in, tap) -> column tap*in + c
+            W = W.transpose(0, 2, 1).reshape(n, -1)
+        return (W * s[:, None]).astype(np.float32), np.asarray(b, np.float32)
+
+    checks = [
+        (1, "LocalLayer_Torso.expand_conv", sp, "LocalLayer_Torso.expand_conv.weight", "LocalLayer_Torso.expand_bn", None),
+        (1, "LocalLayer_LLeg.layers_conv.2", sp, "LocalLayer_LLeg.layers_conv.2.weight", "LocalLayer_LLeg.layers_bn.2", None),
+        (1, "LocalLayer_RArm.layers_conv.1", sp, "LocalLayer_RArm.layers_conv.1.weight", "LocalLayer_RArm.layers_bn.1", None),
+        (1, "LocalLayer_RArm.shrink", sp, "LocalLayer_RArm.shrink.weight", None, "LocalLayer_RArm.shrink.bias"),
+        (1, "GlobalInfo.fc_1", sp, "GlobalInfo.fc_1.weight", "GlobalInfo.bn_1", "GlobalInfo.fc_1.bias"),
+        (1, "FuseBlocks.3.layers.0.w2", sp, "FuseBlocks.3.layers.0.w2.weight", "FuseBlocks.3.layers.0.batch_norm2", "FuseBlocks.3.layers.0.w2.bias"),
+        (1, "Integration_Torso.fc_2", sp, "Integration_Torso.fc_2.weight", None, "Integration_Torso.fc_2.bias"),
+        (2, "LocalLayer.expand_conv", st, "LocalLayer.expand_conv.weight", "LocalLayer.expand_bn", None),
+        (2, "Integration.fc_2", st, "Integration.fc_2.weight", None, "Integration.fc_2.bias"),
+        (2, "embedder.w2", st, "embedder.w2.weight", "embedder.b2", "embedder.w2.bias"),
+    ]
+    for net, layer, sd, w, bn, bias in checks:
+        W, b = fold(sd, w, bn, bias)
+        pw, pb = p.packed_layer(net, layer)
+        n, k = W.shape
+        assert pw.shape[0] >= n and pw.shape[1] >= k and pw.shape[1] % 64 in (0, k % 64)
+        assert np.array_equal(pw[:n, :k], W), layer
+        assert np.array_equal(pb[:n], b), layer
+        assert not pw[n:].any() and not pw[:, k:].any() and not pb[n:].any()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_launch_graph_replay_matches_reference(golden_meta, name):
+    """Wiring + packing + gather tables: numpy replay of the native graph vs the reference's outputs."""
+    spec = spec_of(golden_meta, name)
+    g = load_golden(name)
+    p, _, _ = make_plan(spec)
+    pos, trj = replay(p, g["x"], g["param"])
+    assert relerr(pos, g["pos64"]) < 5e-6
+    assert relerr(trj, g["trj64"]) < 5e-6
+    assert p.receptive_field == spec.receptive_field
+    assert p.kernel_launches == len(p.describe()["ops"]) + 2
+
+
+@pytest.mark.parametrize("nets", [1, 2])
+def test_single_net_plans_replay(golden_meta, nets):
+    spec = spec_of(golden_meta, "h36m_s3_t9")
+    g = load_golden("h36m_s3_t9")
+    p, _, _ = make_plan(spec, nets=nets)
+    pos, trj = replay(p, g["x"], g["param"])
+    if nets == 1:
+        assert trj is None and relerr(pos, g["pos64"]) < 5e-6
+    else:
+        assert pos is None and relerr(trj, g["trj64"]) < 5e-6
+
+
+def test_error_behaviour():
+    spec = NetSpec(filter_widths=(3, 3))
+    sp, st = synth.make_state_dicts(spec)
+    p = _capi.Plan(spec, 3, "fp32")
+    with pytest.raises(_capi.R3DError, match="unknown state_dict key"):
+        p.set_tensor(_capi.NET_POS, "LocalLayer_Nose.expand_conv.weight", np.zeros((2, 2), np.float32))
+    with pytest.raises(_capi.R3DError, match="shape mismatch"):
+        p.set_tensor(_capi.NET_POS, "LocalLayer_Torso.expand_conv.weight", np.zeros((256, 45, 5), np.float32))
+    p.load_state(_capi.NET_POS, sp)
+    with pytest.raises(_capi.R3DError, match="never supplied") as ei:    # trj weights missing
+        p.finalize()
+    assert ei.value.code == _capi.ERR_MISSING_WEIGHT
+    # DataParallel-style prefixes are accepted (trainer.py:232-240)
+    p.load_state(_capi.NET_TRJ, {"module." + k: v for k, v in st.items()})
+    p.finalize()
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.R3DError) as ei:
+            p.upload(0)
+        assert ei.value.code == _capi.ERR_NO_DEVICE     # loud, no CPU fallback
+    for bad in (dict(num_joints=16), dict(in_features=4), dict(filter_widths=(2, 3))):
+        with pytest.raises(ValueError):
+            NetSpec(**bad)
+    cfg = _capi.make_config(spec, 3, "fp32")
+    cfg.channels = 100
+    h = _capi.C.c_void_p()
+    assert _capi.lib().r3d_plan_create(_capi.C.byref(cfg), _capi.C.byref(h)) == _capi.ERR_UNSUPPORTED
+    assert b"multiples of 64" in _capi.lib().r3d_last_error()
+
+
+def test_tensor_precision_plans_finalize():
+    spec = NetSpec(filter_widths=(3, 3))
+    for prec in ("bf16x3", "bf16"):
+        p, _, _ = make_plan(spec, precision=prec)
+        assert p.weight_bytes > 0
+    p32, _, _ = make_plan(spec, precision="fp32")
+    pb, _, _ = make_plan(spec, precision="bf16")
+    assert pb.weight_bytes < 0.6 * p32.weight_bytes
