@@ -67,7 +67,8 @@ class RayCamera:
         self.res_w, self.res_h, self.undistort = res_w, res_h, False
         self.Rc2w = R.T
         # camera.py:273-283,308-316: optical axis in world coordinates vs world up
-        ray_world = self.Rc2w @ np.array([0.0, 0.0, 1.0])
+        # (Rc2w @ e_z is exactly the third column of Rc2w: index it instead of going through BLAS)
+        ray_world = self.Rc2w[:, 2]
         norm = math.sqrt(sum(float(c) * float(c) for c in ray_world))
         self.cam_pitch_rad = math.acos(float(ray_world[2]) / (norm * 1.0)) - np.pi / 2
         self.cam_orig_world = -self.Rw2c.T @ self.Tw2c                  # camera.py:265-271

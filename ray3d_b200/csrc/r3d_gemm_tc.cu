@@ -1,7 +1,469 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Grouped split-precision GEMM on the Blackwell tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   out[p][m, n] = res[p][m, n] + lrelu( sum_k A[p][m, k] * W[p][n, k] + bias[p][n] )
+//
+// This is the same contraction as r3d_gemm_ffma.cu (F.conv1d with stride == kernel / F.linear, eval
+// BatchNorm folded, LeakyReLU, residual: lib/model/rie.py:86-99, 122-135, 159-169), but every fp32
+// operand is carried as two bf16 planes (x = hi + lo, 16 mantissa bits) and the product is formed
+// as hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory (R3D_PREC_BF16X3, ~1e-5 normwise
+// end to end), or hi*hi only (R3D_PREC_BF16).
+//
+// Structure (one persistent CTA per SM, 256 threads, static round-robin tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A / W planes of one 64-wide K block
+//               into a ring of 128B-swizzled smem stages, completion on "full" mbarriers
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16, bf16 -> fp32) for the
+//               1 or 3 products of every K step; tcgen05.commit releases the smem stage ("empty")
+//               and, after the last K block, publishes the accumulator ("tmem_full")
+//   warp 2      allocates / frees the 2 x BLOCK_N TMEM columns (double-buffered accumulators)
+//   warps 4..7  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias + LeakyReLU + residual in
+//               registers, re-split to bf16 hi/lo, 64-byte row-segment stores to up to 6 destinations
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
 #include "r3d_internal.h"
+
 namespace r3d {
-cudaError_t launch_gemm_tc(const GemmOpDev*, const GemmOpDev&, const void*, int, int, cudaStream_t) { return cudaErrorNotSupported; }
-int tc_build_tmaps(const GemmOpDev&, int, int64_t, void*) { return 0; }
-cudaError_t tc_configure() { return cudaSuccess; }
+
+constexpr int TBM = 128;            // UMMA M (one TMEM lane per output row)
+constexpr int TBK = 64;             // K block: 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+__host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit) { return nsplit * (TBM + block_n) * TBK * 2; }
+__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit) {
+  int s = (SMEM_LIMIT - 2048) / tc_stage_bytes(block_n, nsplit);
+  return s > 6 ? 6 : s;
 }
+__host__ __device__ constexpr int tc_tmem_cols(int block_n) {
+  int c = 2 * block_n;
+  return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("r3d gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzled operand tile ([rows][64] bf16, 8-row groups 1024 bytes apart):
+// start address >> 4 | LBO (ignored for swizzled K-major; canonical value 1) | SBO = 1024 >> 4 |
+// descriptor version 1 (sm_100) | layout type 2 = SWIZZLE_128B        (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+}
+
+struct TileCoord {
+  int p, m0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int tile, int m_tiles, int block_n) {
+  int p = 0, n_tiles = 1;
+  for (;; ++p) {
+    n_tiles = op.prob[p].n_pad / block_n;
+    const int cnt = m_tiles * n_tiles;
+    if (tile < cnt) break;
+    tile -= cnt;
+  }
+  return TileCoord{p, (tile / n_tiles) * TBM, (tile % n_tiles) * block_n};
+}
+
+__device__ __forceinline__ void split_store16(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+  // 16 consecutive outputs -> 32 bytes per plane
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    if (lo != nullptr) {
+      const float2 hf = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+  }
+  reinterpret_cast<uint4*>(hi)[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  reinterpret_cast<uint4*>(hi)[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  if (lo != nullptr) {
+    reinterpret_cast<uint4*>(lo)[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    reinterpret_cast<uint4*>(lo)[1] = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+}
+
+__device__ __forceinline__ void add_residual16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* v) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi) + q);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+      v[q * 8 + 2 * j] += f.x;
+      v[q * 8 + 2 * j + 1] += f.y;
+    }
+    if (lo != nullptr) {
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo) + q);
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[j]));
+        v[q * 8 + 2 * j] += f.x;
+        v[q * 8 + 2 * j + 1] += f.y;
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, int NSPLIT>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
+                                                                int M, int total_tiles) {
+  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT);
+  constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = BLOCK_N * TBK * 2;
+  constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT);
+  constexpr int TMEM_COLS = tc_tmem_cols(BLOCK_N);
+  constexpr int CH = BLOCK_N >= 32 ? 32 : 16;         // epilogue column chunk
+  static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const GemmOpDev& op = *opp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + TBM - 1) / TBM;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
+        const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
+        const int nkb = op.prob[tc.p].K / TBK;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0);
+          tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0);
+          if (NSPLIT == 2) {
+            tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0);
+            tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
+        const int nkb = op.prob[tc.p].K / TBK;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + NSPLIT * A_BYTES);
+          const uint64_t a_lo = make_smem_desc(st + A_BYTES), w_lo = make_smem_desc(st + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+          for (int k = 0; k < TBK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // 32 bytes per K step inside the swizzle atom
+            umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+            if (NSPLIT == 2) {
+              umma_bf16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+              umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);                     // smem stage free once these MMAs retire
+          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);    // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float slope = op.slope;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
+      const GemmProb& pr = op.prob[tc.p];
+      const int row = tc.m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / CH; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * CH);
+        if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        const int n = tc.n0 + c * CH;
+        if (row_ok && n < pr.N) {
+          float v[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float x = __uint_as_float(r[j]) + __ldg(pr.bias + n + j);
+            v[j] = x > 0.f ? x : slope * x;
+          }
+          if (pr.res.p0 != nullptr) {
+            const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
+#pragma unroll
+            for (int h = 0; h < CH / 16; ++h)
+              add_residual16(reinterpret_cast<const __nv_bfloat16*>(pr.res.p0) + ro + h * 16,
+                             pr.res.p1 ? reinterpret_cast<const __nv_bfloat16*>(pr.res.p1) + ro + h * 16 : nullptr, v + h * 16);
+          }
+          for (int t = 0; t < pr.ndst; ++t) {
+            const Dst& d = pr.dst[t];
+            const int64_t o = (int64_t)row * d.m.ld + d.col + n;
+            if (d.f32) {
+              float* out = reinterpret_cast<float*>(d.m.p0) + o;
+              if (n + CH <= pr.N && ((d.m.ld | d.col) & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                  if (n + j < pr.N) out[j] = v[j];
+              }
+            } else {
+              __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.m.p0) + o;
+              __nv_bfloat16* lo = d.m.p1 ? reinterpret_cast<__nv_bfloat16*>(d.m.p1) + o : nullptr;
+#pragma unroll
+              for (int h = 0; h < CH / 16; ++h) split_store16(hi + h * 16, lo ? lo + h * 16 : nullptr, v + h * 16);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int encode_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_elems, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  if (base == nullptr) { memset(out, 0, sizeof(*out)); return 0; }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int tc_block_n(const GemmOpDev& h) { return h.n_tile; }
+
+int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* out_v) {
+  static_assert(sizeof(CUtensorMap) == kTmapBytes, "CUtensorMap size");
+  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(out_v);
+  const int bn = tc_block_n(h);
+  for (int p = 0; p < h.nprob; ++p) {
+    const GemmProb& g = h.prob[p];
+    if (g.K % TBK || g.a.ld % 8 || g.n_pad % bn) return -2;
+    for (int t = 0; t < g.ndst; ++t)   // bf16 destinations are written in whole 16/32-column chunks
+      if (!g.dst[t].f32 && (g.N % (bn >= 32 ? 32 : 16) || g.dst[t].col % 16 || g.dst[t].m.ld % 16)) return -3;
+    if (g.res.p0 && (g.res_col % 16 || g.res.ld % 16)) return -4;
+    int rc = encode_2d(out + p * kTmapsPerProb + 0, g.a.p0, (uint64_t)g.a.ld, (uint64_t)cap_rows, (uint64_t)g.a.ld, TBM);
+    if (rc) return rc;
+    rc = encode_2d(out + p * kTmapsPerProb + 1, precision == R3D_PREC_BF16X3 ? g.a.p1 : nullptr, (uint64_t)g.a.ld, (uint64_t)cap_rows,
+                   (uint64_t)g.a.ld, TBM);
+    if (rc) return rc;
+    rc = encode_2d(out + p * kTmapsPerProb + 2, g.w0, (uint64_t)g.K, (uint64_t)g.n_pad, (uint64_t)g.K, (uint32_t)bn);
+    if (rc) return rc;
+    rc = encode_2d(out + p * kTmapsPerProb + 3, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
+                   (uint64_t)g.K, (uint32_t)bn);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <int BN, int NS>
+static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_bytes(BN, NS) + 1024 /*align*/ + 256 /*barriers*/; }
+
+template <int BN, int NS>
+static cudaError_t configure_one() {
+  return cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
+}
+
+static int g_num_sms = 0;
+
+cudaError_t tc_configure() {
+  cudaError_t e;
+#define R3D_CFG(BN)                                               \
+  if ((e = configure_one<BN, 1>()) != cudaSuccess) return e;      \
+  if ((e = configure_one<BN, 2>()) != cudaSuccess) return e;
+  R3D_CFG(16) R3D_CFG(32) R3D_CFG(64) R3D_CFG(128) R3D_CFG(256)
+#undef R3D_CFG
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  return cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+template <int BN, int NS>
+static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps, int M, int tiles, cudaStream_t s) {
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tc_kernel<BN, NS><<<grid, TC_THREADS, tc_smem_bytes<BN, NS>(), s>>>(d_op, d_tmaps, M, tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h, const void* d_tmaps, int M, int precision, cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  if (g_num_sms <= 0) return cudaErrorNotReady;
+  const int bn = tc_block_n(h);
+  const int m_tiles = (M + TBM - 1) / TBM;
+  int tiles = 0;
+  for (int p = 0; p < h.nprob; ++p) tiles += m_tiles * (h.prob[p].n_pad / bn);
+  const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(d_tmaps);
+  const int ns = precision == R3D_PREC_BF16X3 ? 2 : 1;
+#define R3D_LAUNCH(BN)                                                             \
+  case BN:                                                                         \
+    return ns == 2 ? launch_one<BN, 2>(d_op, tm, M, tiles, s) : launch_one<BN, 1>(d_op, tm, M, tiles, s);
+  switch (bn) {
+    R3D_LAUNCH(16) R3D_LAUNCH(32) R3D_LAUNCH(64) R3D_LAUNCH(128) R3D_LAUNCH(256)
+    default: return cudaErrorInvalidValue;
+  }
+#undef R3D_LAUNCH
+}
+
+}  // namespace r3d

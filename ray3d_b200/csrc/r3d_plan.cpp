@@ -898,7 +898,8 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
 }
 
 static int check_forward(r3d_plan* p, const void* src, float* pos, float* trj, float* sum, int batch) {
-  if (!p || !src) return fail(R3D_ERR_BAD_ARG, "forward: null plan or input");
+  if (!p) return fail(R3D_ERR_BAD_ARG, "forward: null plan");
+  if (!src && batch != 0) return fail(R3D_ERR_BAD_ARG, "forward: null input");
   if (!p->uploaded) return fail(R3D_ERR_STATE, "forward before r3d_plan_upload");
   if (batch < 0) return fail(R3D_ERR_BAD_ARG, "batch=%d", batch);
   if ((pos || sum) && !p->has_pos) return fail(R3D_ERR_BAD_ARG, "plan has no pose net but pos/sum output requested");
@@ -911,8 +912,8 @@ static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is
                        float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
   int rc = check_forward(p, src, pos, trj, sum, batch);
   if (rc) return rc;
-  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   if (batch == 0) return R3D_OK;
+  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -939,7 +940,7 @@ extern "C" R3D_API int r3d_forward_uv(r3d_plan* p, const float* uv, const float*
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv needs in_features == 3 (ray encoding, utils.py:91-96)");
   if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv derives param=[height,pitch]: extrinsic_dim must be 2");
-  if (!cam) return fail(R3D_ERR_BAD_ARG, "cam is null");
+  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
   return forward_dev(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, (cudaStream_t)stream);
 }
 
@@ -956,8 +957,8 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
                         float* pos, float* trj, float* sum, int batch) {
   int rc = check_forward(p, src, pos, trj, sum, batch);
   if (rc) return rc;
-  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   if (batch == 0) return R3D_OK;
+  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -1012,7 +1013,7 @@ extern "C" R3D_API int r3d_forward_uv_host(r3d_plan* p, const float* uv, const f
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv_host needs in_features == 3");
   if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim must be 2");
-  if (!cam) return fail(R3D_ERR_BAD_ARG, "cam is null");
+  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
   return forward_host(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch);
 }
 

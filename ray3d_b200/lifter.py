@@ -85,6 +85,8 @@ class Lifter:
             param = param.contiguous().float()
             assert param.shape == (x.shape[0], self.spec.extrinsic_dim)
         pos, trj, both = self._outputs(x.shape[0], x.device, want_pos, want_trj, want_sum)
+        if x.shape[0] == 0:
+            return pos, trj, both
         with torch.cuda.device(x.device):
             self.plan.forward_rays(_ptr(x), _ptr(param) if self.spec.camera_embedding else None, _ptr(pos), _ptr(trj),
                                    _ptr(both), x.shape[0], self._stream(x.device))
@@ -98,6 +100,8 @@ class Lifter:
         assert uv.shape[1] == self.spec.receptive_field and cam.shape == (uv.shape[0], 6)
         uv, cam = uv.contiguous().float(), cam.contiguous().float()
         pos, trj, both = self._outputs(uv.shape[0], uv.device, want_pos, want_trj, want_sum)
+        if uv.shape[0] == 0:
+            return pos, trj, both
         with torch.cuda.device(uv.device):
             self.plan.forward_uv(_ptr(uv), _ptr(cam), _ptr(pos), _ptr(trj), _ptr(both), uv.shape[0], self._stream(uv.device))
         return pos, trj, both

@@ -60,9 +60,11 @@ def test_camera_scalars_and_encodings():
     c = load_golden("camera")
     for i in range(6):
         pitch, height = O.camera_pitch_height(c[f"R{i}"], c[f"t{i}"])
-        assert pitch == float(c[f"pitch{i}"]) and height == float(c[f"height{i}"])
+        # libm / BLAS last-ulp behaviour is host dependent; identical on the box that wrote the fixture
+        assert abs(pitch - float(c[f"pitch{i}"])) <= 4 * np.spacing(abs(float(c[f"pitch{i}"])))
+        assert abs(height - float(c[f"height{i}"])) <= 4 * np.spacing(abs(float(c[f"height{i}"])))
         K = c[f"K{i}"]
-        ray = O.ray_encode(c[f"uv{i}"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], pitch)
+        ray = O.ray_encode(c[f"uv{i}"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], float(c[f"pitch{i}"]))
         assert np.array_equal(ray, c[f"ray{i}"])
         assert np.array_equal(O.normalize_screen_coordinates(c[f"uv{i}"], 1000, 1002), c[f"norm{i}"])
 
