@@ -114,6 +114,14 @@ R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* plan);  /* device bytes
 R3D_API int r3d_plan_receptive_field(const r3d_plan* plan);       /* rie.py:278-282 */
 R3D_API int r3d_plan_kernel_launches(const r3d_plan* plan);       /* kernels one forward enqueues */
 
+/* Per-launch device timing (benchmark instrumentation): when enabled every forward records CUDA events on the
+ * launch stream around each kernel.  r3d_plan_launch_times synchronises on the recorded events and returns the
+ * mean duration (ms) of each launch position over the recorded forwards (ring of the last 64).
+ * Position 0 is the input stage, the last is the output stage, the others the grouped GEMMs in graph order. */
+R3D_API int r3d_plan_set_profiling(r3d_plan* plan, int enable);
+R3D_API int r3d_plan_launch_times(r3d_plan* plan, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs);
+R3D_API const char* r3d_plan_launch_name(const r3d_plan* plan, int32_t index);
+
 /* --- forward: replaces nn.Module.forward(x, param) ------------------------------------------------
  * x_dev     (B, T, J, Cin) float32 contiguous, T == receptive field (rie.py:284-304; the reference
  *           only works for T == RF).

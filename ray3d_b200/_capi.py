@@ -48,6 +48,9 @@ EXPORTS = {
     "r3d_plan_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "r3d_plan_receptive_field": (C.c_int, [C.c_void_p]),
     "r3d_plan_kernel_launches": (C.c_int, [C.c_void_p]),
+    "r3d_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "r3d_plan_launch_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "r3d_plan_launch_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
     "r3d_forward_rays": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_forward_uv": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_forward_rays_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
@@ -187,6 +190,18 @@ class Plan:
     @property
     def kernel_launches(self) -> int:
         return int(lib().r3d_plan_kernel_launches(self._h))
+
+    def set_profiling(self, enable: bool) -> None:
+        check(lib().r3d_plan_set_profiling(self._h, 1 if enable else 0))
+
+    def launch_times(self):
+        """[(launch name, mean ms)] over the forwards recorded since set_profiling(True), and the number of runs."""
+        n, runs = C.c_int32(), C.c_int32()
+        check(lib().r3d_plan_launch_times(self._h, None, 0, C.byref(n), C.byref(runs)))
+        buf = (C.c_float * n.value)()
+        check(lib().r3d_plan_launch_times(self._h, buf, n.value, C.byref(n), C.byref(runs)))
+        names = [lib().r3d_plan_launch_name(self._h, i).decode() for i in range(n.value)]
+        return list(zip(names, [float(v) for v in buf])), runs.value
 
     # -- forward (raw pointers; torch-facing wrappers live in lifter.py / model.py) ------------------
     def forward_rays(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> None:

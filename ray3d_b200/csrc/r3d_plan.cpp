@@ -149,6 +149,10 @@ struct r3d_plan {
   struct EmbBind { int net; std::vector<std::pair<int, int>> dst; };
   std::vector<EmbBind> emb_binds;
   std::vector<int> m_a0;
+  // optional per-launch timing (r3d_plan_set_profiling): ring of event sets, one per forward chunk
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;                   // [kProfRing][nops + 3]
+  int prof_runs = 0;
   // host-call staging
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -653,7 +657,10 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
          ",\"slope\":" + sl + ",\"prob\":[";
     for (int q = 0; q < op.dev.nprob; ++q) {
       const auto& b = op.bind[q];
-      j += std::string(q ? "," : "") + "{\"a\":" + std::to_string(b.a) + ",\"a_ld\":" + std::to_string(b.a_ld) + ",\"layer\":\"" + b.layer +
+      const PackedLayer& pl = p->layers.at(b.layer);
+      j += std::string(q ? "," : "") + "{\"a\":" + std::to_string(b.a) + ",\"a_ld\":" + std::to_string(b.a_ld) + ",\"n\":" + std::to_string(pl.n) +
+           ",\"k\":" + std::to_string(pl.k) + ",\"n_pad\":" + std::to_string(pl.n_pad) + ",\"k_pad\":" + std::to_string(pl.k_pad) +
+           ",\"layer\":\"" + b.layer +
            "\",\"res\":" + std::to_string(b.res) + ",\"res_ld\":" + std::to_string(b.res_ld) + ",\"res_col\":" + std::to_string(b.res_col) +
            ",\"dst\":[";
       for (size_t d = 0; d < b.dst.size(); ++d)
@@ -706,6 +713,9 @@ static void free_device(r3d_plan* p) {
     if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
     p->ev_in[i] = p->ev_done[i] = nullptr;
   }
+  for (auto& e : p->prof_ev) cudaEventDestroy(e);
+  p->prof_ev.clear();
+  p->prof_runs = 0;
   if (p->s_copy) cudaStreamDestroy(p->s_copy);
   if (p->s_comp) cudaStreamDestroy(p->s_comp);
   p->d_weights = p->d_ws = p->d_desc = p->d_stage = nullptr;
@@ -879,12 +889,25 @@ static int ensure_capacity(r3d_plan* p, int batch) {
 
 // ---- forward -------------------------------------------------------------------------------------
 static constexpr int kMaxChunk = 8192;
+static constexpr int kProfRing = 64;
 
 static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
                      float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
   const int prec = p->cfg.precision;
+  const int nev = (int)p->ops.size() + 3;
+  cudaEvent_t* ev = nullptr;
+  if (p->profiling) {
+    if (p->prof_ev.empty()) {
+      p->prof_ev.resize((size_t)kProfRing * nev);
+      for (auto& e : p->prof_ev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    ev = p->prof_ev.data() + (size_t)(p->prof_runs % kProfRing) * nev;
+    ++p->prof_runs;
+    CUDA_TRY(cudaEventRecord(ev[0], s));
+  }
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, src, src_stride,
                            is_uv, prm, prm_stride, batch, s));
+  if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const GemmOpDev* d_op = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops) + i;
     const int M = batch * p->ops[i].dev.rows_per_seq;
@@ -892,8 +915,10 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
       CUDA_TRY(launch_gemm_ffma(d_op, p->ops[i].dev, M, s));
     else
       CUDA_TRY(launch_gemm_tc(d_op, p->ops[i].dev, p->d_desc + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes, M, prec, s));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2 + i], s));
   }
   CUDA_TRY(launch_assemble(reinterpret_cast<const AssembleDev*>(p->d_desc + p->off_asm), p->asmb, pos, trj, sum, batch, s));
+  if (ev) CUDA_TRY(cudaEventRecord(ev[nev - 1], s));
   return R3D_OK;
 }
 
@@ -1015,6 +1040,45 @@ extern "C" R3D_API int r3d_forward_uv_host(r3d_plan* p, const float* uv, const f
   if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim must be 2");
   if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
   return forward_host(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch);
+}
+
+extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  std::lock_guard<std::mutex> lk(p->mu);
+  p->profiling = enable != 0;
+  p->prof_runs = 0;
+  return R3D_OK;
+}
+
+extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  std::lock_guard<std::mutex> lk(p->mu);
+  const int nl = (int)p->ops.size() + 2, nev = nl + 1;
+  if (n_launches) *n_launches = nl;
+  const int runs = std::min(p->prof_runs, kProfRing);
+  if (n_runs) *n_runs = runs;
+  if (!ms_out || runs == 0) return R3D_OK;
+  std::vector<double> acc(nl, 0.0);
+  for (int r = 0; r < runs; ++r) {
+    cudaEvent_t* ev = p->prof_ev.data() + (size_t)r * nev;
+    CUDA_TRY(cudaEventSynchronize(ev[nev - 1]));
+    for (int i = 0; i < nl; ++i) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < nl && i < cap; ++i) ms_out[i] = (float)(acc[i] / runs);
+  return R3D_OK;
+}
+
+extern "C" R3D_API const char* r3d_plan_launch_name(const r3d_plan* p, int32_t i) {
+  if (!p) return "";
+  const int nl = (int)p->ops.size() + 2;
+  if (i == 0) return "input_stage";
+  if (i == nl - 1) return "output_stage";
+  if (i > 0 && i < nl - 1) return p->ops[i - 1].name.c_str();
+  return "";
 }
 
 extern "C" R3D_API int r3d_ray_encode_f64(const double* uv, double* ray, int64_t n, double fx, double fy, double ppx, double ppy,
