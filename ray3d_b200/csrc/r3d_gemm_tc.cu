@@ -30,12 +30,14 @@ namespace r3d {
 constexpr int TBM = 128;            // UMMA M (one TMEM lane per output row)
 constexpr int TBK = 64;             // K block: 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;            // 4 control warps + 8 epilogue warps
+constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 255) / 256 * 256;
+constexpr int kAuxBytes = 256 + kOpSmemBytes + 8 * 512 + 8 * 2048;   // barriers, descriptor, bias slices, store staging
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 __host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit) { return nsplit * (TBM + block_n) * TBK * 2; }
 __host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit) {
-  int s = (SMEM_LIMIT - 2048) / tc_stage_bytes(block_n, nsplit);
+  int s = (SMEM_LIMIT - 1024 - kAuxBytes) / tc_stage_bytes(block_n, nsplit);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
@@ -144,50 +146,64 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int tile, 
   return TileCoord{p, (tile / n_tiles) * TBM, (tile % n_tiles) * block_n};
 }
 
-__device__ __forceinline__ void split_store16(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
-  // 16 consecutive outputs -> 32 bytes per plane
-  uint32_t h[8], l[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-    if (lo != nullptr) {
-      const float2 hf = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-  }
-  reinterpret_cast<uint4*>(hi)[0] = make_uint4(h[0], h[1], h[2], h[3]);
-  reinterpret_cast<uint4*>(hi)[1] = make_uint4(h[4], h[5], h[6], h[7]);
-  if (lo != nullptr) {
-    reinterpret_cast<uint4*>(lo)[0] = make_uint4(l[0], l[1], l[2], l[3]);
-    reinterpret_cast<uint4*>(lo)[1] = make_uint4(l[4], l[5], l[6], l[7]);
-  }
-}
+// ---- epilogue helpers -------------------------------------------------------------------------------
+// Per-warp staging tile in shared memory: 32 rows x 64 bytes (one 32-column bf16 chunk), 16-byte units
+// XOR-swizzled so that both the row-per-thread access and the 4-lanes-per-row access are conflict free.
+__device__ __forceinline__ int stg_index(int row, int unit) { return row * 4 + (unit ^ ((row >> 1) & 3)); }
 
-__device__ __forceinline__ void add_residual16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* v) {
+// registers (thread = row, 32 bf16 packed in w[16]) -> coalesced global stores (4 lanes x 16 B per row)
+__device__ __forceinline__ void staged_store(uint4* stg, const uint32_t (&w)[16], int lane, int m_base, int M, const GemmProb& pr,
+                                             int n, bool lo_plane) {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi) + q);
-    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+  for (int u = 0; u < 4; ++u) stg[stg_index(lane, u)] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+  __syncwarp();
+  const int u = lane & 3;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-      v[q * 8 + 2 * j] += f.x;
-      v[q * 8 + 2 * j + 1] += f.y;
-    }
-    if (lo != nullptr) {
-      const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo) + q);
-      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[j]));
-        v[q * 8 + 2 * j] += f.x;
-        v[q * 8 + 2 * j + 1] += f.y;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 8 + (lane >> 2);
+    const uint4 val = stg[stg_index(r, u)];
+    const int row = m_base + r;
+    if (row < M) {
+      for (int t = 0; t < pr.ndst; ++t) {
+        const Dst& d = pr.dst[t];
+        if (d.f32) continue;
+        __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(lo_plane ? d.m.p1 : d.m.p0);
+        if (plane != nullptr) *reinterpret_cast<uint4*>(plane + (int64_t)row * d.m.ld + d.col + n + u * 8) = val;
       }
     }
   }
+  __syncwarp();
 }
+
+// coalesced global loads of one residual plane -> registers (thread = row), accumulated into v[32]
+__device__ __forceinline__ void staged_residual(uint4* stg, const __nv_bfloat16* plane, int ld, int col, int lane, int m_base, int M,
+                                                float (&v)[32]) {
+  const int u = lane & 3;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 8 + (lane >> 2);
+    const int row = m_base + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (row < M) val = __ldg(reinterpret_cast<const uint4*>(plane + (int64_t)row * ld + col + u * 8));
+    stg[stg_index(r, u)] = val;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int uu = 0; uu < 4; ++uu) {
+    const uint4 val = stg[stg_index(lane, uu)];
+    const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      v[uu * 8 + 2 * j] += f.x;
+      v[uu * 8 + 2 * j + 1] += f.y;
+    }
+  }
+  __syncwarp();
+}
+
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 4;
 
 template <int BLOCK_N, int NSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
@@ -197,21 +213,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT);
   constexpr int TMEM_COLS = tc_tmem_cols(BLOCK_N);
   constexpr int CH = BLOCK_N >= 32 ? 32 : 16;         // epilogue column chunk
+  constexpr int NCHUNK = BLOCK_N / CH;
+  constexpr int COL_SPLIT = NCHUNK >= 2 ? 2 : 1;      // two epilogue warps share a TMEM lane quarter when possible
+  constexpr int CHUNKS_PER_WARP = NCHUNK / COL_SPLIT;
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* aux = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
+  float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes);             // [EPI_WARPS][128]
+  uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes + EPI_WARPS * 512);   // [EPI_WARPS][128 x 16 B]
 
-  const GemmOpDev& op = *opp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + TBM - 1) / TBM;
 
+  {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(opp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sop);
+    for (int i = threadIdx.x; i < (int)(sizeof(GemmOpDev) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -219,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -231,6 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const GemmOpDev& op = *sop;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -291,58 +319,109 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= EPI_WARP0) {
     // =============================== epilogue ===============================
+    const int ew = warp - EPI_WARP0;
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                                 // which half of the columns
+    const bool active = half < COL_SPLIT;
+    float* my_bias = bias_s + ew * 128;
+    uint4* my_stage = stage_s + ew * 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float slope = op.slope;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
       const GemmProb& pr = op.prob[tc.p];
-      const int row = tc.m0 + q * 32 + lane;
+      const int m_base = tc.m0 + q * 32;
+      const int row = m_base + lane;
       const bool row_ok = row < M;
+      const int c_begin = half * CHUNKS_PER_WARP;
+      if (active) {   // this warp's slice of the folded bias -> smem (overlaps the wait for the accumulator)
+        __syncwarp();
+        for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(pr.bias + tc.n0 + c_begin * CH + j);
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (active) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / CH; ++c) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * CH);
-        if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
-        tmem_ld_wait();
-        const int n = tc.n0 + c * CH;
-        if (row_ok && n < pr.N) {
-          float v[CH];
+        for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+          const int c = c_begin + cc;
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * CH);
+          if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          const int n = tc.n0 + c * CH;
+          if (n < pr.N) {          // warp-uniform
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            float x = __uint_as_float(r[j]) + __ldg(pr.bias + n + j);
-            v[j] = x > 0.f ? x : slope * x;
-          }
-          if (pr.res.p0 != nullptr) {
-            const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
+            for (int j4 = 0; j4 < CH / 4; ++j4) {
+              const float4 b = *reinterpret_cast<const float4*>(my_bias + cc * CH + j4 * 4);
+              const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int h = 0; h < CH / 16; ++h)
-              add_residual16(reinterpret_cast<const __nv_bfloat16*>(pr.res.p0) + ro + h * 16,
-                             pr.res.p1 ? reinterpret_cast<const __nv_bfloat16*>(pr.res.p1) + ro + h * 16 : nullptr, v + h * 16);
-          }
-          for (int t = 0; t < pr.ndst; ++t) {
-            const Dst& d = pr.dst[t];
-            const int64_t o = (int64_t)row * d.m.ld + d.col + n;
-            if (d.f32) {
-              float* out = reinterpret_cast<float*>(d.m.p0) + o;
-              if (n + CH <= pr.N && ((d.m.ld | d.col) & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
+              for (int j = 0; j < 4; ++j) {
+                const float x = __uint_as_float(r[j4 * 4 + j]) + bb[j];
+                v[j4 * 4 + j] = x > 0.f ? x : slope * x;
+              }
+            }
+            if (pr.res.p0 != nullptr) {
+              if (CH == 32) {
+                staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
+                if (pr.res.p1 != nullptr)
+                  staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p1), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
+              } else if (row_ok) {
+                const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
+                for (int j = 0; j < CH; ++j) {
+                  v[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.res.p0)[ro + j]);
+                  if (pr.res.p1 != nullptr) v[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.res.p1)[ro + j]);
+                }
+              }
+            }
+            bool any_f32 = false, any_bf = false, any_lo = false;
+            for (int t = 0; t < pr.ndst; ++t) {
+              any_f32 |= pr.dst[t].f32 != 0;
+              any_bf |= pr.dst[t].f32 == 0;
+              any_lo |= pr.dst[t].f32 == 0 && pr.dst[t].m.p1 != nullptr;
+            }
+            if (any_f32 && row_ok) {      // network outputs (tiny): direct masked stores
+              for (int t = 0; t < pr.ndst; ++t) {
+                const Dst& d = pr.dst[t];
+                if (!d.f32) continue;
+                float* out = reinterpret_cast<float*>(d.m.p0) + (int64_t)row * d.m.ld + d.col + n;
 #pragma unroll
                 for (int j = 0; j < CH; ++j)
                   if (n + j < pr.N) out[j] = v[j];
               }
-            } else {
-              __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.m.p0) + o;
-              __nv_bfloat16* lo = d.m.p1 ? reinterpret_cast<__nv_bfloat16*>(d.m.p1) + o : nullptr;
+            }
+            if (any_bf) {
+              uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int h = 0; h < CH / 16; ++h) split_store16(hi + h * 16, lo ? lo + h * 16 : nullptr, v + h * 16);
+              for (int j = 0; j < CH / 2; ++j) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              if (CH == 32) {
+                staged_store(my_stage, hi, lane, m_base, M, pr, n, false);
+                if (any_lo) staged_store(my_stage, lo, lane, m_base, M, pr, n, true);
+              } else if (row_ok) {
+                for (int t = 0; t < pr.ndst; ++t) {
+                  const Dst& d = pr.dst[t];
+                  if (d.f32) continue;
+                  const int64_t o = (int64_t)row * d.m.ld + d.col + n;
+                  uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.m.p0) + o);
+                  ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                  if (d.m.p1 != nullptr) {
+                    uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.m.p1) + o);
+                    pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                  }
+                }
+              }
             }
           }
         }
@@ -419,7 +498,7 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
 }
 
 template <int BN, int NS>
-static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_bytes(BN, NS) + 1024 /*align*/ + 256 /*barriers*/; }
+static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_bytes(BN, NS) + 1024 /*align*/ + kAuxBytes; }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {

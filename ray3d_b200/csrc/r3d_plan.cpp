@@ -106,6 +106,8 @@ struct MatReq {          // one activation matrix in the workspace slab
 struct OpHost {
   GemmOpDev dev;                         // pointers filled by bind_workspace()
   std::string name;
+  bool side = false;                     // runs on the side stream (independent of the temporal tree)
+  bool join_before = false;              // first op that consumes side-stream results
   // symbolic bindings resolved to pointers once the slabs exist
   struct Bind { int a = -1, a_ld = 0, res = -1, res_ld = 0, res_col = 0; std::string layer;
                 std::vector<std::pair<int, int>> dst; std::vector<int> dst_f32; };
@@ -151,10 +153,12 @@ struct r3d_plan {
   std::vector<int> m_a0;
   // optional per-launch timing (r3d_plan_set_profiling): ring of event sets, one per forward chunk
   bool profiling = false;
+  bool use_side_stream = true;
   std::vector<cudaEvent_t> prof_ev;                   // [kProfRing][nops + 3]
   int prof_runs = 0;
   // host-call staging
-  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   char* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -470,9 +474,14 @@ static void build_graph(r3d_plan* p) {
   }
 
   // --- FC chains.  Hidden buffers: 3 x [B][1024] per problem slot, shared by successive chains.
-  int hb[3][kMaxProb];
+  // GlobalInfo runs on the side stream concurrently with the tree / fuse chains, so it owns its own set.
+  int hb_main[3][kMaxProb], hb_side[3][kMaxProb];
   for (int j = 0; j < 3; ++j)
-    for (int q = 0; q < kMaxProb; ++q) hb[j][q] = add_mat(p, 1, kFcWidth);
+    for (int q = 0; q < kMaxProb; ++q) {
+      hb_main[j][q] = add_mat(p, 1, kFcWidth);
+      hb_side[j][q] = q < 2 ? add_mat(p, 1, kFcWidth) : -1;
+    }
+  int (*hb)[kMaxProb] = hb_main;
   struct Chain { std::string key; int a; int a_ld; int nblocks; std::vector<std::pair<int, int>> dst; bool f32; };
   auto fc_chain = [&](const std::string& name, std::vector<Chain>& ch) {
     const int n = (int)ch.size();
@@ -518,7 +527,11 @@ static void build_graph(r3d_plan* p) {
       for (int q = 0; q < ntb; ++q) if (p->tbs[q].net == 1) c.dst.push_back({m_feat[q], L});
       ch.push_back(c);
     }
+    const size_t first = p->ops.size();
+    hb = hb_side;
     fc_chain("GlobalInfo", ch);
+    hb = hb_main;
+    for (size_t i = first; i < p->ops.size(); ++i) p->ops[i].side = true;   // depends only on the input stage
   }
   if (fuse) {                                                                            // rie.py:388-394
     std::vector<Chain> ch;
@@ -532,7 +545,9 @@ static void build_graph(r3d_plan* p) {
       const std::string key = tb.net == 0 ? std::string("0:Integration_") + kGroupNames[tb.group] : std::string("1:Integration");
       ch.push_back({key, m_feat[q], p->mats[m_feat[q]].ld, 1, {{p->m_heads[tb.head], 0}}, true});
     }
+    const size_t first = p->ops.size();
     fc_chain("Integration", ch);
+    p->ops[first].join_before = true;                                          // needs x_global from the side stream
   }
 
   // --- embedder destinations (rie.py:375-380, 395-401, :549-551)
@@ -718,6 +733,10 @@ static void free_device(r3d_plan* p) {
   p->prof_runs = 0;
   if (p->s_copy) cudaStreamDestroy(p->s_copy);
   if (p->s_comp) cudaStreamDestroy(p->s_comp);
+  if (p->s_side) cudaStreamDestroy(p->s_side);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  p->s_side = nullptr; p->ev_fork = p->ev_join = nullptr;
   p->d_weights = p->d_ws = p->d_desc = p->d_stage = nullptr;
   p->s_copy = p->s_comp = nullptr;
   p->ws_bytes = p->stage_bytes = 0;
@@ -770,6 +789,9 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
@@ -894,7 +916,7 @@ static constexpr int kProfRing = 64;
 static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
                      float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
   const int prec = p->cfg.precision;
-  const int nev = (int)p->ops.size() + 3;
+  const int nl = (int)p->ops.size() + 2, nev = 2 * nl;      // start/end event per launch
   cudaEvent_t* ev = nullptr;
   if (p->profiling) {
     if (p->prof_ev.empty()) {
@@ -908,15 +930,40 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, src, src_stride,
                            is_uv, prm, prm_stride, batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
+  // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
+  // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.
+  const bool use_side = p->use_side_stream;
+  bool forked = false;
   for (size_t i = 0; i < p->ops.size(); ++i) {
+    const OpHost& oh = p->ops[i];
     const GemmOpDev* d_op = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops) + i;
-    const int M = batch * p->ops[i].dev.rows_per_seq;
+    const int M = batch * oh.dev.rows_per_seq;
+    cudaStream_t st = s;
+    if (use_side && oh.side) {
+      if (!forked) {
+        CUDA_TRY(cudaEventRecord(p->ev_fork, s));      // recorded right after the input stage in stream order
+        CUDA_TRY(cudaStreamWaitEvent(p->s_side, p->ev_fork, 0));
+        forked = true;
+      }
+      st = p->s_side;
+    }
+    if (use_side && oh.join_before && forked) {
+      CUDA_TRY(cudaEventRecord(p->ev_join, p->s_side));
+      CUDA_TRY(cudaStreamWaitEvent(s, p->ev_join, 0));
+      forked = false;
+    }
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (i + 1)], st));
     if (prec == R3D_PREC_FP32)
-      CUDA_TRY(launch_gemm_ffma(d_op, p->ops[i].dev, M, s));
+      CUDA_TRY(launch_gemm_ffma(d_op, oh.dev, M, st));
     else
-      CUDA_TRY(launch_gemm_tc(d_op, p->ops[i].dev, p->d_desc + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes, M, prec, s));
-    if (ev) CUDA_TRY(cudaEventRecord(ev[2 + i], s));
+      CUDA_TRY(launch_gemm_tc(d_op, oh.dev, p->d_desc + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes, M, prec, st));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (i + 1) + 1], st));
   }
+  if (forked) {
+    CUDA_TRY(cudaEventRecord(p->ev_join, p->s_side));
+    CUDA_TRY(cudaStreamWaitEvent(s, p->ev_join, 0));
+  }
+  if (ev) CUDA_TRY(cudaEventRecord(ev[nev - 2], s));
   CUDA_TRY(launch_assemble(reinterpret_cast<const AssembleDev*>(p->d_desc + p->off_asm), p->asmb, pos, trj, sum, batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[nev - 1], s));
   return R3D_OK;
@@ -1053,7 +1100,7 @@ extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
 extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   std::lock_guard<std::mutex> lk(p->mu);
-  const int nl = (int)p->ops.size() + 2, nev = nl + 1;
+  const int nl = (int)p->ops.size() + 2, nev = 2 * nl;
   if (n_launches) *n_launches = nl;
   const int runs = std::min(p->prof_runs, kProfRing);
   if (n_runs) *n_runs = runs;
@@ -1064,7 +1111,7 @@ extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t
     CUDA_TRY(cudaEventSynchronize(ev[nev - 1]));
     for (int i = 0; i < nl; ++i) {
       float ms = 0.f;
-      CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      CUDA_TRY(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
       acc[i] += ms;
     }
   }
