@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "r3d_internal.h"
@@ -86,6 +87,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -98,6 +115,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -135,15 +157,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 struct TileCoord {
   int p, m0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int tile, int m_tiles, int block_n) {
+// Work unit -> (problem, m tile, n tile).  With clusters a unit covers `cl` consecutive m tiles (one per CTA of the
+// cluster) that share the same W tile, which is what the TMA multicast exploits.
+__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int m_groups, int block_n, int cl, int rank) {
   int p = 0, n_tiles = 1;
   for (;; ++p) {
     n_tiles = op.prob[p].n_pad / block_n;
-    const int cnt = m_tiles * n_tiles;
-    if (tile < cnt) break;
-    tile -= cnt;
+    const int cnt = m_groups * n_tiles;
+    if (unit < cnt) break;
+    unit -= cnt;
   }
-  return TileCoord{p, (tile / n_tiles) * TBM, (tile % n_tiles) * block_n};
+  return TileCoord{p, ((unit / n_tiles) * cl + rank) * TBM, (unit % n_tiles) * block_n};
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------------------
@@ -205,7 +229,7 @@ __device__ __forceinline__ void staged_residual(uint4* stg, const __nv_bfloat16*
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 
-template <int BLOCK_N, int NSPLIT>
+template <int BLOCK_N, int NSPLIT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
                                                                 int M, int total_tiles) {
   constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT);
@@ -232,7 +256,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes + EPI_WARPS * 512);   // [EPI_WARPS][128 x 16 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (M + TBM - 1) / TBM;
+  const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA loads (and multicasts)
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(opp);
@@ -242,7 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);                             // every CTA of the cluster must have consumed the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -256,6 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const GemmOpDev& op = *sop;
@@ -265,8 +294,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -274,10 +303,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0);
-          tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0);
-          if (NSPLIT == 2) {
-            tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0);
-            tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0);
+          if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0);
+          if (CL == 1) {
+            tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0);
+            if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0);
+          } else {   // this CTA fetches 1/CL of the W tile and multicasts it to every CTA of the cluster
+            const int wrow = tc.n0 + crank * W_PART_ROWS, woff = crank * W_PART_ROWS * TBK * 2;
+            tma_load_2d_mc(st + NSPLIT * A_BYTES + woff, tm + 4, &full_bar[stage], kb * TBK, wrow, MC_MASK);
+            if (NSPLIT == 2) tma_load_2d_mc(st + 2 * A_BYTES + W_BYTES + woff, tm + 5, &full_bar[stage], kb * TBK, wrow, MC_MASK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -290,8 +323,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
         const int nkb = op.prob[tc.p].K / TBK;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
@@ -311,7 +344,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
               umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
             }
           }
-          umma_commit(&empty_bar[stage]);                     // smem stage free once these MMAs retire
+          if (CL == 1) umma_commit(&empty_bar[stage]);        // smem stage free once these MMAs retire
+          else umma_commit_mc(&empty_bar[stage], MC_MASK);     // ... in every CTA the multicast writes into
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);    // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -330,8 +364,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     int acc = 0;
     uint32_t acc_phase = 0;
     const float slope = op.slope;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N);
+    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+      const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
       const GemmProb& pr = op.prob[tc.p];
       const int m_base = tc.m0 + q * 32;
       const int row = m_base + lane;
@@ -435,6 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA exits while a peer may still multicast into its smem
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -493,6 +528,13 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
     rc = encode_2d(out + p * kTmapsPerProb + 3, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
                    (uint64_t)g.K, (uint32_t)bn);
     if (rc) return rc;
+    if (bn >= 32) {   // half-tile W maps for the 2-CTA multicast variant
+      rc = encode_2d(out + p * kTmapsPerProb + 4, g.w0, (uint64_t)g.K, (uint64_t)g.n_pad, (uint64_t)g.K, (uint32_t)bn / 2);
+      if (rc) return rc;
+      rc = encode_2d(out + p * kTmapsPerProb + 5, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
+                     (uint64_t)g.K, (uint32_t)bn / 2);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
@@ -502,10 +544,14 @@ static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_b
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
+  if (e != cudaSuccess) return e;
+  if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, (BN >= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
+  return e;
 }
 
 static int g_num_sms = 0;
+static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
 
 cudaError_t tc_configure() {
   cudaError_t e;
@@ -514,30 +560,53 @@ cudaError_t tc_configure() {
   if ((e = configure_one<BN, 2>()) != cudaSuccess) return e;
   R3D_CFG(16) R3D_CFG(32) R3D_CFG(64) R3D_CFG(128) R3D_CFG(256)
 #undef R3D_CFG
+  if (const char* env = getenv("R3D_TC_CLUSTER")) g_cluster_mode = atoi(env);
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   return cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
+
 template <int BN, int NS>
-static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps, int M, int tiles, cudaStream_t s) {
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN, NS><<<grid, TC_THREADS, tc_smem_bytes<BN, NS>(), s>>>(d_op, d_tmaps, M, tiles);
-  return cudaGetLastError();
+static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps, int M, const GemmOpDev& h, cudaStream_t s) {
+  const int m_tiles = (M + TBM - 1) / TBM;
+  constexpr int CL2 = BN >= 32 ? 2 : 1;
+  const bool use_cl = CL2 == 2 && g_cluster_mode && m_tiles >= 2;
+  const int cl = use_cl ? 2 : 1;
+  const int m_groups = (m_tiles + cl - 1) / cl;
+  int units = 0;
+  for (int p = 0; p < h.nprob; ++p) units += m_groups * (h.prob[p].n_pad / BN);
+  if (!use_cl) {
+    const int grid = units < g_num_sms ? units : g_num_sms;
+    gemm_tc_kernel<BN, NS, 1><<<grid, TC_THREADS, tc_smem_bytes<BN, NS>(), s>>>(d_op, d_tmaps, M, units);
+    return cudaGetLastError();
+  }
+  const int max_clusters = g_num_sms / 2;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = tc_smem_bytes<BN, NS>();
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2>, d_op, d_tmaps, M, units);
 }
 
 cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h, const void* d_tmaps, int M, int precision, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
   if (g_num_sms <= 0) return cudaErrorNotReady;
   const int bn = tc_block_n(h);
-  const int m_tiles = (M + TBM - 1) / TBM;
-  int tiles = 0;
-  for (int p = 0; p < h.nprob; ++p) tiles += m_tiles * (h.prob[p].n_pad / bn);
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(d_tmaps);
   const int ns = precision == R3D_PREC_BF16X3 ? 2 : 1;
 #define R3D_LAUNCH(BN)                                                             \
   case BN:                                                                         \
-    return ns == 2 ? launch_one<BN, 2>(d_op, tm, M, tiles, s) : launch_one<BN, 1>(d_op, tm, M, tiles, s);
+    return ns == 2 ? launch_one<BN, 2>(d_op, tm, M, h, s) : launch_one<BN, 1>(d_op, tm, M, h, s);
   switch (bn) {
     R3D_LAUNCH(16) R3D_LAUNCH(32) R3D_LAUNCH(64) R3D_LAUNCH(128) R3D_LAUNCH(256)
     default: return cudaErrorInvalidValue;

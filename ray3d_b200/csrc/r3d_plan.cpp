@@ -1187,6 +1187,13 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   CUDA_TRY(cudaMemcpy(dWh, Wh.data(), nw * nprob * 2, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dWl, Wl.data(), nw * nprob * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(dRh, Rh.data(), nc * nprob * 2, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dRl, Rl.data(), nc * nprob * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(dC0, 0, nc * nprob * 4)); CUDA_TRY(cudaMemset(dC1, 0, nc * nprob * 4));
+  // the tensor path writes its result the way the network does: bf16 hi (+lo) planes when n is a multiple of 32
+  const bool bf_dst = n % 32 == 0;
+  uint16_t *dOh = nullptr, *dOl = nullptr;
+  if (bf_dst) {
+    CUDA_TRY(cudaMalloc(&dOh, nc * nprob * 2)); CUDA_TRY(cudaMalloc(&dOl, nc * nprob * 2));
+    CUDA_TRY(cudaMemset(dOh, 0, nc * nprob * 2)); CUDA_TRY(cudaMemset(dOl, 0, nc * nprob * 2));
+  }
   GemmOpDev f{}, t{};
   f.nprob = t.nprob = nprob; f.rows_per_seq = t.rows_per_seq = 1; f.slope = t.slope = 0.2f; f.n_tile = t.n_tile = pick_n_tile(n);
   for (int q = 0; q < nprob; ++q) {
@@ -1200,6 +1207,7 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
     b.w0 = dWh + q * nw; b.w1 = precision == R3D_PREC_BF16X3 ? dWl + q * nw : nullptr;
     b.res = Mat{dRh + q * nc, precision == R3D_PREC_BF16X3 ? dRl + q * nc : nullptr, n, 0};
     b.dst[0] = Dst{Mat{dC1 + q * nc, nullptr, n, 0}, 0, 1};
+    if (bf_dst) b.dst[0] = Dst{Mat{dOh + q * nc, precision == R3D_PREC_BF16X3 ? dOl + q * nc : nullptr, n, 0}, 0, 0};
   }
   GemmOpDev *dF, *dT;
   void* dMaps;
@@ -1230,6 +1238,12 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   std::vector<float> c0(nc * nprob), c1(nc * nprob);
   CUDA_TRY(cudaMemcpy(c0.data(), dC0, nc * nprob * 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(c1.data(), dC1, nc * nprob * 4, cudaMemcpyDeviceToHost));
+  if (bf_dst) {
+    std::vector<uint16_t> oh(nc * nprob), ol(nc * nprob);
+    CUDA_TRY(cudaMemcpy(oh.data(), dOh, nc * nprob * 2, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ol.data(), dOl, nc * nprob * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < c1.size(); ++i) c1[i] = bf2f(oh[i]) + (precision == R3D_PREC_BF16X3 ? bf2f(ol[i]) : 0.f);
+  }
   double mx = 0, md = 0;
   for (size_t i = 0; i < c0.size(); ++i) {
     mx = std::max(mx, (double)std::fabs(c0[i]));
@@ -1238,7 +1252,7 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   }
   if (rel_err) *rel_err = md / std::max(mx, 1e-30);
   for (void* q : {(void*)dA, (void*)dW, (void*)dB, (void*)dR, (void*)dC0, (void*)dC1, (void*)dAh, (void*)dAl, (void*)dWh, (void*)dWl,
-                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps})
+                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps, (void*)dOh, (void*)dOl})
     cudaFree(q);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return R3D_OK;

@@ -83,16 +83,38 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PrologueDev* __rest
   __syncthreads();
 
   // ---- 2. first-layer A matrices: row (b, tq), column kk = tap*Cg + channel --------------------
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  // One thread produces 8 consecutive columns (k_pad is a multiple of 64) => 16-byte stores per bf16 plane
+  // (32-byte for fp32), consecutive threads write consecutive 16-byte units of the same row.
   for (int p = 0; p < d.nprob; ++p) {
     const PrologueProb& pr = d.prob[p];
-    const int kp = pr.k_pad;
-    for (int tq = warp; tq < d.L0; tq += nwarp) {
-      const int64_t row = (int64_t)b * d.L0 + tq;
-      for (int kk = lane * 2; kk < kp; kk += 64) {
-        const int2 e = __ldg(reinterpret_cast<const int2*>(pr.tab + kk));
-        store_act2(pr.a0, precision, row, kk, tab_value(e.x, xs, JC, d.tc, d.w0, tq),
-                   tab_value(e.y, xs, JC, d.tc, d.w0, tq));
+    const int units = pr.k_pad >> 3;
+    const int total = d.L0 * units;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int tq = i / units, kk = (i - tq * units) << 3;
+      const int4 e0 = __ldg(reinterpret_cast<const int4*>(pr.tab + kk));
+      const int4 e1 = __ldg(reinterpret_cast<const int4*>(pr.tab + kk + 4));
+      const int ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tab_value(ee[j], xs, JC, d.tc, d.w0, tq);
+      const int64_t idx = ((int64_t)b * d.L0 + tq) * pr.a0.ld + kk;
+      if (precision == R3D_PREC_FP32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.a0.p0) + idx);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+          const float2 hf = __bfloat1622float2(hh);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+          l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p0) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (precision == R3D_PREC_BF16X3)
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p1) + idx) = make_uint4(l[0], l[1], l[2], l[3]);
       }
     }
   }

@@ -191,4 +191,7 @@ def test_tensor_core_gemm_selftest(precision):
     for m, n, k, npb in [(128, 256, 64, 1), (300, 256, 768, 2), (1024, 1024, 1024, 1), (81 * 8, 256, 192, 6),
                          (37, 16, 1024, 3), (256, 256, 256, 6), (5, 1024, 576, 2)]:
         err, ms_tc, ms_ff = _capi.selftest_gemm(m, n, k, npb, precision)
-        assert err < (2e-5 if precision == "bf16x3" else 1e-5), (m, n, k, npb, err)
+        # outputs are stored as the network stores them: bf16 hi+lo planes (16 mantissa bits) for bf16x3, one bf16
+        # plane for the bf16 precision (when n % 32 == 0), fp32 otherwise
+        tol = 2e-5 if precision == "bf16x3" else (6e-3 if n % 32 == 0 else 1e-5)
+        assert err < tol, (m, n, k, npb, err)
