@@ -94,6 +94,10 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap,
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -294,11 +298,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch cursor: runs PF_DIST K blocks ahead of the loads (across tile boundaries).  The smem ring is
+      // only 2-3 stages deep for the 3-product tiles, far too shallow to cover HBM latency for the A operand
+      // (activations stream from HBM; W is L2 resident), so the stream is pulled into L2 early.
+      constexpr int PF_DIST = 6;
+      int pf_tile = unit0, pf_kb = 0, pf_nkb = 0, pf_m0 = 0, pf_p = 0, pf_ahead = 0;
+      if (pf_tile < total_tiles) {
+        const TileCoord t0 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank);
+        pf_p = t0.p; pf_m0 = t0.m0; pf_nkb = op.prob[t0.p].K / TBK;
+      }
+      auto prefetch_step = [&]() {
+        if (pf_tile >= total_tiles) return;
+        const CUtensorMap* tm = tmaps + pf_p * kTmapsPerProb;
+        tma_prefetch_2d(tm + 0, pf_kb * TBK, pf_m0);
+        if (NSPLIT == 2) tma_prefetch_2d(tm + 1, pf_kb * TBK, pf_m0);
+        if (++pf_kb == pf_nkb) {
+          pf_kb = 0;
+          pf_tile += unit_step;
+          if (pf_tile < total_tiles) {
+            const TileCoord t1 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank);
+            pf_p = t1.p; pf_m0 = t1.m0; pf_nkb = op.prob[t1.p].K / TBK;
+          }
+        }
+      };
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         for (int kb = 0; kb < nkb; ++kb) {
+          while (pf_ahead < PF_DIST + 1) { prefetch_step(); ++pf_ahead; }
+          --pf_ahead;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
