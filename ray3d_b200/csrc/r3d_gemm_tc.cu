@@ -203,31 +203,42 @@ __device__ __forceinline__ void staged_store(uint4* stg, const uint32_t (&w)[16]
   __syncwarp();
 }
 
-// coalesced global loads of one residual plane -> registers (thread = row), accumulated into v[32]
-__device__ __forceinline__ void staged_residual(uint4* stg, const __nv_bfloat16* plane, int ld, int col, int lane, int m_base, int M,
-                                                float (&v)[32]) {
+// coalesced global loads of the residual planes (both issued before any use, so their HBM latencies overlap)
+// -> registers (thread = row), accumulated into v[32]
+__device__ __forceinline__ void staged_residual(uint4* stg, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int col, int lane,
+                                                int m_base, int M, float (&v)[32]) {
   const int u = lane & 3;
+  uint4 vh[4], vl[4];
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
-    const int r = pass * 8 + (lane >> 2);
-    const int row = m_base + r;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (row < M) val = __ldg(reinterpret_cast<const uint4*>(plane + (int64_t)row * ld + col + u * 8));
-    stg[stg_index(r, u)] = val;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int uu = 0; uu < 4; ++uu) {
-    const uint4 val = stg[stg_index(lane, uu)];
-    const uint32_t w[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-      v[uu * 8 + 2 * j] += f.x;
-      v[uu * 8 + 2 * j + 1] += f.y;
+    const int row = m_base + pass * 8 + (lane >> 2);
+    vh[pass] = make_uint4(0, 0, 0, 0);
+    vl[pass] = make_uint4(0, 0, 0, 0);
+    if (row < M) {
+      const int64_t o = (int64_t)row * ld + col + u * 8;
+      vh[pass] = __ldg(reinterpret_cast<const uint4*>(hi + o));
+      if (lo != nullptr) vl[pass] = __ldg(reinterpret_cast<const uint4*>(lo + o));
     }
   }
-  __syncwarp();
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (plane == 1 && lo == nullptr) break;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) stg[stg_index(pass * 8 + (lane >> 2), u)] = plane ? vl[pass] : vh[pass];
+    __syncwarp();
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu) {
+      const uint4 val = stg[stg_index(lane, uu)];
+      const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        v[uu * 8 + 2 * j] += f.x;
+        v[uu * 8 + 2 * j + 1] += f.y;
+      }
+    }
+    __syncwarp();
+  }
 }
 
 constexpr int EPI_WARPS = 8;
@@ -246,8 +257,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   constexpr int CHUNKS_PER_WARP = NCHUNK / COL_SPLIT;
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
 
+  // NB: every pointer below is derived from smem_raw by constant offsets so the compiler keeps the shared address
+  // space (LDS/STS); round-tripping through uintptr_t to align by hand degrades them to generic LD/ST.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();      // 128B-swizzled operand tiles need a 1024-byte aligned base
   uint8_t* aux = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
   uint64_t* full_bar = bars;                    // [STAGES]
@@ -430,9 +444,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             }
             if (pr.res.p0 != nullptr) {
               if (CH == 32) {
-                staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
-                if (pr.res.p1 != nullptr)
-                  staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p1), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
+                staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0),
+                                reinterpret_cast<const __nv_bfloat16*>(pr.res.p1), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
               } else if (row_ok) {
                 const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
                 for (int j = 0; j < CH; ++j) {

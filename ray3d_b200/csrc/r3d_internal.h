@@ -54,14 +54,15 @@ struct GemmOpDev {
 };
 
 // ---- input stage --------------------------------------------------------------------------------
-// tab entry for column kk of a problem's first-layer A matrix:
-//   bits 0..7 source channel (j*Cin+c), 8..9 part (0 x, 1 x-root, 2 x-x[tc]), 10..15 tap k,
-//   16..17 coordinate c (root channel); -1 => zero padding column.
+// Gather table of a problem's first-layer A matrix, one int2 per column kk:
+//   .x = offset of the minuend in the smem window, bit 30 set => relative to the row base (tq*w0*JC)
+//   .y = offset of the subtrahend, bit 30 set => relative to the row base; the zero slot (index T*JC) otherwise
+// (host-side semantic form: source channel j*Cin+c, part {x, x-root, x-x[tc]}, tap -- see r3d_plan.cpp)
 struct PrologueProb {
   Mat a0;
-  const int32_t* tab;
+  const int2* tab;
   int32_t k_pad;
-  int32_t _pad;
+  int32_t unit_begin;    // first 8-column unit of this problem in the flattened unit list
 };
 
 struct EmbedDev {

@@ -607,7 +607,7 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
     l.off_b = take(l.b.size() * 4);
   }
   p->tab_off.clear();
-  for (auto& t : p->tabs) p->tab_off.push_back(take(t.size() * 4));
+  for (auto& t : p->tabs) p->tab_off.push_back(take(t.size() * 8));   // device form: int2 per column
   p->weight_bytes = off;
   p->finalized = true;
   p->uploaded = false;
@@ -783,7 +783,26 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
     }
     memcpy(slab.data() + l.off_b, l.b.data(), l.b.size() * 4);
   }
-  for (size_t i = 0; i < p->tabs.size(); ++i) memcpy(slab.data() + p->tab_off[i], p->tabs[i].data(), p->tabs[i].size() * 4);
+  // Device form of the gather tables: per column {main offset, sub code} into the smem window, both relative to
+  // the row base rb = tq*w0*JC unless bit 30 of the sub code is clear (absolute: x[tc] term).  value = xs[rb+main] -
+  // xs[(rel ? rb : 0) + sub]; columns without a subtrahend (part 0) and padding columns subtract / reference the
+  // shared zero slot at index T*JC.
+  for (size_t i = 0; i < p->tabs.size(); ++i) {
+    int32_t* dt = reinterpret_cast<int32_t*>(slab.data() + p->tab_off[i]);
+    const int zero_slot = p->T * p->JC;
+    for (size_t kk = 0; kk < p->tabs[i].size(); ++kk) {
+      const int32_t e = p->tabs[i][kk];
+      int32_t main_off = zero_slot, main_abs = 1, sub = zero_slot, rel = 0;
+      if (e >= 0) {
+        const int src = e & 0xff, part = (e >> 8) & 3, tap = (e >> 10) & 63, c = (e >> 16) & 3;
+        main_off = tap * p->JC + src; main_abs = 0;
+        if (part == 1) { sub = tap * p->JC + c; rel = 1; }
+        else if (part == 2) { sub = p->tc * p->JC + src; rel = 0; }
+      }
+      dt[2 * kk + 0] = main_off | (main_abs ? 0 : (1 << 30));
+      dt[2 * kk + 1] = sub | (rel << 30);
+    }
+  }
   CUDA_TRY(cudaMemcpy(p->d_weights, slab.data(), p->weight_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(prologue_configure(200 * 1024 + 1024));
   if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
@@ -858,8 +877,9 @@ static int bind_workspace(r3d_plan* p, int cap) {
   pd.nprob = (int)p->tbs.size();
   for (int q = 0; q < pd.nprob; ++q) {
     pd.prob[q].a0 = mat(p->m_a0[q], 0);
-    pd.prob[q].tab = reinterpret_cast<const int32_t*>(p->d_weights + p->tab_off[q]);
+    pd.prob[q].tab = reinterpret_cast<const int2*>(p->d_weights + p->tab_off[q]);
     pd.prob[q].k_pad = p->mats[p->m_a0[q]].ld;
+    pd.prob[q].unit_begin = q == 0 ? 0 : pd.prob[q - 1].unit_begin + pd.prob[q - 1].k_pad / 8;
   }
   pd.inc = mat(p->m_inc, 0);
   pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;

@@ -38,18 +38,8 @@ __device__ __forceinline__ void store_act2(const Mat& m, int precision, int64_t 
   }
 }
 
-__device__ __forceinline__ float tab_value(int32_t e, const float* __restrict__ xs, int JC, int tc, int w0, int tq) {
-  if (e < 0) return 0.f;
-  const int src = e & 0xff, part = (e >> 8) & 3, k = (e >> 10) & 63, c = (e >> 16) & 3;
-  const float* row = xs + (tq * w0 + k) * JC;
-  float v = row[src];
-  if (part == 1) v -= row[c];                 // x - root joint (rie.py:301)
-  else if (part == 2) v -= xs[tc * JC + src]; // x - x[current frame] (rie.py:304)
-  return v;
-}
-
 // One CTA per sequence (window).  Dynamic smem: T*J*Cin floats (+ embed scratch).
-__global__ void __launch_bounds__(256) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
+__global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
                                                        const float* __restrict__ src, int64_t src_batch_stride,
                                                        int src_is_uv, const float* __restrict__ cam_or_param,
                                                        int64_t param_stride, int batch) {
@@ -57,8 +47,9 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PrologueDev* __rest
   const PrologueDev& d = *dp;
   const int b = blockIdx.x;
   const int T = d.T, J = d.J, JC = d.JC;
-  float* xs = smem;                    // [T][JC]
-  float* scratch = smem + T * JC;      // [emb_mid] embed hidden
+  float* xs = smem;                    // [T][JC] + one zero slot
+  float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
+  if (threadIdx.x == 0) xs[T * JC] = 0.f;
 
   // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
   if (src_is_uv) {
@@ -83,38 +74,53 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PrologueDev* __rest
   __syncthreads();
 
   // ---- 2. first-layer A matrices: row (b, tq), column kk = tap*Cg + channel --------------------
-  // One thread produces 8 consecutive columns (k_pad is a multiple of 64) => 16-byte stores per bf16 plane
-  // (32-byte for fp32), consecutive threads write consecutive 16-byte units of the same row.
-  for (int p = 0; p < d.nprob; ++p) {
-    const PrologueProb& pr = d.prob[p];
-    const int units = pr.k_pad >> 3;
-    const int total = d.L0 * units;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int tq = i / units, kk = (i - tq * units) << 3;
-      const int4 e0 = __ldg(reinterpret_cast<const int4*>(pr.tab + kk));
-      const int4 e1 = __ldg(reinterpret_cast<const int4*>(pr.tab + kk + 4));
-      const int ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-      float v[8];
+  // A work item owns one 8-column unit (16 bytes per bf16 plane) of one problem for a contiguous range of rows:
+  // its 8 gather-table entries live in registers and are reused for every row, consecutive lanes own consecutive
+  // units, so each warp store covers 512 contiguous bytes of one row.
+  {
+    const int units_total = d.prob[d.nprob - 1].unit_begin + (d.prob[d.nprob - 1].k_pad >> 3);
+    int rsplit = blockDim.x / units_total;
+    rsplit = rsplit < 1 ? 1 : (rsplit > d.L0 ? d.L0 : rsplit);
+    const int rows_per = (d.L0 + rsplit - 1) / rsplit;
+    const int rstep = d.w0 * JC;
+    for (int w = threadIdx.x; w < units_total * rsplit; w += blockDim.x) {
+      const int u = w % units_total, part = w / units_total;
+      int p = 0;
+      while (p + 1 < d.nprob && u >= d.prob[p + 1].unit_begin) ++p;
+      const PrologueProb& pr = d.prob[p];
+      const int kk = (u - pr.unit_begin) << 3;
+      int moff[8], soff[8], mrel[8], srel[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tab_value(ee[j], xs, JC, d.tc, d.w0, tq);
-      const int64_t idx = ((int64_t)b * d.L0 + tq) * pr.a0.ld + kk;
-      if (precision == R3D_PREC_FP32) {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.a0.p0) + idx);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
-      } else {
-        uint32_t h[4], l[4];
+      for (int j = 0; j < 8; ++j) {
+        const int2 e = __ldg(pr.tab + kk + j);
+        moff[j] = e.x & 0xffffff; mrel[j] = (e.x >> 30) & 1 ? -1 : 0;
+        soff[j] = e.y & 0xffffff; srel[j] = (e.y >> 30) & 1 ? -1 : 0;
+      }
+      const int t_begin = part * rows_per, t_end = min(d.L0, t_begin + rows_per);
+      int rb = t_begin * rstep;
+      int64_t idx = ((int64_t)b * d.L0 + t_begin) * pr.a0.ld + kk;
+      for (int tq = t_begin; tq < t_end; ++tq, rb += rstep, idx += pr.a0.ld) {
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-          const float2 hf = __bfloat1622float2(hh);
-          const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-          l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        for (int j = 0; j < 8; ++j) v[j] = xs[moff[j] + (rb & mrel[j])] - xs[soff[j] + (rb & srel[j])];
+        if (precision == R3D_PREC_FP32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.a0.p0) + idx);
+          o[0] = make_float4(v[0], v[1], v[2], v[3]);
+          o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p0) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (precision == R3D_PREC_BF16X3)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p1) + idx) = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p0) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
-        if (precision == R3D_PREC_BF16X3)
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p1) + idx) = make_uint4(l[0], l[1], l[2], l[3]);
       }
     }
   }
@@ -161,9 +167,12 @@ cudaError_t prologue_configure(int max_smem_bytes) {
 cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const void* src,
                             int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
                             int64_t param_stride, int batch, cudaStream_t s) {
-  const size_t smem = (size_t)(h.T * h.JC + h.emb_mid + 8) * sizeof(float);
+  const size_t smem = (size_t)(h.T * h.JC + h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
-  prologue_kernel<<<batch, 256, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
+  const int units_total = h.prob[h.nprob - 1].unit_begin + (h.prob[h.nprob - 1].k_pad >> 3);
+  int threads = 320;                                   // 152 units x 2 row ranges for the 6-problem plan
+  if (units_total * 2 <= 256) threads = 256;
+  prologue_kernel<<<batch, threads, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
                                            src_is_uv, cam_or_param, param_stride, batch);
   return cudaGetLastError();
 }
