@@ -246,7 +246,7 @@ constexpr int EPI_WARP0 = 4;
 
 template <int BLOCK_N, int NSPLIT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
-                                                                int M, int total_tiles) {
+                                                                int M, int total_tiles, int dbg) {
   constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT);
   constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = BLOCK_N * TBK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT);
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA loads (and multicasts)
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its own setup early
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(opp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(sop);
@@ -304,6 +305,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   __syncthreads();
   if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
+  // Programmatic dependent launch: everything above (descriptor copy, barrier init, TMEM allocation) only touches
+  // launch-invariant data and overlaps the tail of the previous kernel in the stream; activations written by that
+  // kernel are first touched below.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const GemmOpDev& op = *sop;
 
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
           tmem_ld_wait();
           const int n = tc.n0 + c * CH;
-          if (n < pr.N) {          // warp-uniform
+          if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             float v[32];
 #pragma unroll
             for (int j4 = 0; j4 < CH / 4; ++j4) {
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                 v[j4 * 4 + j] = x > 0.f ? x : slope * x;
               }
             }
-            if (pr.res.p0 != nullptr) {
+            if (pr.res.p0 != nullptr && !(dbg & 2)) {
               if (CH == 32) {
                 staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0),
                                 reinterpret_cast<const __nv_bfloat16*>(pr.res.p1), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
@@ -481,8 +486,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                 lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
               }
               if (CH == 32) {
-                staged_store(my_stage, hi, lane, m_base, M, pr, n, false);
-                if (any_lo) staged_store(my_stage, lo, lane, m_base, M, pr, n, true);
+                staged_store(my_stage, hi, lane, m_base, (dbg & 1) ? 0 : M, pr, n, false);
+                if (any_lo) staged_store(my_stage, lo, lane, m_base, (dbg & 1) ? 0 : M, pr, n, true);
               } else if (row_ok) {
                 for (int t = 0; t < pr.ndst; ++t) {
                   const Dst& d = pr.dst[t];
@@ -593,6 +598,8 @@ static cudaError_t configure_one() {
 }
 
 static int g_num_sms = 0;
+static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math (timing experiments only)
+static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
 
 cudaError_t tc_configure() {
@@ -603,6 +610,8 @@ cudaError_t tc_configure() {
   R3D_CFG(16) R3D_CFG(32) R3D_CFG(64) R3D_CFG(128) R3D_CFG(256)
 #undef R3D_CFG
   if (const char* env = getenv("R3D_TC_CLUSTER")) g_cluster_mode = atoi(env);
+  if (const char* env = getenv("R3D_TC_PDL")) g_pdl = atoi(env);
+  if (const char* env = getenv("R3D_TC_DEBUG")) g_dbg = atoi(env);
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   return cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -618,26 +627,34 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   const int m_groups = (m_tiles + cl - 1) / cl;
   int units = 0;
   for (int p = 0; p < h.nprob; ++p) units += m_groups * (h.prob[p].n_pad / BN);
-  if (!use_cl) {
-    const int grid = units < g_num_sms ? units : g_num_sms;
-    gemm_tc_kernel<BN, NS, 1><<<grid, TC_THREADS, tc_smem_bytes<BN, NS>(), s>>>(d_op, d_tmaps, M, units);
-    return cudaGetLastError();
-  }
-  const int max_clusters = g_num_sms / 2;
-  const int clusters = units < max_clusters ? units : max_clusters;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(clusters * 2);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = tc_smem_bytes<BN, NS>();
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (!use_cl) {
+    cfg.gridDim = dim3(units < g_num_sms ? units : g_num_sms);
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, 1>, d_op, d_tmaps, M, units, g_dbg);
+  }
+  const int max_clusters = g_num_sms / 2;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cfg.gridDim = dim3(clusters * 2);
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2>, d_op, d_tmaps, M, units);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2>, d_op, d_tmaps, M, units, g_dbg);
 }
 
 cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h, const void* d_tmaps, int M, int precision, cudaStream_t s) {
