@@ -32,13 +32,13 @@ constexpr int TBM = 128;            // UMMA M (one TMEM lane per output row)
 constexpr int TBK = 64;             // K block: 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 384;            // 4 control warps + 8 epilogue warps
-constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 255) / 256 * 256;
-constexpr int kAuxBytes = 256 + kOpSmemBytes + 8 * 512 + 8 * 2048;   // barriers, descriptor, bias slices, store staging
+constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 256;   // keeps the staging tiles 1024-byte aligned
+constexpr int kAuxBytes = 256 + kOpSmemBytes + 8 * 4096;   // barriers, descriptor, per-warp hi/lo store staging tiles
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 __host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit) { return nsplit * (TBM + block_n) * TBK * 2; }
 __host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit) {
-  int s = (SMEM_LIMIT - 1024 - kAuxBytes) / tc_stage_bytes(block_n, nsplit);
+  int s = (SMEM_LIMIT - kAuxBytes) / tc_stage_bytes(block_n, nsplit);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
@@ -98,6 +98,16 @@ __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
                : "memory");
 }
+// TMA store of one swizzled smem box; completion tracked per thread with bulk groups
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -179,28 +189,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, 
 // XOR-swizzled so that both the row-per-thread access and the 4-lanes-per-row access are conflict free.
 __device__ __forceinline__ int stg_index(int row, int unit) { return row * 4 + (unit ^ ((row >> 1) & 3)); }
 
-// registers (thread = row, 32 bf16 packed in w[16]) -> coalesced global stores (4 lanes x 16 B per row)
-__device__ __forceinline__ void staged_store(uint4* stg, const uint32_t (&w)[16], int lane, int m_base, int M, const GemmProb& pr,
-                                             int n, bool lo_plane) {
+// registers (thread = row, 32 bf16 packed in w[16]) -> staging tile in the 64B-swizzle layout the TMA store expects
+__device__ __forceinline__ void stage_write(uint4* stg, const uint32_t (&w)[16], int lane) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) stg[stg_index(lane, u)] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
-  __syncwarp();
-  const int u = lane & 3;
-#pragma unroll
-  for (int pass = 0; pass < 4; ++pass) {
-    const int r = pass * 8 + (lane >> 2);
-    const uint4 val = stg[stg_index(r, u)];
-    const int row = m_base + r;
-    if (row < M) {
-      for (int t = 0; t < pr.ndst; ++t) {
-        const Dst& d = pr.dst[t];
-        if (d.f32) continue;
-        __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(lo_plane ? d.m.p1 : d.m.p0);
-        if (plane != nullptr) *reinterpret_cast<uint4*>(plane + (int64_t)row * d.m.ld + d.col + n + u * 8) = val;
-      }
-    }
-  }
-  __syncwarp();
 }
 
 // coalesced global loads of the residual planes (both issued before any use, so their HBM latencies overlap)
@@ -270,8 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
-  float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes);             // [EPI_WARPS][128]
-  uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes + EPI_WARPS * 512);   // [EPI_WARPS][128 x 16 B]
+  uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][2 planes][32 rows x 64 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
@@ -407,22 +398,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
     const int half = ew >> 2;                                 // which half of the columns
     const bool active = half < COL_SPLIT;
-    float* my_bias = bias_s + ew * 128;
-    uint4* my_stage = stage_s + ew * 128;
+    uint4* stage_hi = stage_s + ew * 256;                     // 32 rows x 64 B, 64B-swizzled
+    uint4* stage_lo = stage_hi + 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float slope = op.slope;
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
       const GemmProb& pr = op.prob[tc.p];
+      const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
       const int m_base = tc.m0 + q * 32;
       const int row = m_base + lane;
       const bool row_ok = row < M;
       const int c_begin = half * CHUNKS_PER_WARP;
-      if (active) {   // this warp's slice of the folded bias -> smem (overlaps the wait for the accumulator)
-        __syncwarp();
-        for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(pr.bias + tc.n0 + c_begin * CH + j);
-        __syncwarp();
+      bool any_f32 = false, any_bf = false, any_lo = false;
+      for (int t = 0; t < pr.ndst; ++t) {
+        any_f32 |= pr.dst[t].f32 != 0;
+        any_bf |= pr.dst[t].f32 == 0;
+        any_lo |= pr.dst[t].f32 == 0 && pr.dst[t].m.p1 != nullptr;
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -433,23 +426,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           uint32_t r[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * CH);
           if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
-          tmem_ld_wait();
           const int n = tc.n0 + c * CH;
+          float bb[CH];
+#pragma unroll
+          for (int j4 = 0; j4 < CH / 4; ++j4) {       // folded bias: warp-uniform 16-byte loads (L1 resident)
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(pr.bias + n) + j4);
+            bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+          }
+          tmem_ld_wait();
           if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             float v[32];
 #pragma unroll
-            for (int j4 = 0; j4 < CH / 4; ++j4) {
-              const float4 b = *reinterpret_cast<const float4*>(my_bias + cc * CH + j4 * 4);
-              const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x = __uint_as_float(r[j4 * 4 + j]) + bb[j];
-                v[j4 * 4 + j] = x > 0.f ? x : slope * x;
-              }
+            for (int j = 0; j < CH; ++j) {
+              const float x = __uint_as_float(r[j]) + bb[j];
+              v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
+            }
+            // the previous chunk's TMA stores must have finished reading the staging tiles before they are reused
+            if (CH == 32) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
             }
             if (pr.res.p0 != nullptr && !(dbg & 2)) {
               if (CH == 32) {
-                staged_residual(my_stage, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0),
+                staged_residual(stage_hi, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0),
                                 reinterpret_cast<const __nv_bfloat16*>(pr.res.p1), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
               } else if (row_ok) {
                 const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
@@ -458,12 +457,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                   if (pr.res.p1 != nullptr) v[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.res.p1)[ro + j]);
                 }
               }
-            }
-            bool any_f32 = false, any_bf = false, any_lo = false;
-            for (int t = 0; t < pr.ndst; ++t) {
-              any_f32 |= pr.dst[t].f32 != 0;
-              any_bf |= pr.dst[t].f32 == 0;
-              any_lo |= pr.dst[t].f32 == 0 && pr.dst[t].m.p1 != nullptr;
             }
             if (any_f32 && row_ok) {      // network outputs (tiny): direct masked stores
               for (int t = 0; t < pr.ndst; ++t) {
@@ -486,8 +479,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                 lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
               }
               if (CH == 32) {
-                staged_store(my_stage, hi, lane, m_base, (dbg & 1) ? 0 : M, pr, n, false);
-                if (any_lo) staged_store(my_stage, lo, lane, m_base, (dbg & 1) ? 0 : M, pr, n, true);
+                // thread = row -> swizzled staging tiles -> one TMA store per destination plane (the TMA engine does
+                // the address generation / coalescing; rows past the buffer capacity are clipped by the tensor map,
+                // rows in [M, capacity) receive don't-care values nobody reads)
+                stage_write(stage_hi, hi, lane);
+                if (any_lo) stage_write(stage_lo, lo, lane);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(dbg & 1)) {
+                  for (int t = 0; t < pr.ndst; ++t) {
+                    const Dst& d = pr.dst[t];
+                    if (d.f32) continue;
+                    tma_store_2d(dmaps + 2 * t, stage_hi, d.col + n, m_base);
+                    if (d.m.p1 != nullptr) tma_store_2d(dmaps + 2 * t + 1, stage_lo, d.col + n, m_base);
+                  }
+                  bulk_commit();
+                }
               } else if (row_ok) {
                 for (int t = 0; t < pr.ndst; ++t) {
                   const Dst& d = pr.dst[t];
@@ -512,6 +519,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait0();             // every TMA store issued by this thread has landed
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -539,17 +548,17 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_elems, uint32_t box_rows) {
+static int encode_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_elems, uint32_t box_rows,
+                     uint32_t box_cols = TBK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   if (base == nullptr) { memset(out, 0, sizeof(*out)); return 0; }
   cuuint64_t dims[2] = {inner, rows};
   cuuint64_t strides[1] = {row_pitch_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TBK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
@@ -575,6 +584,16 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
     rc = encode_2d(out + p * kTmapsPerProb + 3, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
                    (uint64_t)g.K, (uint32_t)bn);
     if (rc) return rc;
+    // epilogue store maps: 32-column x 32-row boxes of every bf16 destination plane, 64B swizzle (the staging layout)
+    for (int t = 0; t < g.ndst; ++t) {
+      CUtensorMap* dm = out + p * kTmapsPerProb + 6 + 2 * t;
+      if (g.dst[t].f32 || bn < 32) { memset(dm, 0, 2 * sizeof(*dm)); continue; }
+      rc = encode_2d(dm, g.dst[t].m.p0, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows, (uint64_t)g.dst[t].m.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      rc = encode_2d(dm + 1, precision == R3D_PREC_BF16X3 ? g.dst[t].m.p1 : nullptr, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows,
+                     (uint64_t)g.dst[t].m.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
     if (bn >= 32) {   // half-tile W maps for the 2-CTA multicast variant
       rc = encode_2d(out + p * kTmapsPerProb + 4, g.w0, (uint64_t)g.K, (uint64_t)g.n_pad, (uint64_t)g.K, (uint32_t)bn / 2);
       if (rc) return rc;
@@ -587,7 +606,7 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
 }
 
 template <int BN, int NS>
-static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_bytes(BN, NS) + 1024 /*align*/ + kAuxBytes; }
+static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_bytes(BN, NS) + kAuxBytes; }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {

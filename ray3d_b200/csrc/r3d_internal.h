@@ -111,7 +111,7 @@ cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h_op, const v
                            cudaStream_t s);
 int tc_build_tmaps(const GemmOpDev& h_op, int precision, int64_t cap_rows, void* h_tmaps_out /* kMaxProb*4 maps */);
 cudaError_t tc_configure();
-constexpr int kTmapsPerProb = 6;     // A hi, A lo, W hi, W lo, W hi (half tile), W lo (half tile)
+constexpr int kTmapsPerProb = 6 + 2 * kMaxDst;   // A hi/lo, W hi/lo, W hi/lo (half tile), then {hi, lo} store maps per destination
 constexpr int kTmapBytes = 128;
 
 }  // namespace r3d

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -1055,7 +1056,10 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
-  const int chunk = std::min(batch, std::max(64, std::min(1024, (batch + 3) / 4)));
+  // chunking trades PCIe/compute overlap against per-launch efficiency (small batches under-fill the GPU)
+  int parts = 4;
+  if (const char* env = getenv("R3D_HOST_CHUNKS")) parts = std::max(1, atoi(env));
+  const int chunk = std::min(batch, std::max(64, std::min(kMaxChunk, (batch + parts - 1) / parts)));
   const size_t in_b = (size_t)chunk * src_stride * 4, prm_b = (size_t)chunk * std::max<int64_t>(prm_stride, 1) * 4;
   const size_t out_b = (size_t)chunk * p->J * 3 * 4, trj_b = (size_t)chunk * 3 * 4;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
