@@ -195,28 +195,34 @@ __device__ __forceinline__ void stage_write(uint4* stg, const uint32_t (&w)[16],
   for (int u = 0; u < 4; ++u) stg[stg_index(lane, u)] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
 }
 
-// coalesced global loads of the residual planes (both issued before any use, so their HBM latencies overlap)
-// -> registers (thread = row), accumulated into v[32]
-__device__ __forceinline__ void staged_residual(uint4* stg, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int col, int lane,
-                                                int m_base, int M, float (&v)[32]) {
+// Residual tile of one 32x32 chunk.  Loads are coalesced (4 lanes x 16 B per row) and *issued one chunk ahead*
+// (software pipelining in registers), so their HBM/L2 latency overlaps the previous chunk's math and stores.
+struct ResidualRegs {
+  uint4 h[4], l[4];
+};
+__device__ __forceinline__ void residual_issue(ResidualRegs& rr, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int col, int lane,
+                                               int m_base, int M) {
   const int u = lane & 3;
-  uint4 vh[4], vl[4];
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     const int row = m_base + pass * 8 + (lane >> 2);
-    vh[pass] = make_uint4(0, 0, 0, 0);
-    vl[pass] = make_uint4(0, 0, 0, 0);
+    rr.h[pass] = make_uint4(0, 0, 0, 0);
+    rr.l[pass] = make_uint4(0, 0, 0, 0);
     if (row < M) {
       const int64_t o = (int64_t)row * ld + col + u * 8;
-      vh[pass] = __ldg(reinterpret_cast<const uint4*>(hi + o));
-      if (lo != nullptr) vl[pass] = __ldg(reinterpret_cast<const uint4*>(lo + o));
+      rr.h[pass] = __ldg(reinterpret_cast<const uint4*>(hi + o));
+      if (lo != nullptr) rr.l[pass] = __ldg(reinterpret_cast<const uint4*>(lo + o));
     }
   }
+}
+// registers (4 lanes per row) -> swizzled staging tile -> registers (thread = row), accumulated into v[32]
+__device__ __forceinline__ void residual_consume(uint4* stg, const ResidualRegs& rr, bool has_lo, int lane, float (&v)[32]) {
+  const int u = lane & 3;
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
-    if (plane == 1 && lo == nullptr) break;
+    if (plane == 1 && !has_lo) break;
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) stg[stg_index(pass * 8 + (lane >> 2), u)] = plane ? vl[pass] : vh[pass];
+    for (int pass = 0; pass < 4; ++pass) stg[stg_index(pass * 8 + (lane >> 2), u)] = plane ? rr.l[pass] : rr.h[pass];
     __syncwarp();
 #pragma unroll
     for (int uu = 0; uu < 4; ++uu) {
@@ -417,6 +423,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         any_bf |= pr.dst[t].f32 == 0;
         any_lo |= pr.dst[t].f32 == 0 && pr.dst[t].m.p1 != nullptr;
       }
+      const bool has_res = pr.res.p0 != nullptr && !(dbg & 2);
+      const __nv_bfloat16* res_hi = reinterpret_cast<const __nv_bfloat16*>(pr.res.p0);
+      const __nv_bfloat16* res_lo = reinterpret_cast<const __nv_bfloat16*>(pr.res.p1);
+      ResidualRegs rr;
+      if (active && has_res && CH == 32)      // first chunk's residual: in flight while the main loop still runs
+        residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + c_begin * CH, lane, m_base, M);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (active) {
@@ -446,10 +458,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
               if (lane == 0) bulk_wait_read0();
               __syncwarp();
             }
-            if (pr.res.p0 != nullptr && !(dbg & 2)) {
+            if (has_res) {
               if (CH == 32) {
-                staged_residual(stage_hi, reinterpret_cast<const __nv_bfloat16*>(pr.res.p0),
-                                reinterpret_cast<const __nv_bfloat16*>(pr.res.p1), pr.res.ld, pr.res_col + n, lane, m_base, M, v);
+                residual_consume(stage_hi, rr, res_lo != nullptr, lane, v);
+                if (cc + 1 < CHUNKS_PER_WARP)     // next chunk's residual, one chunk ahead
+                  residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + n + CH, lane, m_base, M);
               } else if (row_ok) {
                 const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
                 for (int j = 0; j < CH; ++j) {
