@@ -89,20 +89,27 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       while (p + 1 < d.nprob && u >= d.prob[p + 1].unit_begin) ++p;
       const PrologueProb& pr = d.prob[p];
       const int kk = (u - pr.unit_begin) << 3;
-      int moff[8], soff[8], mrel[8], srel[8];
+      // running smem offsets of the 8 minuends / subtrahends and their per-row strides (rstep when the entry is
+      // relative to the row's frames, 0 when it addresses the fixed x[tc] frame or the zero slot)
+      const int t_begin = part * rows_per, t_end = min(d.L0, t_begin + rows_per);
+      int mo[8], so[8], ms[8], ss[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int2 e = __ldg(pr.tab + kk + j);
-        moff[j] = e.x & 0xffffff; mrel[j] = (e.x >> 30) & 1 ? -1 : 0;
-        soff[j] = e.y & 0xffffff; srel[j] = (e.y >> 30) & 1 ? -1 : 0;
+        ms[j] = ((e.x >> 30) & 1) ? rstep : 0;
+        ss[j] = ((e.y >> 30) & 1) ? rstep : 0;
+        mo[j] = (e.x & 0xffffff) + t_begin * ms[j];
+        so[j] = (e.y & 0xffffff) + t_begin * ss[j];
       }
-      const int t_begin = part * rows_per, t_end = min(d.L0, t_begin + rows_per);
-      int rb = t_begin * rstep;
       int64_t idx = ((int64_t)b * d.L0 + t_begin) * pr.a0.ld + kk;
-      for (int tq = t_begin; tq < t_end; ++tq, rb += rstep, idx += pr.a0.ld) {
+      for (int tq = t_begin; tq < t_end; ++tq, idx += pr.a0.ld) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = xs[moff[j] + (rb & mrel[j])] - xs[soff[j] + (rb & srel[j])];
+        for (int j = 0; j < 8; ++j) {
+          v[j] = xs[mo[j]] - xs[so[j]];
+          mo[j] += ms[j];
+          so[j] += ss[j];
+        }
         if (precision == R3D_PREC_FP32) {
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.a0.p0) + idx);
           o[0] = make_float4(v[0], v[1], v[2], v[3]);
