@@ -156,6 +156,19 @@ R3D_API int r3d_forward_uv_host(r3d_plan* plan, const float* uv_host, const floa
 R3D_API int r3d_forward_video(r3d_plan* plan, const float* seq_dev, const float* param_dev, float* pos_dev,
                       float* trj_dev, float* sum_dev, int32_t frames_out, void* stream);
 
+/* --- test-time flip augmentation: Trainer.evaluate_core with flip_test=True (trainer.py:299-302, 338-353) ---------
+ * r3d_plan_set_flip: in_perm[j] = source joint of input joint j in the mirrored copy (the kps_left/kps_right swap of
+ *   trainer.py:302), out_perm[s] = output slot whose mirrored prediction lands in slot s (trainer.py:341-342); both
+ *   have num_joints entries.
+ * r3d_forward_*_tta: every window is lifted twice inside ONE launch sequence (direct, and mirrored: x negated + L/R
+ *   swapped in the input stage), the mirrored prediction is un-mirrored and averaged with the direct one in the output
+ *   stage (torch.mean of the two), then pos + trj.  Same argument meaning as r3d_forward_rays / r3d_forward_video. */
+R3D_API int r3d_plan_set_flip(r3d_plan* plan, const int32_t* in_perm, const int32_t* out_perm);
+R3D_API int r3d_forward_rays_tta(r3d_plan* plan, const float* x_dev, const float* param_dev, float* pos_dev, float* trj_dev,
+                                 float* sum_dev, int32_t batch, void* stream);
+R3D_API int r3d_forward_video_tta(r3d_plan* plan, const float* seq_dev, const float* param_dev, float* pos_dev, float* trj_dev,
+                                  float* sum_dev, int32_t frames_out, void* stream);
+
 /* --- standalone camera encode: CameraInfoPacket.get_cam_ray_given_uv in float64 ------------------
  * uv_dev (n_points, 2) float64 -> ray_dev (n_points, 3) float64; one camera (fx, fy, ppx, ppy) and
  * cos/sin of the pitch computed by the caller with libm (math.cos/math.sin, camera.py:333-338) so the

@@ -194,6 +194,26 @@ def lift(sd_pos: State, sd_trj: State, spec: NetSpec, x: Tensor, param: Tensor):
         return pos, trj, pos + trj
 
 
+def lift_tta(sd_pos: State, sd_trj: State, spec: NetSpec, x: Tensor, param: Tensor, kps_left, kps_right):
+    """Flip test-time augmentation of Trainer.evaluate_core (trainer.py:299-302, 337-353): returns (pos, trj, pos+trj)
+    after averaging the direct and the un-mirrored mirrored predictions."""
+    kl, kr = list(kps_left), list(kps_right)
+    with torch.no_grad():
+        xf = x.clone()
+        xf[:, :, :, 0] *= -1                                                # trainer.py:301
+        xf[:, :, kl + kr, :] = xf[:, :, kr + kl, :]                         # trainer.py:302
+        pos = pos_forward(sd_pos, spec, x, param)
+        pos_f = pos_forward(sd_pos, spec, xf, param)
+        pos_f[:, :, :, 0] *= -1                                             # trainer.py:340
+        pos_f[:, :, kl + kr] = pos_f[:, :, kr + kl]                         # trainer.py:341-342
+        pos = torch.mean(torch.cat((pos, pos_f), dim=1), dim=1, keepdim=True)   # trainer.py:343-345
+        trj = trj_forward(sd_trj, spec, x, param)
+        trj_f = trj_forward(sd_trj, spec, xf, param)
+        trj_f[:, :, :, 0] *= -1                                             # trainer.py:349
+        trj = torch.mean(torch.cat((trj, trj_f), dim=1), dim=1, keepdim=True)   # trainer.py:350-352
+        return pos, trj, pos + trj                                          # trainer.py:353
+
+
 def lift_uv(sd_pos: State, sd_trj: State, spec: NetSpec, uv: np.ndarray, cam: np.ndarray):
     """Full hot path from pixels: ray encode (float64 -> float32, trainer.py:298) + both nets.
     cam (B,6) = [fx, fy, cx, cy, pitch, height]; param = [height, pitch] (trainer.py:297)."""

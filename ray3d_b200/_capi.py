@@ -56,6 +56,9 @@ EXPORTS = {
     "r3d_forward_rays_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
     "r3d_forward_uv_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
     "r3d_forward_video": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "r3d_plan_set_flip": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "r3d_forward_rays_tta": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
+    "r3d_forward_video_tta": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_ray_encode_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_double] * 6 + [C.c_void_p]),
     "r3d_normalize_screen_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "r3d_selftest_gemm": (C.c_int, [C.c_int32] * 6 + [C.POINTER(C.c_double)] * 3),
@@ -212,6 +215,18 @@ class Plan:
 
     def forward_video(self, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out: int, stream: int) -> None:
         check(lib().r3d_forward_video(self._h, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out, stream))
+
+    def set_flip(self, in_perm, out_perm) -> None:
+        n = self.spec.num_joints
+        a = (C.c_int32 * n)(*[int(v) for v in in_perm])
+        b = (C.c_int32 * n)(*[int(v) for v in out_perm])
+        check(lib().r3d_plan_set_flip(self._h, a, b))
+
+    def forward_rays_tta(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> None:
+        check(lib().r3d_forward_rays_tta(self._h, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch, stream))
+
+    def forward_video_tta(self, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out: int, stream: int) -> None:
+        check(lib().r3d_forward_video_tta(self._h, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out, stream))
 
     def forward_rays_host(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int) -> None:
         check(lib().r3d_forward_rays_host(self._h, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch))

@@ -82,6 +82,7 @@ struct PrologueDev {
   Mat inc;               // in_current, [B][roundup(J*Cin,64)]
   int32_t n_embed, ext_dim, emb_mid, emb_dim;
   EmbedDev embed[2];
+  int8_t flip_perm[32];   // flip test-time augmentation: source joint of every input joint (L/R swap)
 };
 
 struct AssembleDev {
@@ -91,14 +92,15 @@ struct AssembleDev {
   int32_t has_pos, has_trj;
   int16_t slot_prob[32];          // output joint slot -> problem index
   int16_t slot_joint[32];         // output joint slot -> joint index inside that head
+  int16_t flip_slot[32];          // flip augmentation: output slot whose flipped prediction lands in this slot
 };
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------------------
 cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h_desc, int precision, const void* src,
                             int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
-                            int64_t param_stride, int batch, cudaStream_t s);
+                            int64_t param_stride, int batch, int flip_from, cudaStream_t s);
 cudaError_t launch_assemble(const AssembleDev* d_desc, const AssembleDev& h_desc, float* pos, float* trj, float* sum,
-                            int batch, cudaStream_t s);
+                            int batch, int flip, cudaStream_t s);
 cudaError_t launch_gemm_ffma(const GemmOpDev* d_op, const GemmOpDev& h_op, int M, cudaStream_t s);
 cudaError_t launch_ray_encode_f64(const double* uv, double* ray, int64_t n, double fx, double fy, double ppx,
                                   double ppy, double c, double s, cudaStream_t st);

@@ -155,6 +155,7 @@ struct r3d_plan {
   // optional per-launch timing (r3d_plan_set_profiling): ring of event sets, one per forward chunk
   bool profiling = false;
   bool use_side_stream = true;
+  std::vector<int> flip_in, flip_out;                 // joint permutations of the flip augmentation (empty: not set)
   std::vector<cudaEvent_t> prof_ev;                   // [kProfRing][nops + 3]
   int prof_runs = 0;
   // host-call staging
@@ -897,6 +898,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
     pd.prob[q].k_pad = p->mats[p->m_a0[q]].ld;
     pd.prob[q].unit_begin = q == 0 ? 0 : pd.prob[q - 1].unit_begin + pd.prob[q - 1].k_pad / 8;
   }
+  for (int j = 0; j < 32; ++j) pd.flip_perm[j] = (int8_t)(j < (int)p->flip_in.size() ? p->flip_in[j] : j);
   pd.inc = mat(p->m_inc, 0);
   pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;
   for (int e = 0; e < pd.n_embed; ++e) {
@@ -914,7 +916,11 @@ static int bind_workspace(r3d_plan* p, int cap) {
   for (int q = 0; q < kMaxProb; ++q)
     ad.heads[q] = p->m_heads[q] >= 0 ? reinterpret_cast<const float*>(p->d_ws + p->mats[p->m_heads[q]].off0) : nullptr;
   ad.head_ld = 16; ad.J = p->J; ad.has_pos = p->has_pos; ad.has_trj = p->has_trj;
-  for (int s = 0; s < p->J; ++s) { ad.slot_prob[s] = (int16_t)p->groups.slots[s].first; ad.slot_joint[s] = (int16_t)p->groups.slots[s].second; }
+  for (int s = 0; s < p->J; ++s) {
+    ad.slot_prob[s] = (int16_t)p->groups.slots[s].first;
+    ad.slot_joint[s] = (int16_t)p->groups.slots[s].second;
+    ad.flip_slot[s] = (int16_t)(s < (int)p->flip_out.size() ? p->flip_out[s] : s);
+  }
 
   // descriptor slab: [ops][prologue][assemble][tensor maps]
   const size_t nops = p->ops.size();
@@ -949,8 +955,10 @@ static int ensure_capacity(r3d_plan* p, int batch) {
 static constexpr int kMaxChunk = 8192;
 static constexpr int kProfRing = 64;
 
+// `batch` windows are read; with tta the launch graph runs on 2*batch windows (direct + mirrored copies)
 static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                     float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
+                     float* pos, float* trj, float* sum, int batch_in, cudaStream_t s, bool tta = false) {
+  const int batch = tta ? 2 * batch_in : batch_in;
   const int prec = p->cfg.precision;
   const int nl = (int)p->ops.size() + 2, nev = 2 * nl;      // start/end event per launch
   cudaEvent_t* ev = nullptr;
@@ -964,7 +972,7 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, src, src_stride,
-                           is_uv, prm, prm_stride, batch, s));
+                           is_uv, prm, prm_stride, batch, tta ? batch_in : batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
   // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
   // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.
@@ -1000,7 +1008,7 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
     CUDA_TRY(cudaStreamWaitEvent(s, p->ev_join, 0));
   }
   if (ev) CUDA_TRY(cudaEventRecord(ev[nev - 2], s));
-  CUDA_TRY(launch_assemble(reinterpret_cast<const AssembleDev*>(p->d_desc + p->off_asm), p->asmb, pos, trj, sum, batch, s));
+  CUDA_TRY(launch_assemble(reinterpret_cast<const AssembleDev*>(p->d_desc + p->off_asm), p->asmb, pos, trj, sum, batch_in, tta ? 1 : 0, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[nev - 1], s));
   return R3D_OK;
 }
@@ -1017,21 +1025,23 @@ static int check_forward(r3d_plan* p, const void* src, float* pos, float* trj, f
 }
 
 static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                       float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
+                       float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta = false) {
   int rc = check_forward(p, src, pos, trj, sum, batch);
   if (rc) return rc;
+  if (tta && p->flip_in.empty()) return fail(R3D_ERR_STATE, "flip augmentation requested before r3d_plan_set_flip");
   if (batch == 0) return R3D_OK;
   if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
-  rc = ensure_capacity(p, std::min(batch, kMaxChunk));
-  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += kMaxChunk) {
-    const int nb = std::min(kMaxChunk, batch - b0);
+  const int max_in = tta ? kMaxChunk / 2 : kMaxChunk;     // the mirrored copies double the rows in flight
+  rc = ensure_capacity(p, std::min(batch, max_in) * (tta ? 2 : 1));
+  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += max_in) {
+    const int nb = std::min(max_in, batch - b0);
     rc = run_chunk(p, src + (int64_t)b0 * src_stride, src_stride, is_uv, prm ? prm + (int64_t)b0 * prm_stride : nullptr, prm_stride,
                    pos ? pos + (int64_t)b0 * p->J * 3 : nullptr, trj ? trj + (int64_t)b0 * 3 : nullptr,
-                   sum ? sum + (int64_t)b0 * p->J * 3 : nullptr, nb, s);
+                   sum ? sum + (int64_t)b0 * p->J * 3 : nullptr, nb, s, tta);
   }
   if (dev != p->device) cudaSetDevice(dev);
   return rc;
@@ -1057,6 +1067,37 @@ extern "C" R3D_API int r3d_forward_video(r3d_plan* p, const float* seq, const fl
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   // window f = frames [f, f+RF) of the padded video: batch stride of one frame, shared param row
   return forward_dev(p, seq, (int64_t)p->JC, 0, param, 0, pos, trj, sum, frames_out, (cudaStream_t)stream);
+}
+
+extern "C" R3D_API int r3d_plan_set_flip(r3d_plan* p, const int32_t* in_perm, const int32_t* out_perm) {
+  if (!p || !in_perm || !out_perm) return fail(R3D_ERR_BAD_ARG, "r3d_plan_set_flip: null argument");
+  std::vector<int> a(in_perm, in_perm + p->J), b(out_perm, out_perm + p->J);
+  for (int j = 0; j < p->J; ++j)
+    if (a[j] < 0 || a[j] >= p->J || b[j] < 0 || b[j] >= p->J) return fail(R3D_ERR_BAD_ARG, "flip permutation entry out of range at joint %d", j);
+  std::lock_guard<std::mutex> lk(p->mu);
+  p->flip_in = a;
+  p->flip_out = b;
+  if (p->cap > 0) {            // descriptors already on the device: rebuild them with the new tables
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+    const int rc = bind_workspace(p, p->cap);
+    if (dev != p->device) cudaSetDevice(dev);
+    return rc;
+  }
+  return R3D_OK;
+}
+
+extern "C" R3D_API int r3d_forward_rays_tta(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
+                                    int32_t batch, void* stream) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  return forward_dev(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, (cudaStream_t)stream, true);
+}
+
+extern "C" R3D_API int r3d_forward_video_tta(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
+                                     int32_t frames_out, void* stream) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  return forward_dev(p, seq, (int64_t)p->JC, 0, param, 0, pos, trj, sum, frames_out, (cudaStream_t)stream, true);
 }
 
 // Host-buffer forward: chunks of the batch flow H2D (copy stream) -> compute stream -> D2H (copy stream)

@@ -42,10 +42,14 @@ __device__ __forceinline__ void store_act2(const Mat& m, int precision, int64_t 
 __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
                                                        const float* __restrict__ src, int64_t src_batch_stride,
                                                        int src_is_uv, const float* __restrict__ cam_or_param,
-                                                       int64_t param_stride, int batch) {
+                                                       int64_t param_stride, int batch, int flip_from) {
   extern __shared__ float smem[];
   const PrologueDev& d = *dp;
   const int b = blockIdx.x;
+  // flip test-time augmentation (trainer.py:299-302): windows [flip_from, batch) are the mirrored copies of
+  // windows [0, batch - flip_from): x component negated, left/right joints swapped, same camera parameters
+  const bool flip = b >= flip_from;
+  const int bs = flip ? b - flip_from : b;
   const int T = d.T, J = d.J, JC = d.JC;
   float* xs = smem;                    // [T][JC] + one zero slot
   float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
@@ -54,22 +58,32 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
   if (src_is_uv) {
     // camera.py:438-439,471 in float64, then .astype(float32) (trainer.py:298)
-    const float* cam = cam_or_param + (int64_t)b * param_stride;
+    const float* cam = cam_or_param + (int64_t)bs * param_stride;
     const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
     double sp, cp;
     sincos((double)cam[4], &sp, &cp);
-    const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)b * src_batch_stride);
+    const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
     for (int i = threadIdx.x; i < T * J; i += blockDim.x) {
-      const float2 p = __ldg(uv + i);
+      const int jj = i % J;
+      const float2 p = __ldg(uv + (flip ? i - jj + d.flip_perm[jj] : i));
       const double xn = __ddiv_rn(__dsub_rn((double)p.x, cx), fx);
       const double yn = __ddiv_rn(__dsub_rn((double)p.y, cy), fy);
-      xs[i * 3 + 0] = (float)xn;
+      xs[i * 3 + 0] = flip ? -(float)xn : (float)xn;
       xs[i * 3 + 1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
       xs[i * 3 + 2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
     }
   } else {
-    const float* x = src + (int64_t)b * src_batch_stride;
-    for (int i = threadIdx.x; i < T * JC; i += blockDim.x) xs[i] = __ldg(x + i);
+    const float* x = src + (int64_t)bs * src_batch_stride;
+    if (!flip) {
+      for (int i = threadIdx.x; i < T * JC; i += blockDim.x) xs[i] = __ldg(x + i);
+    } else {
+      const int Cin = d.Cin;
+      for (int i = threadIdx.x; i < T * JC; i += blockDim.x) {
+        const int c = i % Cin, jj = (i / Cin) % J;
+        const float v = __ldg(x + i + (d.flip_perm[jj] - jj) * Cin);
+        xs[i] = c == 0 ? -v : v;
+      }
+    }
   }
   __syncthreads();
 
@@ -141,11 +155,11 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     const EmbedDev& em = d.embed[e];
     float prm[8];
     if (src_is_uv) {   // param = [height, pitch] (trainer.py:297)
-      const float* cam = cam_or_param + (int64_t)b * param_stride;
+      const float* cam = cam_or_param + (int64_t)bs * param_stride;
       prm[0] = cam[5];
       prm[1] = cam[4];
     } else {
-      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)b * param_stride + i];
+      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)bs * param_stride + i];
     }
     __syncthreads();
     for (int j = threadIdx.x; j < d.emb_mid; j += blockDim.x) {
@@ -173,41 +187,50 @@ cudaError_t prologue_configure(int max_smem_bytes) {
 
 cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const void* src,
                             int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
-                            int64_t param_stride, int batch, cudaStream_t s) {
+                            int64_t param_stride, int batch, int flip_from, cudaStream_t s) {
   const size_t smem = (size_t)(h.T * h.JC + h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
   const int units_total = h.prob[h.nprob - 1].unit_begin + (h.prob[h.nprob - 1].k_pad >> 3);
   int threads = 320;                                   // 152 units x 2 row ranges for the 6-problem plan
   if (units_total * 2 <= 256) threads = 256;
   prologue_kernel<<<batch, threads, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
-                                           src_is_uv, cam_or_param, param_stride, batch);
+                                           src_is_uv, cam_or_param, param_stride, batch, flip_from);
   return cudaGetLastError();
 }
 
 // ---- output stage ------------------------------------------------------------------------------
+// flip != 0: head rows [batch, 2*batch) hold the predictions for the mirrored windows; un-mirror them (negate x,
+// swap left/right slots) and average with the direct prediction (trainer.py:338-353; torch.mean of two values).
 __global__ void assemble_kernel(const AssembleDev* __restrict__ dp, float* __restrict__ pos, float* __restrict__ trj,
-                                float* __restrict__ sum, int batch) {
+                                float* __restrict__ sum, int batch, int flip) {
   const AssembleDev& d = *dp;
   const int per = d.J * 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)batch * per) return;
   const int b = (int)(i / per), r = (int)(i % per), slot = r / 3, c = r % 3;
+  const float sgn = c == 0 ? -1.f : 1.f;
   float t = 0.f;
   if (d.has_trj) {
-    t = d.heads[kMaxProb - 1][(int64_t)b * d.head_ld + c];
+    const float* h = d.heads[kMaxProb - 1];
+    t = h[(int64_t)b * d.head_ld + c];
+    if (flip) t = (t + sgn * h[(int64_t)(b + batch) * d.head_ld + c]) / 2.f;
     if (trj != nullptr && slot == 0) trj[(int64_t)b * 3 + c] = t;
   }
   if (d.has_pos) {
-    const float v = d.heads[d.slot_prob[slot]][(int64_t)b * d.head_ld + d.slot_joint[slot] * 3 + c];
+    float v = d.heads[d.slot_prob[slot]][(int64_t)b * d.head_ld + d.slot_joint[slot] * 3 + c];
+    if (flip) {
+      const int fs = d.flip_slot[slot];
+      v = (v + sgn * d.heads[d.slot_prob[fs]][(int64_t)(b + batch) * d.head_ld + d.slot_joint[fs] * 3 + c]) / 2.f;
+    }
     if (pos != nullptr) pos[i] = v;
     if (sum != nullptr) sum[i] = v + t;
   }
 }
 
 cudaError_t launch_assemble(const AssembleDev* d_desc, const AssembleDev& h, float* pos, float* trj, float* sum,
-                            int batch, cudaStream_t s) {
+                            int batch, int flip, cudaStream_t s) {
   const int64_t n = (int64_t)batch * h.J * 3;
-  assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_desc, pos, trj, sum, batch);
+  assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_desc, pos, trj, sum, batch, flip);
   return cudaGetLastError();
 }
 

@@ -125,6 +125,55 @@ class Lifter:
                                     _ptr(both), frames, self._stream(seq.device))
         return pos, trj, both
 
+    # -- flip test-time augmentation (Trainer.evaluate_core with flip_test=True) ------------------------------
+    def set_flip(self, kps_left, kps_right, out_left=None, out_right=None) -> None:
+        """Declare the left/right joint pairs.  Inputs are mirrored with (kps_left, kps_right) as in
+        trainer.py:302; predictions are un-mirrored with (out_left, out_right), which default to the same lists
+        because evaluate_core itself indexes the outputs with kps_left/kps_right (trainer.py:341-342)."""
+        J = self.spec.num_joints
+        out_left = kps_left if out_left is None else out_left
+        out_right = kps_right if out_right is None else out_right
+
+        def swap(left, right):
+            perm = list(range(J))
+            for l, r in zip(left, right):
+                perm[l], perm[r] = r, l
+            return perm
+        self.plan.set_flip(swap(list(kps_left), list(kps_right)), swap(list(out_left), list(out_right)))
+
+    def forward_rays_tta(self, x: torch.Tensor, param: Optional[torch.Tensor]):
+        """forward_rays with the mirrored copy lifted in the same launch sequence and averaged (trainer.py:338-353)."""
+        self._check_x(x)
+        _require_cuda(x, "x")
+        x = x.contiguous().float()
+        if self.spec.camera_embedding:
+            _require_cuda(param, "param")
+            param = param.contiguous().float()
+        pos, trj, both = self._outputs(x.shape[0], x.device)
+        if x.shape[0] == 0:
+            return pos, trj, both
+        with torch.cuda.device(x.device):
+            self.plan.forward_rays_tta(_ptr(x), _ptr(param) if self.spec.camera_embedding else None, _ptr(pos), _ptr(trj), _ptr(both),
+                                       x.shape[0], self._stream(x.device))
+        return pos, trj, both
+
+    def forward_video_tta(self, seq: torch.Tensor, param: Optional[torch.Tensor]):
+        """forward_video + flip augmentation: the whole evaluate_core inner step (trainer.py:299-353) in one call."""
+        _require_cuda(seq, "seq")
+        assert seq.dim() == 3 and seq.shape[1] == self.spec.num_joints and seq.shape[2] == self.spec.in_features
+        frames = seq.shape[0] - self.spec.receptive_field + 1
+        if frames <= 0:
+            raise RuntimeError("video shorter than one receptive field")
+        seq = seq.contiguous().float()
+        if self.spec.camera_embedding:
+            _require_cuda(param, "param")
+            param = param.contiguous().float().reshape(-1)
+        pos, trj, both = self._outputs(frames, seq.device)
+        with torch.cuda.device(seq.device):
+            self.plan.forward_video_tta(_ptr(seq), _ptr(param) if self.spec.camera_embedding else None, _ptr(pos), _ptr(trj),
+                                        _ptr(both), frames, self._stream(seq.device))
+        return pos, trj, both
+
     # -- host entry points (end-to-end: H2D + kernels + D2H inside the call) ---------------------------
     def forward_uv_host(self, uv: torch.Tensor, cam: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """uv/cam are CPU tensors (pinned for full PCIe rate); returns pos+trj (B,1,J,3) on the CPU."""

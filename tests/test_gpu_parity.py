@@ -145,6 +145,41 @@ def test_forward_video_equals_materialised_windows(golden_meta, precision):
     assert relerr(both.cpu().numpy(), ref.numpy()) < TOL[precision]
 
 
+H36M_LEFT, H36M_RIGHT = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]     # h36m keypoints_symmetry (h36m_dataset.py)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_flip_test_time_augmentation(golden_meta, precision):
+    """Trainer.evaluate_core(flip_test=True) fused into one launch sequence (trainer.py:299-353)."""
+    spec, lf, sp, st = lifter_for(golden_meta, "h36m_s1_t27", precision)
+    lf.set_flip(H36M_LEFT, H36M_RIGHT)
+    uv, cam = synth.make_inputs(spec, 37, seed=11)
+    x = torch.from_numpy(O.ray_encode_batch(uv, cam))
+    prm = torch.from_numpy(np.ascontiguousarray(cam[:, [5, 4]]))
+    pos, trj, both = lf.forward_rays_tta(x.cuda(), prm.cuda())
+    rp, rt, rb = O.lift_tta(O.to_torch_state(sp, torch.float64), O.to_torch_state(st, torch.float64), spec, x.double(), prm.double(),
+                            H36M_LEFT, H36M_RIGHT)
+    tol = TOL[precision]
+    assert relerr(pos.cpu().numpy(), rp.numpy()) < tol and relerr(trj.cpu().numpy(), rt.numpy()) < tol
+    assert relerr(both.cpu().numpy(), rb.numpy()) < tol
+    # identical to composing two plain forwards the way the trainer does (same kernels => bit identical)
+    xf = x.clone(); xf[:, :, :, 0] *= -1; xf[:, :, H36M_LEFT + H36M_RIGHT, :] = xf[:, :, H36M_RIGHT + H36M_LEFT, :]
+    p0, t0, _ = lf.forward_rays(x.cuda(), prm.cuda())
+    p1, t1, _ = lf.forward_rays(xf.cuda(), prm.cuda())
+    p1[:, :, :, 0] *= -1; p1[:, :, H36M_LEFT + H36M_RIGHT] = p1[:, :, H36M_RIGHT + H36M_LEFT]; t1[:, :, :, 0] *= -1
+    pm = torch.mean(torch.cat((p0, p1), dim=1), dim=1, keepdim=True)
+    tm = torch.mean(torch.cat((t0, t1), dim=1), dim=1, keepdim=True)
+    assert torch.equal(pos, pm) and torch.equal(trj, tm) and torch.equal(both, pm + tm)
+    # video form
+    seq = torch.from_numpy(O.ray_encode_batch(*synth.make_inputs(NetSpec(filter_widths=(3, 3, 3, 3)), 1, seed=5))[0])
+    cam1 = synth.make_inputs(NetSpec(filter_widths=(3, 3, 3, 3)), 1, seed=5)[1]
+    prm1 = torch.from_numpy(cam1[0, [5, 4]].copy())
+    vp, vt, vb = lf.forward_video_tta(seq.cuda(), prm1.cuda())
+    win = O.eval_windows(seq, 27)
+    wp, wt, wb = lf.forward_rays_tta(win.cuda(), prm1[None].repeat(win.shape[0], 1).cuda())
+    assert torch.equal(vb, wb) and vb.shape == (55, 1, 17, 3)
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_edge_batches(golden_meta, precision):
     spec, lf, sp, st = lifter_for(golden_meta, "h36m_s1_t27", precision)
