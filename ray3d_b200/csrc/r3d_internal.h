@@ -62,7 +62,7 @@ struct PrologueProb {
   Mat a0;
   const int2* tab;
   int32_t k_pad;
-  int32_t unit_begin;    // first 8-column unit of this problem in the flattened unit list
+  int32_t unit_begin;    // first 2-column unit of this problem in the flattened unit list
 };
 
 struct EmbedDev {

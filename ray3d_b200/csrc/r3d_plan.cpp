@@ -896,7 +896,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
     pd.prob[q].a0 = mat(p->m_a0[q], 0);
     pd.prob[q].tab = reinterpret_cast<const int2*>(p->d_weights + p->tab_off[q]);
     pd.prob[q].k_pad = p->mats[p->m_a0[q]].ld;
-    pd.prob[q].unit_begin = q == 0 ? 0 : pd.prob[q - 1].unit_begin + pd.prob[q - 1].k_pad / 8;
+    pd.prob[q].unit_begin = q == 0 ? 0 : pd.prob[q - 1].unit_begin + pd.prob[q - 1].k_pad / 2;
   }
   for (int j = 0; j < 32; ++j) pd.flip_perm[j] = (int8_t)(j < (int)p->flip_in.size() ? p->flip_in[j] : j);
   pd.inc = mat(p->m_inc, 0);

@@ -88,11 +88,12 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   __syncthreads();
 
   // ---- 2. first-layer A matrices: row (b, tq), column kk = tap*Cg + channel --------------------
-  // A work item owns one 8-column unit (16 bytes per bf16 plane) of one problem for a contiguous range of rows:
-  // its 8 gather-table entries live in registers and are reused for every row, consecutive lanes own consecutive
-  // units, so each warp store covers 512 contiguous bytes of one row.
+  // A work item owns one 2-column unit of one problem for a contiguous range of rows: its gather-table entries
+  // live in registers and are reused for every row.  Consecutive lanes own consecutive units, so a warp store
+  // covers 128 contiguous bytes of one bf16 plane row, and the smem reads of a warp are (at worst 2-way) spread
+  // over the banks (8-column units per lane made every LDS an 8-way bank conflict).
   {
-    const int units_total = d.prob[d.nprob - 1].unit_begin + (d.prob[d.nprob - 1].k_pad >> 3);
+    const int units_total = d.prob[d.nprob - 1].unit_begin + (d.prob[d.nprob - 1].k_pad >> 1);
     int rsplit = blockDim.x / units_total;
     rsplit = rsplit < 1 ? 1 : (rsplit > d.L0 ? d.L0 : rsplit);
     const int rows_per = (d.L0 + rsplit - 1) / rsplit;
@@ -102,45 +103,28 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       int p = 0;
       while (p + 1 < d.nprob && u >= d.prob[p + 1].unit_begin) ++p;
       const PrologueProb& pr = d.prob[p];
-      const int kk = (u - pr.unit_begin) << 3;
-      // running smem offsets of the 8 minuends / subtrahends and their per-row strides (rstep when the entry is
+      const int kk = (u - pr.unit_begin) << 1;
+      // running smem offsets of the minuends / subtrahends and their per-row strides (rstep when the entry is
       // relative to the row's frames, 0 when it addresses the fixed x[tc] frame or the zero slot)
       const int t_begin = part * rows_per, t_end = min(d.L0, t_begin + rows_per);
-      int mo[8], so[8], ms[8], ss[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int2 e = __ldg(pr.tab + kk + j);
-        ms[j] = ((e.x >> 30) & 1) ? rstep : 0;
-        ss[j] = ((e.y >> 30) & 1) ? rstep : 0;
-        mo[j] = (e.x & 0xffffff) + t_begin * ms[j];
-        so[j] = (e.y & 0xffffff) + t_begin * ss[j];
-      }
+      const int4 e = __ldg(reinterpret_cast<const int4*>(pr.tab + kk));     // two int2 entries
+      const int ms0 = ((e.x >> 30) & 1) ? rstep : 0, ss0 = ((e.y >> 30) & 1) ? rstep : 0;
+      const int ms1 = ((e.z >> 30) & 1) ? rstep : 0, ss1 = ((e.w >> 30) & 1) ? rstep : 0;
+      int mo0 = (e.x & 0xffffff) + t_begin * ms0, so0 = (e.y & 0xffffff) + t_begin * ss0;
+      int mo1 = (e.z & 0xffffff) + t_begin * ms1, so1 = (e.w & 0xffffff) + t_begin * ss1;
       int64_t idx = ((int64_t)b * d.L0 + t_begin) * pr.a0.ld + kk;
       for (int tq = t_begin; tq < t_end; ++tq, idx += pr.a0.ld) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = xs[mo[j]] - xs[so[j]];
-          mo[j] += ms[j];
-          so[j] += ss[j];
-        }
+        const float v0 = xs[mo0] - xs[so0], v1 = xs[mo1] - xs[so1];
+        mo0 += ms0; so0 += ss0; mo1 += ms1; so1 += ss1;
         if (precision == R3D_PREC_FP32) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.a0.p0) + idx);
-          o[0] = make_float4(v[0], v[1], v[2], v[3]);
-          o[1] = make_float4(v[4], v[5], v[6], v[7]);
+          *reinterpret_cast<float2*>(reinterpret_cast<float*>(pr.a0.p0) + idx) = make_float2(v0, v1);
         } else {
-          uint32_t h[4], l[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+          *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p0) + idx) = hh;
+          if (precision == R3D_PREC_BF16X3) {
             const float2 hf = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+            *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p1) + idx) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
           }
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p0) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
-          if (precision == R3D_PREC_BF16X3)
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p1) + idx) = make_uint4(l[0], l[1], l[2], l[3]);
         }
       }
     }
@@ -181,6 +165,8 @@ static int g_prologue_smem_cap = 48 * 1024;
 
 cudaError_t prologue_configure(int max_smem_bytes) {
   cudaError_t e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  if (e == cudaSuccess)   // several windows per SM: ask for the largest shared-memory carve-out
+    e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) g_prologue_smem_cap = max_smem_bytes;
   return e;
 }
@@ -190,9 +176,7 @@ cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int
                             int64_t param_stride, int batch, int flip_from, cudaStream_t s) {
   const size_t smem = (size_t)(h.T * h.JC + h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
-  const int units_total = h.prob[h.nprob - 1].unit_begin + (h.prob[h.nprob - 1].k_pad >> 3);
-  int threads = 320;                                   // 152 units x 2 row ranges for the 6-problem plan
-  if (units_total * 2 <= 256) threads = 256;
+  const int threads = 320;
   prologue_kernel<<<batch, threads, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
                                            src_is_uv, cam_or_param, param_stride, batch, flip_from);
   return cudaGetLastError();
