@@ -80,18 +80,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+// L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // activations: streamed once
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // weights: re-read by every tile of the problem
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
           smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask,
+                                               uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5, %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
@@ -173,7 +177,8 @@ struct TileCoord {
 };
 // Work unit -> (problem, m tile, n tile).  With clusters a unit covers `cl` consecutive m tiles (one per CTA of the
 // cluster) that share the same W tile, which is what the TMA multicast exploits.
-__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int m_groups, int block_n, int cl, int rank) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int m_groups, int block_n, int cl, int rank, int total) {
+  if (op.reverse) unit = total - 1 - unit;
   int p = 0, n_tiles = 1;
   for (;; ++p) {
     n_tiles = op.prob[p].n_pad / block_n;
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       constexpr int PF_DIST = 6;
       int pf_tile = unit0, pf_kb = 0, pf_nkb = 0, pf_m0 = 0, pf_p = 0, pf_ahead = 0;
       if (pf_tile < total_tiles) {
-        const TileCoord t0 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank);
+        const TileCoord t0 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         pf_p = t0.p; pf_m0 = t0.m0; pf_nkb = op.prob[t0.p].K / TBK;
       }
       auto prefetch_step = [&]() {
@@ -332,13 +337,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           pf_kb = 0;
           pf_tile += unit_step;
           if (pf_tile < total_tiles) {
-            const TileCoord t1 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank);
+            const TileCoord t1 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
             pf_p = t1.p; pf_m0 = t1.m0; pf_nkb = op.prob[t1.p].K / TBK;
           }
         }
       };
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -347,15 +352,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0);
-          if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0);
+          tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
+          if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
           if (CL == 1) {
-            tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0);
-            if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0);
+            tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
+            if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
           } else {   // this CTA fetches 1/CL of the W tile and multicasts it to every CTA of the cluster
             const int wrow = tc.n0 + crank * W_PART_ROWS, woff = crank * W_PART_ROWS * TBK * 2;
-            tma_load_2d_mc(st + NSPLIT * A_BYTES + woff, tm + 4, &full_bar[stage], kb * TBK, wrow, MC_MASK);
-            if (NSPLIT == 2) tma_load_2d_mc(st + 2 * A_BYTES + W_BYTES + woff, tm + 5, &full_bar[stage], kb * TBK, wrow, MC_MASK);
+            tma_load_2d_mc(st + NSPLIT * A_BYTES + woff, tm + 4, &full_bar[stage], kb * TBK, wrow, MC_MASK, kEvictLast);
+            if (NSPLIT == 2) tma_load_2d_mc(st + 2 * A_BYTES + W_BYTES + woff, tm + 5, &full_bar[stage], kb * TBK, wrow, MC_MASK, kEvictLast);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     uint32_t acc_phase = 0;
     const float slope = op.slope;
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-      const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank);
+      const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
       const GemmProb& pr = op.prob[tc.p];
       const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
       const int m_base = tc.m0 + q * 32;

@@ -50,6 +50,9 @@ struct GemmOpDev {
   int32_t rows_per_seq;  // M = batch * rows_per_seq
   float slope;           // LeakyReLU slope; 1.0f = linear
   int32_t n_tile;
+  int32_t reverse;       // walk the tiles last-to-first (alternates per layer: the tail of the previous layer's
+                         // output is what is still L2 resident when this one starts)
+  int32_t _pad;
   GemmProb prob[kMaxProb];
 };
 

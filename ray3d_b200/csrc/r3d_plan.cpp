@@ -887,6 +887,15 @@ static int bind_workspace(r3d_plan* p, int cap) {
     }
     op.dev.n_tile = ntile;
   }
+  {   // alternate the tile walk direction along each dependency chain (input stage writes front-to-back)
+    int main_i = 0, side_i = 0;
+    for (auto& op : p->ops) {
+      int& i = op.side ? side_i : main_i;
+      op.dev.reverse = (i % 2 == 0) ? 1 : 0;
+      ++i;
+    }
+    if (const char* env = getenv("R3D_TC_REVERSE")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.reverse = 0;
+  }
   // prologue
   PrologueDev& pd = p->pro;
   memset(&pd, 0, sizeof(pd));
