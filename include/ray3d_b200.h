@@ -181,6 +181,15 @@ R3D_API int r3d_ray_encode_f64(const double* uv_dev, double* ray_dev, int64_t n_
 R3D_API int r3d_normalize_screen_f64(const double* xy_dev, double* out_dev, int64_t n_points, double w, double h,
                                      void* stream);
 
+/* --- evaluation tail on the device: cam.normalized2world (lib/camera/camera.py:401-410) followed by the error sums of
+ * mpjpe / root mpjpe / n_mpjpe / mean_velocity_error (lib/loss/loss.py:12-18, 72-81, 95-104) as evaluate_core applies
+ * them (trainer.py:355-395), in float64 like the reference.  pred_dev/target_dev (frames, joints, 3) float32;
+ * rn2w_tn2w_dev: 12 doubles = Rn2w row-major then Tn2w, or NULL to stay in the normalised frame; sums_dev: 4 doubles
+ * written with [sum ||p-t||, sum over frames of the root error, sum ||s*p-t||, sum of velocity errors]; the caller
+ * divides by frames*joints, frames, frames*joints and (frames-1)*joints.  p_mpjpe (Procrustes/SVD) is not covered. */
+R3D_API int r3d_eval_metrics(const float* pred_dev, const float* target_dev, int32_t frames, int32_t joints,
+                             const double* rn2w_tn2w_dev, double* sums_dev, void* stream);
+
 /* --- self tests (used by tests/ and smoke(); run on the device, compare the tensor-core GEMM with
  * the FP32 FFMA GEMM on seeded data).  Returns max |tc - ffma| / max|ffma| in *rel_err. */
 R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,

@@ -223,6 +223,25 @@ def lift_uv(sd_pos: State, sd_trj: State, spec: NetSpec, uv: np.ndarray, cam: np
     return lift(sd_pos, sd_trj, spec, x, param)
 
 
+def normalized2world(pt: np.ndarray, Rn2w: np.ndarray, Tn2w: np.ndarray) -> np.ndarray:
+    """camera.py:401-410 (numpy branch): pt @ Rn2w.T + Tn2w.T."""
+    return pt @ Rn2w.T + Tn2w.T
+
+
+def eval_metrics(pred_world: np.ndarray, target_world: np.ndarray) -> Dict[str, float]:
+    """lib/loss/loss.py mpjpe (:12-18), n_mpjpe (:72-81), mean_velocity_error (:95-104) as called at
+    trainer.py:386-395 on (F,1,J,3) float64 world coordinates."""
+    p, t = torch.from_numpy(np.asarray(pred_world)), torch.from_numpy(np.asarray(target_world))
+    mp = torch.mean(torch.norm(p - t, dim=3)).item()
+    mr = torch.mean(torch.norm(p[:, :, 0:1] - t[:, :, 0:1], dim=3)).item()
+    norm_p = torch.mean(torch.sum(p ** 2, dim=3, keepdim=True), dim=2, keepdim=True)
+    norm_t = torch.mean(torch.sum(t * p, dim=3, keepdim=True), dim=2, keepdim=True)
+    nm = torch.mean(torch.norm(norm_t / norm_p * p - t, dim=3)).item()
+    pn, tn = p.numpy().reshape(-1, p.shape[-2], 3), t.numpy().reshape(-1, p.shape[-2], 3)
+    mv = float(np.mean(np.linalg.norm(np.diff(pn, axis=0) - np.diff(tn, axis=0), axis=2)))
+    return {"mpjpe": mp, "mrpe": mr, "n_mpjpe": nm, "mpjve": mv}
+
+
 def eval_windows(seq: Tensor, receptive_field: int) -> Tensor:
     """trainer.py:47-58 eval_data_prepare: (F+RF-1, J, C) -> (F, RF, J, C) sliding windows."""
     return seq.unfold(0, receptive_field, 1).permute(0, 3, 1, 2).contiguous()

@@ -10,5 +10,6 @@ from .spec import NetSpec  # noqa: F401
 from .lifter import Lifter, DEFAULT_PRECISION  # noqa: F401
 from .model import Model, RIEModel, RIETrajectoryModel, TemporalBlock, FCBlock, Linear, Embedding, fused_lifter  # noqa: F401
 from .camera import RayCamera, normalize_screen_coordinates  # noqa: F401
+from . import metrics  # noqa: F401
 
 __version__ = "0.1.0"

@@ -76,6 +76,10 @@ class RayCamera:
         c, s = math.cos(self.cam_pitch_rad), math.sin(self.cam_pitch_rad)
         self.Rc2n = np.array([[1.0, 0.0, 0.0], [0.0, c, s], [0.0, -s, c]])   # camera.py:333-338
         self.pp_cam = np.array([[K[0, 2], K[1, 2]]])                     # camera.py:258-259
+        # normalised frame <-> world (camera.py:246-256): Tc2n = (0, -height, 0)
+        Tc2n = np.array([[0.0], [-self.height], [0.0]])
+        self.Rn2w = self.Rc2w @ self.Rc2n.T
+        self.Tn2w = -self.Rn2w @ Tc2n - self.Rc2w @ self.Tw2c
 
     @property
     def param(self) -> np.ndarray:

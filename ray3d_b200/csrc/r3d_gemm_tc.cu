@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         for (int kb = 0; kb < nkb; ++kb) {
-          while (pf_ahead < PF_DIST + 1) { prefetch_step(); ++pf_ahead; }
-          --pf_ahead;
+          if (!(dbg & 8)) {
+            while (pf_ahead < PF_DIST + 1) { prefetch_step(); ++pf_ahead; }
+            --pf_ahead;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -635,7 +637,7 @@ static cudaError_t configure_one() {
 }
 
 static int g_num_sms = 0;
-static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math (timing experiments only)
+static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 no L2 prefetch (timing experiments only)
 static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
 

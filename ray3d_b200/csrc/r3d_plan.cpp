@@ -1232,6 +1232,13 @@ extern "C" R3D_API int r3d_normalize_screen_f64(const double* xy, double* out, i
   return R3D_OK;
 }
 
+extern "C" R3D_API int r3d_eval_metrics(const float* pred, const float* target, int32_t frames, int32_t joints, const double* rn2w_tn2w,
+                                double* sums_dev, void* stream) {
+  if (!pred || !target || !sums_dev || frames < 0 || joints < 1 || joints > 32) return fail(R3D_ERR_BAD_ARG, "r3d_eval_metrics: bad argument");
+  CUDA_TRY(launch_eval_metrics(pred, target, frames, joints, rn2w_tn2w, sums_dev, (cudaStream_t)stream));
+  return R3D_OK;
+}
+
 // ---- on-device self test: tensor-core GEMM vs FP32 FFMA GEMM -----------------------------------------
 extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
                                  double* rel_err, double* ms_tc, double* ms_ffma) {

@@ -255,4 +255,66 @@ cudaError_t launch_normalize_screen_f64(const double* xy, double* out, int64_t n
   return cudaGetLastError();
 }
 
+// ---- evaluation tail: normalized2world (camera.py:401-410) + MPJPE / MRPE / N-MPJPE / MPJVE (lib/loss/loss.py) ------
+// One warp per frame, lane = joint (J <= 32), float64 like the reference (numpy promotes the float32 predictions when
+// they are multiplied by the float64 Rn2w).  acc[0..3] += sum of per-joint errors: position, root, scale-normalised
+// position, velocity.  Means are taken by the caller (trainer.py:386-395 weights them by frame count anyway).
+__global__ void eval_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target, int frames, int J,
+                                    const double* __restrict__ rt /* 9 + 3, or null */, double* __restrict__ acc) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= frames) return;
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3] = {0, 0, 0};
+  if (rt != nullptr) {
+    for (int i = 0; i < 9; ++i) R[i] = rt[i];
+    for (int i = 0; i < 3; ++i) T[i] = rt[9 + i];
+  }
+  auto world = [&](const float* src, int f, double (&o)[3]) {    // pt @ Rn2w.T + Tn2w.T
+    const float* q = src + ((int64_t)f * J + lane) * 3;
+    const double x = q[0], y = q[1], z = q[2];
+    for (int i = 0; i < 3; ++i) o[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, R[3 * i]), __dmul_rn(y, R[3 * i + 1])), __dmul_rn(z, R[3 * i + 2])), T[i]);
+  };
+  const bool on = lane < J;
+  double p[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+  if (on) { world(pred, warp, p); world(target, warp, t); }
+  double e_pos = 0, s_pp = 0, s_tp = 0, e_vel = 0;
+  if (on) {
+    const double dx = p[0] - t[0], dy = p[1] - t[1], dz = p[2] - t[2];
+    e_pos = sqrt(dx * dx + dy * dy + dz * dz);                                   // loss.py:17
+    s_pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];                              // loss.py:79
+    s_tp = t[0] * p[0] + t[1] * p[1] + t[2] * p[2];                              // loss.py:80
+    if (warp + 1 < frames) {                                                     // loss.py:101-104
+      double p1[3], t1[3];
+      world(pred, warp + 1, p1); world(target, warp + 1, t1);
+      const double vx = (p1[0] - p[0]) - (t1[0] - t[0]), vy = (p1[1] - p[1]) - (t1[1] - t[1]), vz = (p1[2] - p[2]) - (t1[2] - t[2]);
+      e_vel = sqrt(vx * vx + vy * vy + vz * vz);
+    }
+  }
+  const double e_root = lane == 0 ? e_pos : 0.0;
+  auto wsum = [](double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  const double scale = (wsum(s_tp) / J) / (wsum(s_pp) / J);                      // loss.py:79-81 (means over joints)
+  double e_n = 0;
+  if (on) {
+    const double dx = scale * p[0] - t[0], dy = scale * p[1] - t[1], dz = scale * p[2] - t[2];
+    e_n = sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  const double a0 = wsum(e_pos), a2 = wsum(e_n), a3 = wsum(e_vel);
+  if (lane == 0) {
+    atomicAdd(acc + 0, a0);
+    atomicAdd(acc + 1, e_root);
+    atomicAdd(acc + 2, a2);
+    atomicAdd(acc + 3, a3);
+  }
+}
+
+cudaError_t launch_eval_metrics(const float* pred, const float* target, int frames, int J, const double* rt, double* acc, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(acc, 0, 4 * sizeof(double), st);
+  if (e != cudaSuccess || frames <= 0) return e;
+  const int warps_per_block = 8;
+  eval_metrics_kernel<<<(frames + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(pred, target, frames, J, rt, acc);
+  return cudaGetLastError();
+}
+
 }  // namespace r3d

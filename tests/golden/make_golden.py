@@ -133,6 +133,19 @@ def main():
     np.savez_compressed(os.path.join(HERE, "camera.npz"),
                         **{f"{k}{i}": np.asarray(c[k]) for i, c in enumerate(cams) for k in c})
 
+    # evaluation tail: normalized2world (camera.py:401-410) + MPJPE family (lib/loss/loss.py) as evaluate_core uses them
+    from lib.loss.loss import mpjpe, n_mpjpe, mean_velocity_error, p_mpjpe  # noqa: E402  (reference)
+    pkt = CameraInfoPacket(P=None, K=cams[0]["K"], R=cams[0]["R"], t=cams[0]["t"], dist_coeff=None, res_w=1000, res_h=1002, undistort=False)
+    pred = rng.standard_normal(size=(50, 1, 17, 3)).astype(np.float32)
+    target = (pred + 0.05 * rng.standard_normal(size=pred.shape)).astype(np.float32)
+    pw, tw = torch.from_numpy(pkt.normalized2world(pred)), torch.from_numpy(pkt.normalized2world(target))   # trainer.py:355-364
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), pred=pred, target=target, Rn2w=pkt.Rn2w, Tn2w=pkt.Tn2w,
+                        pred_world=pw.numpy(), target_world=tw.numpy(), mpjpe=mpjpe(pw, tw).item(),
+                        mrpe=mpjpe(pw[:, :, 0:1, :], tw[:, :, 0:1, :]).item(), n_mpjpe=n_mpjpe(pw, tw).item(),
+                        mpjve=mean_velocity_error(pw.numpy().reshape(-1, 17, 3), tw.numpy().reshape(-1, 17, 3)),
+                        p_mpjpe=p_mpjpe(pw.numpy().reshape(-1, 17, 3), tw.numpy().reshape(-1, 17, 3)),
+                        K=cams[0]["K"], R=cams[0]["R"], t=cams[0]["t"])
+
     # sliding-window materialisation (trainer.py:47-58) -- imported lazily, it pulls in lib.loss etc.
     try:
         from lib.train_val.trainer import Trainer  # noqa: E402  (reference)

@@ -230,3 +230,16 @@ def test_tensor_core_gemm_selftest(precision):
         # plane for the bf16 precision (when n % 32 == 0), fp32 otherwise
         tol = 2e-5 if precision == "bf16x3" else (6e-3 if n % 32 == 0 else 1e-5)
         assert err < tol, (m, n, k, npb, err)
+
+
+def test_eval_tail_on_device_matches_reference():
+    """normalized2world + mpjpe / mrpe / n_mpjpe / mpjve (trainer.py:355-395) vs values computed by the reference."""
+    m = load_golden("metrics")
+    got = ray3d_b200.metrics.evaluate(torch.from_numpy(m["pred"]).cuda(), torch.from_numpy(m["target"]).cuda(), m["Rn2w"], m["Tn2w"])
+    for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve"):
+        assert abs(got[k] - float(m[k])) <= 1e-11 * abs(float(m[k])), (k, got[k], float(m[k]))
+    cam = RayCamera(m["K"], m["R"], m["t"])
+    assert np.allclose(cam.Rn2w, m["Rn2w"], rtol=0, atol=1e-14) and np.allclose(cam.Tn2w, m["Tn2w"], rtol=0, atol=1e-13)
+    plain = ray3d_b200.metrics.evaluate(torch.from_numpy(m["pred"]).cuda(), torch.from_numpy(m["target"]).cuda())
+    ref = O.eval_metrics(m["pred"].astype(np.float64), m["target"].astype(np.float64))
+    assert abs(plain["mpjpe"] - ref["mpjpe"]) < 1e-12 and abs(plain["mpjve"] - ref["mpjve"]) < 1e-12

@@ -83,3 +83,13 @@ def test_work_model_matches_survey_table():
     assert abs(flops_per_sequence(NetSpec(filter_widths=(3, 3, 3, 3))) / 1e6 - 104.8) < 0.1
     # params incl. BN affine + running stats; survey table counts nn.Parameters only
     assert weight_count(s) > 23_772_307 + 8_462_435
+
+
+def test_eval_tail_matches_reference_losses():
+    m = load_golden("metrics")
+    pw = O.normalized2world(m["pred"], m["Rn2w"], m["Tn2w"])
+    tw = O.normalized2world(m["target"], m["Rn2w"], m["Tn2w"])
+    assert np.array_equal(pw, m["pred_world"]) and np.array_equal(tw, m["target_world"])
+    got = O.eval_metrics(pw, tw)
+    for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve"):
+        assert abs(got[k] - float(m[k])) <= 1e-12 * abs(float(m[k])), k
