@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // L2 prefetch cursor: runs PF_DIST K blocks ahead of the loads (across tile boundaries).  The smem ring is
-      // only 2-3 stages deep for the 3-product tiles, far too shallow to cover HBM latency for the A operand
-      // (activations stream from HBM; W is L2 resident), so the stream is pulled into L2 early.
+      // Optional L2 prefetch cursor (R3D_TC_DEBUG bit 8): runs PF_DIST K blocks ahead of the loads across tile
+      // boundaries.  Kept for experiments only: on B200 it raised DRAM reads by ~60% (evictions before use) and
+      // slowed the step by 6%, the 2-3 stage ring plus TMA's own latency tolerance is enough.
       constexpr int PF_DIST = 6;
       int pf_tile = unit0, pf_kb = 0, pf_nkb = 0, pf_m0 = 0, pf_p = 0, pf_ahead = 0;
       if (pf_tile < total_tiles) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         for (int kb = 0; kb < nkb; ++kb) {
-          if (!(dbg & 8)) {
+          if (dbg & 8) {   // measured on B200: the extra L2 prefetch stream costs more DRAM traffic than it hides -> off
             while (pf_ahead < PF_DIST + 1) { prefetch_step(); ++pf_ahead; }
             --pf_ahead;
           }
@@ -637,7 +637,7 @@ static cudaError_t configure_one() {
 }
 
 static int g_num_sms = 0;
-static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 no L2 prefetch (timing experiments only)
+static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 enable the L2 prefetch cursor (timing experiments only)
 static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
 
