@@ -57,17 +57,6 @@ struct GemmOpDev {
 };
 
 // ---- input stage --------------------------------------------------------------------------------
-// Gather table of a problem's first-layer A matrix, one int2 per column kk:
-//   .x = offset of the minuend in the smem window, bit 30 set => relative to the row base (tq*w0*JC)
-//   .y = offset of the subtrahend, bit 30 set => relative to the row base; the zero slot (index T*JC) otherwise
-// (host-side semantic form: source channel j*Cin+c, part {x, x-root, x-x[tc]}, tap -- see r3d_plan.cpp)
-struct PrologueProb {
-  Mat a0;
-  const int2* tab;
-  int32_t k_pad;
-  int32_t unit_begin;    // first 2-column unit of this problem in the flattened unit list
-};
-
 struct EmbedDev {
   const float* w1;   // [mid][ext]  BN folded
   const float* b1;   // [mid]
@@ -80,8 +69,8 @@ struct EmbedDev {
 
 struct PrologueDev {
   int32_t T, J, Cin, JC, tc, w0, L0;
-  int32_t nprob;
-  PrologueProb prob[kMaxProb];
+  int32_t k_pad;         // row pitch of a0
+  Mat a0;                // first-layer operand shared by all problems: [B*L0][k_pad] = [w0 frames | x[tc] | 0]
   Mat inc;               // in_current, [B][roundup(J*Cin,64)]
   int32_t n_embed, ext_dim, emb_mid, emb_dim;
   EmbedDev embed[2];

@@ -95,6 +95,7 @@ struct PackedLayer {
   std::vector<float> w, b;        // [n_pad][k_pad], [n_pad]  BN folded, fp32
   size_t off_w0 = 0, off_w1 = 0, off_b = 0;   // offsets in the device weight slab
   bool plain = false;             // embedder matrices: no padding, fp32 only
+  int alg_k = 0;                  // K of the reference's own op (flop accounting); 0 => k
 };
 
 struct MatReq {          // one activation matrix in the workspace slab
@@ -143,8 +144,6 @@ struct r3d_plan {
   std::vector<OpHost> ops;
   PrologueDev pro{};
   AssembleDev asmb{};
-  std::vector<std::vector<int32_t>> tabs;
-  std::vector<size_t> tab_off;
   char* d_desc = nullptr;                             // ops + prologue + assemble + tmaps
   size_t off_ops = 0, off_pro = 0, off_asm = 0, off_tmaps = 0;
   // symbolic ids used while building
@@ -350,11 +349,46 @@ struct Folder {
 };
 }  // namespace
 
-static void pack_tblock(r3d_plan* p, int net, const std::string& pre, int in_ch) {
+// expand_conv is linear in its input [x_g | x_g - root | x_g - x_g[tc]] (rie.py:301-357), so the positional and temporal
+// differences are folded into the weights instead of being materialised per joint group:
+//   sum_{tap,ch} W[o,ch,tap] * in[ch, w0*t'+tap]
+//     = sum_{tap,s} Wf[o,tap,s] * x[s, w0*t'+tap]  +  sum_s Wc[o,s] * x[s, tc]
+//   Wf[o,tap,(j,c)] = [j in group] (Wx+Wd+Wt)[o,(jj,c),tap]  -  [j == root] sum_jj Wd[o,(jj,c),tap]
+//   Wc[o,(j,c)]     = -[j in group] sum_tap Wt[o,(jj,c),tap]
+// Every problem then reads the SAME compact operand row  [x[:, w0*t' .. w0*t'+w0-1] | x[:, tc]]  (K = (w0+1)*J*Cin
+// instead of w0*3*|group|*Cin per group: 4.75x fewer bytes at T=243), summed in float64 with the BatchNorm scale.
+static PackedLayer pack_expand_folded(r3d_plan* p, int net, const std::string& pre, const std::vector<int>& joints) {
+  Folder f{p, net};
+  const int C = p->C, Cin = p->Cin, JC = p->JC, w0 = p->widths[0], nj = (int)joints.size(), cg = 3 * nj * Cin;
+  PackedLayer pl;
+  pl.n = C; pl.k = (w0 + 1) * JC; pl.n_pad = round_up(C, 16); pl.k_pad = round_up(pl.k, kKAlign);
+  pl.alg_k = cg * w0;
+  pl.w.assign((size_t)pl.n_pad * pl.k_pad, 0.f); pl.b.assign(pl.n_pad, 0.f);
+  std::vector<double> sc, sh;
+  f.bn(pre + ".expand_bn", C, sc, sh);
+  const float* W = f.get(pre + ".expand_conv.weight");     // (C, cg, w0), channel = part*nj*Cin + jj*Cin + c
+  std::vector<double> row(pl.k_pad);
+  for (int o = 0; o < C; ++o) {
+    std::fill(row.begin(), row.end(), 0.0);
+    auto w = [&](int part, int jj, int c, int tap) { return (double)W[((size_t)o * cg + part * nj * Cin + jj * Cin + c) * w0 + tap]; };
+    for (int jj = 0; jj < nj; ++jj)
+      for (int c = 0; c < Cin; ++c)
+        for (int tap = 0; tap < w0; ++tap) {
+          row[tap * JC + joints[jj] * Cin + c] += w(0, jj, c, tap) + w(1, jj, c, tap) + w(2, jj, c, tap);
+          row[tap * JC + c] -= w(1, jj, c, tap);                       // root joint 0, same coordinate (rie.py:301)
+          row[w0 * JC + joints[jj] * Cin + c] -= w(2, jj, c, tap);     // x[:, tc] term (rie.py:304)
+        }
+    for (int k = 0; k < pl.k; ++k) pl.w[(size_t)o * pl.k_pad + k] = (float)(row[k] * sc[o]);
+    pl.b[o] = (float)sh[o];
+  }
+  return pl;
+}
+
+static void pack_tblock(r3d_plan* p, int net, const std::string& pre, const std::vector<int>& joints) {
   Folder f{p, net};
   const std::string key = std::to_string(net) + ":" + pre;
   const int C = p->C;
-  p->layers[key + ".expand_conv"] = f.conv(pre + ".expand_conv.weight", C, in_ch, p->widths[0], pre + ".expand_bn", "");
+  p->layers[key + ".expand_conv"] = pack_expand_folded(p, net, pre, joints);
   for (size_t i = 1; i < p->widths.size(); ++i) {
     const std::string a = std::to_string(2 * (i - 1)), b = std::to_string(2 * (i - 1) + 1);
     p->layers[key + ".layers_conv." + a] = f.conv(pre + ".layers_conv." + a + ".weight", C, C, p->widths[i], pre + ".layers_bn." + a, "");
@@ -400,21 +434,14 @@ static OpHost& add_op(r3d_plan* p, const std::string& name, int nprob, int rows_
 }
 
 static void build_graph(r3d_plan* p) {
-  p->mats.clear(); p->ops.clear(); p->tabs.clear(); p->emb_binds.clear(); p->m_a0.clear();
+  p->mats.clear(); p->ops.clear(); p->emb_binds.clear(); p->m_a0.clear();
   const int C = p->C, L = p->L, nl = (int)p->widths.size(), ntb = (int)p->tbs.size();
   const float act = 0.2f;   // nn.LeakyReLU(0.2), rie.py:27,113,156
 
-  // --- input stage tables + first-layer A matrices
-  for (int q = 0; q < ntb; ++q) {
-    const auto& tb = p->tbs[q];
-    const int nj = (int)tb.joints.size(), cg = 3 * nj * p->Cin, k = cg * p->widths[0], kp = round_up(k, kKAlign);
-    std::vector<int32_t> tab(kp, -1);
-    for (int kk = 0; kk < k; ++kk) {
-      const int tap = kk / cg, ch = kk % cg, part = ch / (nj * p->Cin), r = ch % (nj * p->Cin), jj = r / p->Cin, c = r % p->Cin;
-      tab[kk] = (tb.joints[jj] * p->Cin + c) | (part << 8) | (tap << 10) | (c << 16);
-    }
-    p->tabs.push_back(tab);
-    p->m_a0.push_back(add_mat(p, p->lens[0], kp));
+  // --- first-layer operand shared by every problem: row (b, t') = [x[b, w0*t' .. w0*t'+w0-1, :] | x[b, tc, :] | 0-pad]
+  {
+    const int a0 = add_mat(p, p->lens[0], round_up((p->widths[0] + 1) * p->JC, kKAlign));
+    for (int q = 0; q < ntb; ++q) p->m_a0.push_back(a0);
   }
   p->m_inc = add_mat(p, 1, round_up(p->JC, kKAlign));
 
@@ -582,7 +609,7 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
   p->layers.clear();
   if (p->has_pos) {
     for (int g = 0; g < 5; ++g)
-      pack_tblock(p, 0, std::string("LocalLayer_") + kGroupNames[g], 3 * (int)p->groups.joints[g].size() * p->Cin);
+      pack_tblock(p, 0, std::string("LocalLayer_") + kGroupNames[g], p->groups.joints[g]);
     pack_fcblock(p, 0, "GlobalInfo", p->JC, p->L, 2);
     if (p->cfg.stage != 1)
       for (int i = 0; i < 5; ++i) pack_fcblock(p, 0, "FuseBlocks." + std::to_string(i), 4 * p->L, p->L, 1);
@@ -591,7 +618,11 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
       pack_fcblock(p, 0, std::string("Integration_") + kGroupNames[g], p->feat_pos, 3 * (int)p->groups.joints[g].size(), 1);
   }
   if (p->has_trj) {
-    pack_tblock(p, 1, "LocalLayer", 3 * p->JC);
+    {
+      std::vector<int> all;
+      for (int j = 0; j < p->J; ++j) all.push_back(j);
+      pack_tblock(p, 1, "LocalLayer", all);
+    }
     pack_fcblock(p, 1, "GlobalInfo", p->JC, p->L, 2);
     if (p->embed) pack_embed(p, 1);
     pack_fcblock(p, 1, "Integration", p->feat_trj, 3, 1);
@@ -608,8 +639,6 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
     else { l.off_w0 = take(ne * 2); l.off_w1 = prec == R3D_PREC_BF16X3 ? take(ne * 2) : 0; }
     l.off_b = take(l.b.size() * 4);
   }
-  p->tab_off.clear();
-  for (auto& t : p->tabs) p->tab_off.push_back(take(t.size() * 8));   // device form: int2 per column
   p->weight_bytes = off;
   p->finalized = true;
   p->uploaded = false;
@@ -647,12 +676,6 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
          std::to_string((int)p->mats[i].f32) + "]";
   j += "],\"a0\":[";
   for (size_t i = 0; i < p->m_a0.size(); ++i) j += std::string(i ? "," : "") + std::to_string(p->m_a0[i]);
-  j += "],\"tabs\":[";
-  for (size_t i = 0; i < p->tabs.size(); ++i) {
-    j += std::string(i ? "," : "") + "[";
-    for (size_t k = 0; k < p->tabs[i].size(); ++k) j += std::string(k ? "," : "") + std::to_string(p->tabs[i][k]);
-    j += "]";
-  }
   j += "],\"heads\":[";
   for (int q = 0; q < kMaxProb; ++q) j += std::string(q ? "," : "") + std::to_string(p->m_heads[q]);
   j += "],\"slots\":[";
@@ -676,7 +699,7 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
       const auto& b = op.bind[q];
       const PackedLayer& pl = p->layers.at(b.layer);
       j += std::string(q ? "," : "") + "{\"a\":" + std::to_string(b.a) + ",\"a_ld\":" + std::to_string(b.a_ld) + ",\"n\":" + std::to_string(pl.n) +
-           ",\"k\":" + std::to_string(pl.k) + ",\"n_pad\":" + std::to_string(pl.n_pad) + ",\"k_pad\":" + std::to_string(pl.k_pad) +
+           ",\"k\":" + std::to_string(pl.k) + ",\"n_pad\":" + std::to_string(pl.n_pad) + ",\"k_pad\":" + std::to_string(pl.k_pad) + ",\"alg_k\":" + std::to_string(pl.alg_k ? pl.alg_k : pl.k) +
            ",\"layer\":\"" + b.layer +
            "\",\"res\":" + std::to_string(b.res) + ",\"res_ld\":" + std::to_string(b.res_ld) + ",\"res_col\":" + std::to_string(b.res_col) +
            ",\"dst\":[";
@@ -785,26 +808,6 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
     }
     memcpy(slab.data() + l.off_b, l.b.data(), l.b.size() * 4);
   }
-  // Device form of the gather tables: per column {main offset, sub code} into the smem window, both relative to
-  // the row base rb = tq*w0*JC unless bit 30 of the sub code is clear (absolute: x[tc] term).  value = xs[rb+main] -
-  // xs[(rel ? rb : 0) + sub]; columns without a subtrahend (part 0) and padding columns subtract / reference the
-  // shared zero slot at index T*JC.
-  for (size_t i = 0; i < p->tabs.size(); ++i) {
-    int32_t* dt = reinterpret_cast<int32_t*>(slab.data() + p->tab_off[i]);
-    const int zero_slot = p->T * p->JC;
-    for (size_t kk = 0; kk < p->tabs[i].size(); ++kk) {
-      const int32_t e = p->tabs[i][kk];
-      int32_t main_off = zero_slot, main_abs = 1, sub = zero_slot, rel = 0;
-      if (e >= 0) {
-        const int src = e & 0xff, part = (e >> 8) & 3, tap = (e >> 10) & 63, c = (e >> 16) & 3;
-        main_off = tap * p->JC + src; main_abs = 0;
-        if (part == 1) { sub = tap * p->JC + c; rel = 1; }
-        else if (part == 2) { sub = p->tc * p->JC + src; rel = 0; }
-      }
-      dt[2 * kk + 0] = main_off | (main_abs ? 0 : (1 << 30));
-      dt[2 * kk + 1] = sub | (rel << 30);
-    }
-  }
   CUDA_TRY(cudaMemcpy(p->d_weights, slab.data(), p->weight_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(prologue_configure(200 * 1024 + 1024));
   if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
@@ -900,13 +903,8 @@ static int bind_workspace(r3d_plan* p, int cap) {
   PrologueDev& pd = p->pro;
   memset(&pd, 0, sizeof(pd));
   pd.T = p->T; pd.J = p->J; pd.Cin = p->Cin; pd.JC = p->JC; pd.tc = p->tc; pd.w0 = p->widths[0]; pd.L0 = p->lens[0];
-  pd.nprob = (int)p->tbs.size();
-  for (int q = 0; q < pd.nprob; ++q) {
-    pd.prob[q].a0 = mat(p->m_a0[q], 0);
-    pd.prob[q].tab = reinterpret_cast<const int2*>(p->d_weights + p->tab_off[q]);
-    pd.prob[q].k_pad = p->mats[p->m_a0[q]].ld;
-    pd.prob[q].unit_begin = q == 0 ? 0 : pd.prob[q - 1].unit_begin + pd.prob[q - 1].k_pad / 2;
-  }
+  pd.a0 = mat(p->m_a0[0], 0);
+  pd.k_pad = p->mats[p->m_a0[0]].ld;
   for (int j = 0; j < 32; ++j) pd.flip_perm[j] = (int8_t)(j < (int)p->flip_in.size() ? p->flip_in[j] : j);
   pd.inc = mat(p->m_inc, 0);
   pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;

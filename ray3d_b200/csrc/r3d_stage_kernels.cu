@@ -51,9 +51,8 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   const bool flip = b >= flip_from;
   const int bs = flip ? b - flip_from : b;
   const int T = d.T, J = d.J, JC = d.JC;
-  float* xs = smem;                    // [T][JC] + one zero slot
+  float* xs = smem;                    // [T][JC]
   float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
-  if (threadIdx.x == 0) xs[T * JC] = 0.f;
 
   // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
   if (src_is_uv) {
@@ -87,46 +86,21 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   }
   __syncthreads();
 
-  // ---- 2. first-layer A matrices: row (b, tq), column kk = tap*Cg + channel --------------------
-  // A work item owns one 2-column unit of one problem for a contiguous range of rows: its gather-table entries
-  // live in registers and are reused for every row.  Consecutive lanes own consecutive units, so a warp store
-  // covers 128 contiguous bytes of one bf16 plane row, and the smem reads of a warp are (at worst 2-way) spread
-  // over the banks (8-column units per lane made every LDS an 8-way bank conflict).
+  // ---- 2. first-layer operand, shared by every joint group (the x-root / x-x[tc] differences are folded into the
+  // weights, see pack_expand_folded): row (b, tq) = [x[b, w0*tq .. w0*tq+w0-1, :] | x[b, tc, :] | 0].  A lane
+  // produces 2 adjacent columns, so warp stores cover 128 contiguous bytes per bf16 plane and the smem reads are
+  // conflict free.
   {
-    const int units_total = d.prob[d.nprob - 1].unit_begin + (d.prob[d.nprob - 1].k_pad >> 1);
-    int rsplit = blockDim.x / units_total;
-    rsplit = rsplit < 1 ? 1 : (rsplit > d.L0 ? d.L0 : rsplit);
-    const int rows_per = (d.L0 + rsplit - 1) / rsplit;
-    const int rstep = d.w0 * JC;
-    for (int w = threadIdx.x; w < units_total * rsplit; w += blockDim.x) {
-      const int u = w % units_total, part = w / units_total;
-      int p = 0;
-      while (p + 1 < d.nprob && u >= d.prob[p + 1].unit_begin) ++p;
-      const PrologueProb& pr = d.prob[p];
-      const int kk = (u - pr.unit_begin) << 1;
-      // running smem offsets of the minuends / subtrahends and their per-row strides (rstep when the entry is
-      // relative to the row's frames, 0 when it addresses the fixed x[tc] frame or the zero slot)
-      const int t_begin = part * rows_per, t_end = min(d.L0, t_begin + rows_per);
-      const int4 e = __ldg(reinterpret_cast<const int4*>(pr.tab + kk));     // two int2 entries
-      const int ms0 = ((e.x >> 30) & 1) ? rstep : 0, ss0 = ((e.y >> 30) & 1) ? rstep : 0;
-      const int ms1 = ((e.z >> 30) & 1) ? rstep : 0, ss1 = ((e.w >> 30) & 1) ? rstep : 0;
-      int mo0 = (e.x & 0xffffff) + t_begin * ms0, so0 = (e.y & 0xffffff) + t_begin * ss0;
-      int mo1 = (e.z & 0xffffff) + t_begin * ms1, so1 = (e.w & 0xffffff) + t_begin * ss1;
-      int64_t idx = ((int64_t)b * d.L0 + t_begin) * pr.a0.ld + kk;
-      for (int tq = t_begin; tq < t_end; ++tq, idx += pr.a0.ld) {
-        const float v0 = xs[mo0] - xs[so0], v1 = xs[mo1] - xs[so1];
-        mo0 += ms0; so0 += ss0; mo1 += ms1; so1 += ss1;
-        if (precision == R3D_PREC_FP32) {
-          *reinterpret_cast<float2*>(reinterpret_cast<float*>(pr.a0.p0) + idx) = make_float2(v0, v1);
-        } else {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-          *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p0) + idx) = hh;
-          if (precision == R3D_PREC_BF16X3) {
-            const float2 hf = __bfloat1622float2(hh);
-            *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(pr.a0.p1) + idx) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
-          }
-        }
+    const int kp = d.k_pad, k_frames = d.w0 * JC, k_all = k_frames + JC, half = kp >> 1;
+    for (int i = threadIdx.x; i < d.L0 * half; i += blockDim.x) {
+      const int tq = i / half, kk = (i - tq * half) << 1;
+      float v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = kk + j;
+        v[j] = k < k_frames ? xs[tq * k_frames + k] : (k < k_all ? xs[d.tc * JC + (k - k_frames)] : 0.f);
       }
+      store_act2(d.a0, precision, (int64_t)b * d.L0 + tq, kk, v[0], v[1]);
     }
   }
 

@@ -16,20 +16,11 @@ def replay(plan, x, param, dtype=np.float32):
     mats = [np.zeros((B * r, ld), dtype=dtype) for r, ld, _ in g["mats"]]
     xs = x.reshape(B, T, JC).astype(dtype)
     tc, w0, L0 = g["tc"], g["w0"], g["L0"]
-    # ---- prologue
-    for q, mid in enumerate(g["a0"]):
-        tab = np.asarray(g["tabs"][q], dtype=np.int64)
-        A0 = mats[mid].reshape(B, L0, -1)
-        for kk, e in enumerate(tab):
-            if e < 0:
-                continue
-            src, part, k, c = e & 0xff, (e >> 8) & 3, (e >> 10) & 63, (e >> 16) & 3
-            v = xs[:, k::w0, src][:, :L0]
-            if part == 1:
-                v = v - xs[:, k::w0, c][:, :L0]
-            elif part == 2:
-                v = v - xs[:, tc:tc + 1, src]
-            A0[:, :, kk] = v
+    # ---- input stage: one operand shared by all first-layer problems, row (b, tq) = [w0 frames | x[tc] | 0 pad]
+    # (the x - root / x - x[tc] differences live in the folded expand_conv weights)
+    A0 = mats[g["a0"][0]].reshape(B, L0, -1)
+    A0[:, :, :w0 * JC] = xs.reshape(B, L0, w0 * JC)
+    A0[:, :, w0 * JC:(w0 + 1) * JC] = xs[:, tc][:, None, :]
     mats[g["inc"]][:, :JC] = xs[:, tc]
     lrelu = lambda v, s: np.where(v > 0, v, v * dtype(s))
     for e in g["embed"]:

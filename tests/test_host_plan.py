@@ -60,14 +60,12 @@ def test_bn_fold_and_packing_match_numpy():
         return (W * s[:, None]).astype(np.float32), np.asarray(b, np.float32)
 
     checks = [
-        (1, "LocalLayer_Torso.expand_conv", sp, "LocalLayer_Torso.expand_conv.weight", "LocalLayer_Torso.expand_bn", None),
         (1, "LocalLayer_LLeg.layers_conv.2", sp, "LocalLayer_LLeg.layers_conv.2.weight", "LocalLayer_LLeg.layers_bn.2", None),
         (1, "LocalLayer_RArm.layers_conv.1", sp, "LocalLayer_RArm.layers_conv.1.weight", "LocalLayer_RArm.layers_bn.1", None),
         (1, "LocalLayer_RArm.shrink", sp, "LocalLayer_RArm.shrink.weight", None, "LocalLayer_RArm.shrink.bias"),
         (1, "GlobalInfo.fc_1", sp, "GlobalInfo.fc_1.weight", "GlobalInfo.bn_1", "GlobalInfo.fc_1.bias"),
         (1, "FuseBlocks.3.layers.0.w2", sp, "FuseBlocks.3.layers.0.w2.weight", "FuseBlocks.3.layers.0.batch_norm2", "FuseBlocks.3.layers.0.w2.bias"),
         (1, "Integration_Torso.fc_2", sp, "Integration_Torso.fc_2.weight", None, "Integration_Torso.fc_2.bias"),
-        (2, "LocalLayer.expand_conv", st, "LocalLayer.expand_conv.weight", "LocalLayer.expand_bn", None),
         (2, "Integration.fc_2", st, "Integration.fc_2.weight", None, "Integration.fc_2.bias"),
         (2, "embedder.w2", st, "embedder.w2.weight", "embedder.b2", "embedder.w2.bias"),
     ]
@@ -79,6 +77,32 @@ def test_bn_fold_and_packing_match_numpy():
         assert np.array_equal(pw[:n, :k], W), layer
         assert np.array_equal(pb[:n], b), layer
         assert not pw[n:].any() and not pw[:, k:].any() and not pb[n:].any()
+
+
+def test_folded_expand_conv_equals_grouped_conv():
+    """expand_conv over [x_g | x_g - root | x_g - x_g[tc]] (rie.py:301-357, :86) == folded weights applied to the
+    shared operand [w0 frames | x[tc]]: checked in float64 on random inputs for every group and the trajectory net."""
+    from ray3d_b200.spec import GROUP_JOINTS
+    spec = NetSpec(filter_widths=(3, 3, 3), stage=1)
+    p, sp, st = make_plan(spec)
+    rng = np.random.default_rng(0)
+    T, J, C = 27, 17, 3
+    x = rng.standard_normal((4, T, J * C))
+    tc, w0 = T // C, 3
+    A = np.concatenate([x.reshape(4, T // w0, w0 * J * C), np.repeat(x[:, tc:tc + 1], T // w0, axis=1)], axis=2)
+    for net, sd, pre, joints in [(1, sp, "LocalLayer_" + g, GROUP_JOINTS[17][g]) for g in ("Torso", "LArm", "RArm", "LLeg", "RLeg")] + \
+                                [(2, st, "LocalLayer", tuple(range(17)))]:
+        idx = [j * C + c for j in joints for c in range(C)]
+        xg = x[:, :, idx]
+        inp = np.concatenate([xg, xg - np.tile(x[:, :, :C], (1, 1, len(joints))), xg - x[:, tc:tc + 1, idx]], axis=2)   # (B,T,Cg)
+        W = sd[pre + ".expand_conv.weight"].astype(np.float64)
+        s = sd[pre + ".expand_bn.weight"].astype(np.float64) / np.sqrt(sd[pre + ".expand_bn.running_var"].astype(np.float64) + BN_EPS)
+        sh = sd[pre + ".expand_bn.bias"].astype(np.float64) - sd[pre + ".expand_bn.running_mean"].astype(np.float64) * s
+        ref = np.einsum("bqkc,ock->bqo", inp.reshape(4, T // w0, w0, -1), W) * s + sh
+        pw, pb = p.packed_layer(net, pre + ".expand_conv")
+        assert pw.shape == (256, 256) and not pw[:, (w0 + 1) * J * C:].any()
+        got = A @ pw[:, :A.shape[2]].astype(np.float64).T + pb.astype(np.float64)
+        assert relerr(got, ref) < 2e-7, pre          # weights are rounded to fp32 after the float64 fold
 
 
 @pytest.mark.parametrize("name", CASES)
