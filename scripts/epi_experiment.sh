@@ -1,9 +1,7 @@
 #!/bin/bash
 # timing experiments on the TC GEMM epilogue (R3D_TC_DEBUG: 1 skip stores, 2 skip residual, 4 skip epilogue math)
-for shape in "82944 256 128 6" "27648 256 256 6" "27648 256 768 6" "1024 1024 1024 6"; do
-  for dbg in 0 1 2 3; do
+for shape in "82944 256 256 6" "27648 256 256 6"; do
+  for dbg in 0 1 2 3 7; do
     echo -n "shape=$shape dbg=$dbg "; R3D_TC_DEBUG=$dbg timeout 100 python scripts/gpu_diag.py selftest $shape bf16x3 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ms_tc=%.4f tflops=%.1f err=%.2e'%(d['ms_tc'],d['tflops_tc'],d['err']))"
   done
 done
-timeout 100 python scripts/gpu_diag.py forward bf16x3 243 1024 1
-for c in 1 2 4; do R3D_HOST_CHUNKS=$c timeout 100 python scripts/e2e_experiment.py; done
