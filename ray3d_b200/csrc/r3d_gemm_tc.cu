@@ -582,7 +582,15 @@ static int encode_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-static int tc_block_n(const GemmOpDev& h) { return h.n_tile; }
+static int tc_block_n(const GemmOpDev& h) {
+  if (const char* env = getenv("R3D_TC_NTILE")) {     // experiments: force a narrower tile when it divides every problem
+    const int bn = atoi(env);
+    bool ok = bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256;
+    for (int p = 0; ok && p < h.nprob; ++p) ok = h.prob[p].n_pad % bn == 0;
+    if (ok && bn <= h.n_tile) return bn;
+  }
+  return h.n_tile;
+}
 
 int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* out_v) {
   static_assert(sizeof(CUtensorMap) == kTmapBytes, "CUtensorMap size");
