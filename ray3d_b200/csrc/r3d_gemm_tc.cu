@@ -36,9 +36,10 @@ constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 25
 constexpr int kAuxBytes = 256 + kOpSmemBytes + 8 * 4096;   // barriers, descriptor, per-warp hi/lo store staging tiles
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-__host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit) { return nsplit * (TBM + block_n) * TBK * 2; }
-__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit) {
-  int s = (SMEM_LIMIT - kAuxBytes) / tc_stage_bytes(block_n, nsplit);
+// per-CTA bytes of one K block: A tile (128 rows) + this CTA's share of the W tile (all of it, or half in 2-SM mode)
+__host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit, int cl = 1) { return nsplit * (TBM + block_n / cl) * TBK * 2; }
+__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1) {
+  int s = (SMEM_LIMIT - kAuxBytes) / tc_stage_bytes(block_n, nsplit, cl);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
@@ -139,6 +140,37 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- 2-SM (cta_group::2) forms: one MMA spans the CTA pair (M = 256), issued by the leader CTA only ----------------
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's barrier (peer bit of the cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], "
+      "%5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -168,8 +200,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
          ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = TBM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct TileCoord {
@@ -250,9 +282,13 @@ constexpr int EPI_WARP0 = 4;
 template <int BLOCK_N, int NSPLIT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
                                                                 int M, int total_tiles, int dbg) {
-  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT);
-  constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = BLOCK_N * TBK * 2;
-  constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT);
+  // CL == 2: the CTA pair works as one 256-row tile with cta_group::2 MMAs; each CTA stages its own 128 A rows and
+  // HALF of the W tile (the tensor cores read the other half from the peer's shared memory), which cuts the bytes
+  // every SM has to receive per MMA by a third -- the measured limiter (~74 GB/s per SM from L2) -- and buys a third
+  // pipeline stage.
+  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL);
+  constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = (BLOCK_N / CL) * TBK * 2;
+  constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT, CL);
   constexpr int TMEM_COLS = tc_tmem_cols(BLOCK_N);
   constexpr int CH = BLOCK_N >= 32 ? 32 : 16;         // epilogue column chunk
   constexpr int NCHUNK = BLOCK_N / CH;
@@ -279,8 +315,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
-  constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA loads (and multicasts)
+  constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA stages
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+  const bool leader = crank == 0;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its own setup early
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
@@ -290,18 +327,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);                             // every CTA of the cluster must have consumed the stage
+      mbar_init(&full_bar[s], 1);                               // CL == 2: only the leader's is used (both CTAs' bytes)
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);
+      mbar_init(&tempty_bar[a], EPI_WARPS * CL);                // CL == 2: the peer's epilogue warps arrive remotely
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {   // same warp id and same destination offset in both CTAs of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -353,16 +395,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
-          if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
           if (CL == 1) {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
+            if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
             tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
             if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
-          } else {   // this CTA fetches 1/CL of the W tile and multicasts it to every CTA of the cluster
-            const int wrow = tc.n0 + crank * W_PART_ROWS, woff = crank * W_PART_ROWS * TBK * 2;
-            tma_load_2d_mc(st + NSPLIT * A_BYTES + woff, tm + 4, &full_bar[stage], kb * TBK, wrow, MC_MASK, kEvictLast);
-            if (NSPLIT == 2) tma_load_2d_mc(st + 2 * A_BYTES + W_BYTES + woff, tm + 5, &full_bar[stage], kb * TBK, wrow, MC_MASK, kEvictLast);
+          } else {
+            // both CTAs' loads complete on the leader's barrier, which the (leader-only) MMA thread waits on
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            const int wrow = tc.n0 + crank * W_PART_ROWS;
+            tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
+            if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
+            tma_load_2d_2sm(st + NSPLIT * A_BYTES, tm + 4, &full_bar[stage], kb * TBK, wrow, kEvictLast);
+            if (NSPLIT == 2) tma_load_2d_2sm(st + 2 * A_BYTES + W_BYTES, tm + 5, &full_bar[stage], kb * TBK, wrow, kEvictLast);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -371,8 +417,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     __syncwarp();
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, TBM * CL);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
@@ -390,15 +436,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // 32 bytes per K step inside the swizzle atom
-            umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
-            if (NSPLIT == 2) {
-              umma_bf16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
-              umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
+            if (CL == 1) {
+              umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+              if (NSPLIT == 2) {
+                umma_bf16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+                umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
+              }
+            } else {
+              umma_bf16_2sm(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+              if (NSPLIT == 2) {
+                umma_bf16_2sm(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+                umma_bf16_2sm(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
+              }
             }
           }
-          if (CL == 1) umma_commit(&empty_bar[stage]);        // smem stage free once these MMAs retire
-          else umma_commit_mc(&empty_bar[stage], MC_MASK);     // ... in every CTA the multicast writes into
-          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);    // accumulator complete
+          if (CL == 1) {
+            umma_commit(&empty_bar[stage]);                    // smem stage free once these MMAs retire
+            if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          } else {                                             // ... signalled in both CTAs of the pair
+            umma_commit_2sm(&empty_bar[stage], MC_MASK);
+            if (kb == nkb - 1) umma_commit_2sm(&tfull_bar[acc], MC_MASK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -536,7 +594,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(&tempty_bar[acc], 0);        // the MMA thread lives in the leader CTA
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait0();             // every TMA store issued by this thread has landed
@@ -548,7 +609,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   if (CL > 1) cluster_sync_all();          // no CTA exits while a peer may still multicast into its smem
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CL == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -633,14 +695,14 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
   return 0;
 }
 
-template <int BN, int NS>
-static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS) * tc_stage_bytes(BN, NS) + kAuxBytes; }
+template <int BN, int NS, int CL = 1>
+static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_stage_bytes(BN, NS, CL) + kAuxBytes; }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
   if (e != cudaSuccess) return e;
-  if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, (BN >= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
+  if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, (BN >= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, (BN >= 32 ? 2 : 1)>());
   return e;
 }
 
@@ -676,7 +738,7 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   for (int p = 0; p < h.nprob; ++p) units += m_groups * (h.prob[p].n_pad / BN);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = tc_smem_bytes<BN, NS>();
+  cfg.dynamicSmemBytes = use_cl ? tc_smem_bytes<BN, NS, CL2>() : tc_smem_bytes<BN, NS, 1>();
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
