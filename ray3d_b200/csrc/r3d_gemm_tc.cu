@@ -33,13 +33,14 @@ constexpr int TBK = 64;             // K block: 64 bf16 = 128 bytes = one swizzl
 constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 384;            // 4 control warps + 8 epilogue warps
 constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 256;   // keeps the staging tiles 1024-byte aligned
-constexpr int kAuxBytes = 256 + kOpSmemBytes + 8 * 4096;   // barriers, descriptor, per-warp hi/lo store staging tiles
+// barriers, descriptor, per-warp hi/lo store staging tiles (double buffered in 2-SM mode, where the W half-tiles leave room)
+__host__ __device__ constexpr int tc_aux_bytes(int cl) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1); }
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // per-CTA bytes of one K block: A tile (128 rows) + this CTA's share of the W tile (all of it, or half in 2-SM mode)
 __host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit, int cl = 1) { return nsplit * (TBM + block_n / cl) * TBK * 2; }
 __host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1) {
-  int s = (SMEM_LIMIT - kAuxBytes) / tc_stage_bytes(block_n, nsplit, cl);
+  int s = (SMEM_LIMIT - tc_aux_bytes(cl)) / tc_stage_bytes(block_n, nsplit, cl);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
@@ -111,6 +112,7 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -469,8 +471,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
     const int half = ew >> 2;                                 // which half of the columns
     const bool active = half < COL_SPLIT;
-    uint4* stage_hi = stage_s + ew * 256;                     // 32 rows x 64 B, 64B-swizzled
-    uint4* stage_lo = stage_hi + 128;
+    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;                 // staging tile sets per warp (hi + lo each)
+    uint4* const stage_base = stage_s + ew * 256 * EPI_BUFS;  // each tile: 32 rows x 64 B, 64B-swizzled
+    int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float slope = op.slope;
@@ -518,10 +521,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
               const float x = __uint_as_float(r[j]) + bb[j];
               v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
             }
-            // the previous chunk's TMA stores must have finished reading the staging tiles before they are reused
+            // the TMA stores that last used this staging set must have finished reading it (with two sets the store
+            // of the previous chunk may still be in flight)
+            uint4* const stage_hi = stage_base + sbuf * 256;
+            uint4* const stage_lo = stage_hi + 128;
             if (CH == 32) {
-              if (lane == 0) bulk_wait_read0();
+              if (lane == 0) { if (EPI_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0(); }
               __syncwarp();
+              sbuf ^= (EPI_BUFS - 1);
             }
             if (has_res) {
               if (CH == 32) {
@@ -696,7 +703,7 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
 }
 
 template <int BN, int NS, int CL = 1>
-static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_stage_bytes(BN, NS, CL) + kAuxBytes; }
+static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_stage_bytes(BN, NS, CL) + tc_aux_bytes(CL); }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
