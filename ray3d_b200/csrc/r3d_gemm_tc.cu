@@ -34,7 +34,7 @@ constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 384;            // 4 control warps + 8 epilogue warps
 constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 256;   // keeps the staging tiles 1024-byte aligned
 // barriers, descriptor, per-warp hi/lo store staging tiles (double buffered in 2-SM mode, where the W half-tiles leave room)
-__host__ __device__ constexpr int tc_aux_bytes(int cl) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1); }
+__host__ __device__ constexpr int tc_aux_bytes(int cl) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + (cl == 2 ? 8 * 512 : 0); }
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // per-CTA bytes of one K block: A tile (128 rows) + this CTA's share of the W tile (all of it, or half in 2-SM mode)
@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
-  uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][2 planes][32 rows x 64 B]
+  uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][sets][2 planes][32 rows x 64 B]
+  float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes + 8 * 4096 * (CL == 2 ? 2 : 1));   // CL == 2: [EPI_WARPS][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
@@ -497,30 +498,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       ResidualRegs rr;
       if (active && has_res && CH == 32)      // first chunk's residual: in flight while the main loop still runs
         residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + c_begin * CH, lane, m_base, M);
+      constexpr bool BIAS_SMEM = CL == 2;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
+      float* my_bias = bias_s + ew * 128;
+      if (BIAS_SMEM && active) {              // this warp's slice of the folded bias -> smem while the main loop still runs
+        __syncwarp();
+        for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(pr.bias + tc.n0 + c_begin * CH + j);
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (active) {
+        uint32_t r[32];
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_begin * CH);
+        if (CH == 32) tmem_ld32(taddr0, r); else tmem_ld16(taddr0, r);       // chunk 0; later chunks are issued one ahead
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
           const int c = c_begin + cc;
-          uint32_t r[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * CH);
-          if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
           const int n = tc.n0 + c * CH;
           float bb[CH];
+          if (BIAS_SMEM) {
 #pragma unroll
-          for (int j4 = 0; j4 < CH / 4; ++j4) {       // folded bias: warp-uniform 16-byte loads (L1 resident)
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(pr.bias + n) + j4);
-            bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+            for (int j4 = 0; j4 < CH / 4; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(my_bias + cc * CH + j4 * 4);
+              bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < CH / 4; ++j4) {       // folded bias: warp-uniform 16-byte loads
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(pr.bias + n) + j4);
+              bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+            }
           }
           tmem_ld_wait();
-          if (n < pr.N && !(dbg & 4)) {          // warp-uniform
-            float v[32];
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const float x = __uint_as_float(r[j]) + bb[j];
-              v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
-            }
+          for (int j = 0; j < CH; ++j) {
+            const float x = __uint_as_float(r[j]) + bb[j];
+            v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
+          }
+          if (cc + 1 < CHUNKS_PER_WARP) {        // next chunk's accumulator columns: in flight during this chunk's stores
+            if (CH == 32) tmem_ld32(taddr0 + (cc + 1) * CH, r); else tmem_ld16(taddr0 + (cc + 1) * CH, r);
+          }
+          if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
             uint4* const stage_hi = stage_base + sbuf * 256;
