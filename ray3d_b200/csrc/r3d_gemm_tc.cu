@@ -209,18 +209,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int m = TBM) {
 struct TileCoord {
   int p, m0, n0;
 };
-// Work unit -> (problem, m tile, n tile).  With clusters a unit covers `cl` consecutive m tiles (one per CTA of the
-// cluster) that share the same W tile, which is what the TMA multicast exploits.
+// Work unit -> (problem, m tile, n tile), m-major: all problems' tiles of one row block are adjacent in the walk, so
+// launches whose problems share the A operand (the folded first layer: 6 problems read the same rows) re-use it
+// from L2 instead of streaming it from HBM once per problem (measured: 575 MB -> DRAM reads for an 85 MB operand when
+// the walk was problem-major, because the 510 MB output stream flushes L2 in between).  With clusters a unit covers
+// `cl` consecutive m tiles (one per CTA of the pair).
 __device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int m_groups, int block_n, int cl, int rank, int total) {
   if (op.reverse) unit = total - 1 - unit;
+  const int per_m = total / m_groups;            // sum over problems of their n tiles
+  const int mg = unit / per_m;
+  int rem = unit - mg * per_m;
   int p = 0, n_tiles = 1;
   for (;; ++p) {
     n_tiles = op.prob[p].n_pad / block_n;
-    const int cnt = m_groups * n_tiles;
-    if (unit < cnt) break;
-    unit -= cnt;
+    if (rem < n_tiles) break;
+    rem -= n_tiles;
   }
-  return TileCoord{p, ((unit / n_tiles) * cl + rank) * TBM, (unit % n_tiles) * block_n};
+  return TileCoord{p, (mg * cl + rank) * TBM, rem * block_n};
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------------------
