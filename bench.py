@@ -265,10 +265,16 @@ def main():
     gemm_ms, gemm_fl = sum(p["ms"] for p in gemms), sum(p["gflop"] for p in gemms)
     peak = peaks["bf16_tflops_sustained"] if precision != "fp32" else 74.4
     achieved = top["gflop"] / top["ms"]              # TFLOP/s (GFLOP / ms)
+    # DRAM traffic of that launch from the committed `ncu --set full` capture of the same workload (per launch)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")
+    if os.path.exists(tpath) and args.workload == "cfg2" and precision == "bf16x3":
+        with open(tpath) as f:
+            traffic = json.load(f).get(top["name"], {}).get("dram_bytes")
     alg_bytes = (spec.receptive_field * 17 * 2 * 4 + 24 + 216) + lifter.plan.weight_bytes / B
     roofline = {
         "bound": "tensor", "kernel": f"gemm_tc_kernel ({top['name']}, largest launch of the step)" if precision != "fp32" else f"gemm_ffma_kernel ({top['name']})",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peaks["source"] + (", sustained bf16 cuBLAS figure (kernel timed inside a long step)" if precision != "fp32" else "; fp32 FFMA nominal 148 SM x 128 x 2 x 1.965 GHz"),
         "note": ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K of the valid shapes); the bf16x3 path issues 3 bf16 MMAs per "
                  "algorithmic MAC, so tensor-pipe issue fraction is 3x this" if precision == "bf16x3" else "algorithmic flops"),

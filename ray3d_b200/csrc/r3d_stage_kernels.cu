@@ -62,14 +62,29 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     double sp, cp;
     sincos((double)cam[4], &sp, &cp);
     const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
-    for (int i = threadIdx.x; i < T * J; i += blockDim.x) {
-      const int jj = i % J;
-      const float2 p = __ldg(uv + (flip ? i - jj + d.flip_perm[jj] : i));
-      const double xn = __ddiv_rn(__dsub_rn((double)p.x, cx), fx);
-      const double yn = __ddiv_rn(__dsub_rn((double)p.y, cy), fy);
-      xs[i * 3 + 0] = flip ? -(float)xn : (float)xn;
-      xs[i * 3 + 1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
-      xs[i * 3 + 2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
+    // keypoints are fetched in batches of 8 independent loads per thread before any float64 math touches them
+    // (one HBM round trip per batch instead of one per keypoint)
+    for (int i0 = threadIdx.x; i0 < T * J; i0 += 8 * blockDim.x) {
+      float2 pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < T * J) {
+          const int jj = i % J;
+          pv[u] = __ldg(uv + (flip ? i - jj + d.flip_perm[jj] : i));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < T * J) {
+          const double xn = __ddiv_rn(__dsub_rn((double)pv[u].x, cx), fx);
+          const double yn = __ddiv_rn(__dsub_rn((double)pv[u].y, cy), fy);
+          xs[i * 3 + 0] = flip ? -(float)xn : (float)xn;
+          xs[i * 3 + 1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
+          xs[i * 3 + 2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
+        }
+      }
     }
   } else {
     const float* x = src + (int64_t)bs * src_batch_stride;
