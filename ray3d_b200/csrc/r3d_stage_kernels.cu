@@ -106,16 +106,21 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   // produces 2 adjacent columns, so warp stores cover 128 contiguous bytes per bf16 plane and the smem reads are
   // conflict free.
   {
-    const int kp = d.k_pad, k_frames = d.w0 * JC, k_all = k_frames + JC, half = kp >> 1;
-    for (int i = threadIdx.x; i < d.L0 * half; i += blockDim.x) {
-      const int tq = i / half, kk = (i - tq * half) << 1;
-      float v[2];
+    const int kp = d.k_pad, k_frames = d.w0 * JC, k_all = k_frames + JC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const float* xtc = xs + d.tc * JC;
+    for (int tq = warp; tq < d.L0; tq += nwarp) {          // one warp per row: no index division, 128-byte warp stores
+      const float* xrow = xs + tq * k_frames;
+      const int64_t row = (int64_t)b * d.L0 + tq;
+      for (int kk = lane * 2; kk < kp; kk += 64) {
+        float v[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = kk + j;
-        v[j] = k < k_frames ? xs[tq * k_frames + k] : (k < k_all ? xs[d.tc * JC + (k - k_frames)] : 0.f);
+        for (int j = 0; j < 2; ++j) {
+          const int k = kk + j;
+          v[j] = k < k_frames ? xrow[k] : (k < k_all ? xtc[k - k_frames] : 0.f);
+        }
+        store_act2(d.a0, precision, row, kk, v[0], v[1]);
       }
-      store_act2(d.a0, precision, (int64_t)b * d.L0 + tq, kk, v[0], v[1]);
     }
   }
 
