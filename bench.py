@@ -259,7 +259,7 @@ def main():
     # -------- roofline of the dominant kernel (grouped GEMM launches of the step)
     peaks = read_peaks()
     graph = lifter.plan.describe()
-    flops = [0.0] + [sum(2.0 * B * o["rows_per_seq"] * q["n"] * q.get("alg_k", q["k"]) for q in o["prob"]) for o in graph["ops"]] + [0.0]
+    flops = [0.0] + [sum(2.0 * B * o["rows_per_seq"] * (q["n"] * q.get("alg_k", q["k"]) + q.get("n2", 0) * q.get("k2", 0)) for q in o["prob"]) for o in graph["ops"]] + [0.0]
     issue_mult = 3.0 if precision == "bf16x3" else 1.0
     per = [dict(name=n, ms=ms, gflop=f / 1e9) for (n, ms), f in zip(launch_times, flops)]
     gemms = [p for p in per if p["gflop"] > 0]

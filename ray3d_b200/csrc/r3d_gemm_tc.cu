@@ -156,6 +156,32 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// A operand from tensor memory (TS mode): lane = row, two bf16 per 32-bit column, 8 columns per K=16 step
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // TMA load whose completion is signalled on the LEADER CTA's barrier (peer bit of the cluster address cleared)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t policy) {
   asm volatile(
@@ -286,7 +312,11 @@ __device__ __forceinline__ void residual_consume(uint4* stg, const ResidualRegs&
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 
-template <int BLOCK_N, int NSPLIT, int CL>
+// FUSED: every tile runs two GEMMs back to back -- acc1 = A*W^T (K = w*C), Y = lrelu(acc1 + bias) re-split to bf16
+// hi/lo IN PLACE in tensor memory (each 32-column fp32 chunk becomes 16 hi + 16 lo packed columns), acc2 = Y*W2^T with
+// the A operand read from tensor memory (TS-mode tcgen05.mma), then the usual epilogue on acc2.  TMEM: columns
+// [0,256) acc1/Y, [256,512) acc2.  Needs BLOCK_N == 256 == channels.
+template <int BLOCK_N, int NSPLIT, int CL, bool FUSED>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
                                                                 int M, int total_tiles, int dbg) {
   // CL == 2: the CTA pair works as one 256-row tile with cta_group::2 MMAs; each CTA stages its own 128 A rows and
@@ -302,6 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   constexpr int COL_SPLIT = NCHUNK >= 2 ? 2 : 1;      // two epilogue warps share a TMEM lane quarter when possible
   constexpr int CHUNKS_PER_WARP = NCHUNK / COL_SPLIT;
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
+  static_assert(!FUSED || BLOCK_N == 256, "the fused conv pair keeps a full 256-channel row per tile");
 
   // NB: every pointer below is derived from smem_raw by constant offsets so the compiler keeps the shared address
   // space (LDS/STS); round-tripping through uintptr_t to align by hand degrades them to generic LD/ST.
@@ -420,6 +451,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (FUSED) {   // second GEMM: only W2 K blocks flow through the ring (its A operand is in tensor memory)
+          const CUtensorMap* tw = tm + kTmapW2;
+          const int nkb2 = op.prob[tc.p].K2 / TBK;
+          for (int kb = 0; kb < nkb2; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * STAGE_BYTES;
+            if (CL == 1) {
+              mbar_expect_tx(&full_bar[stage], NSPLIT * W_BYTES);
+              tma_load_2d(st + NSPLIT * A_BYTES, tw + 0, &full_bar[stage], kb * TBK, 0, kEvictLast);
+              if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tw + 1, &full_bar[stage], kb * TBK, 0, kEvictLast);
+            } else {
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * NSPLIT * W_BYTES);
+              const int wrow = crank * W_PART_ROWS;
+              tma_load_2d_2sm(st + NSPLIT * A_BYTES, tw + 2, &full_bar[stage], kb * TBK, wrow, kEvictLast);
+              if (NSPLIT == 2) tma_load_2d_2sm(st + 2 * A_BYTES + W_BYTES, tw + 3, &full_bar[stage], kb * TBK, wrow, kEvictLast);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
     __syncwarp();
@@ -432,9 +482,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if (!FUSED) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
+          tc_fence_after();
+        }   // FUSED: acc1 is free again once the previous tile's second GEMM was issued (same thread, in order)
+        const uint32_t d_tmem = tmem_base + (FUSED ? 0 : acc * BLOCK_N);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -458,16 +510,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
               }
             }
           }
+          const int tf = FUSED ? 0 : acc;
           if (CL == 1) {
             umma_commit(&empty_bar[stage]);                    // smem stage free once these MMAs retire
-            if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+            if (kb == nkb - 1) umma_commit(&tfull_bar[tf]);    // accumulator complete
           } else {                                             // ... signalled in both CTAs of the pair
             umma_commit_2sm(&empty_bar[stage], MC_MASK);
-            if (kb == nkb - 1) umma_commit_2sm(&tfull_bar[acc], MC_MASK);
+            if (kb == nkb - 1) umma_commit_2sm(&tfull_bar[tf], MC_MASK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (FUSED) {
+          // second GEMM: Y (bf16 hi/lo, written in place over acc1 by the epilogue warps) x W2^T -> acc2
+          mbar_wait(&tempty_bar[0], acc_phase);               // Y complete in both CTAs
+          mbar_wait(&tempty_bar[1], acc_phase ^ 1);           // previous tile's epilogue has drained acc2
+          tc_fence_after();
+          const uint32_t d2 = tmem_base + BLOCK_N;
+          const int nkb2 = op.prob[tc.p].K2 / TBK;
+          for (int kb = 0; kb < nkb2; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t w_hi = make_smem_desc(st + NSPLIT * A_BYTES), w_lo = make_smem_desc(st + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+            for (int k = 0; k < TBK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+              const int sidx = kb * (TBK / UMMA_K) + k;                       // K step = Y channels [16 s, 16 s + 16)
+              const uint32_t y_hi = tmem_base + 32 * (sidx >> 1) + 8 * (sidx & 1), y_lo = y_hi + 16;
+              if (CL == 1) {
+                umma_bf16_ts(d2, y_hi, w_hi + koff, idesc, (kb | k) != 0);
+                if (NSPLIT == 2) {
+                  umma_bf16_ts(d2, y_hi, w_lo + koff, idesc, 1);
+                  umma_bf16_ts(d2, y_lo, w_hi + koff, idesc, 1);
+                }
+              } else {
+                umma_bf16_ts_2sm(d2, y_hi, w_hi + koff, idesc, (kb | k) != 0);
+                if (NSPLIT == 2) {
+                  umma_bf16_ts_2sm(d2, y_hi, w_lo + koff, idesc, 1);
+                  umma_bf16_ts_2sm(d2, y_lo, w_hi + koff, idesc, 1);
+                }
+              }
+            }
+            if (CL == 1) {
+              umma_commit(&empty_bar[stage]);
+              if (kb == nkb2 - 1) umma_commit(&tfull_bar[1]);
+            } else {
+              umma_commit_2sm(&empty_bar[stage], MC_MASK);
+              if (kb == nkb2 - 1) umma_commit_2sm(&tfull_bar[1], MC_MASK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          acc_phase ^= 1;
+        } else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
@@ -505,16 +599,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + c_begin * CH, lane, m_base, M);
       constexpr bool BIAS_SMEM = CL == 2;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
       float* my_bias = bias_s + ew * 128;
+      if (FUSED) {
+        // ---- epilogue of the first GEMM: acc1 -> Y = lrelu(acc1 + bias) as bf16 hi/lo, in place in tensor memory
+        if (BIAS_SMEM) {
+          __syncwarp();
+          for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(pr.bias + c_begin * CH + j);
+          __syncwarp();
+        }
+        mbar_wait(&tfull_bar[0], acc_phase);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin * CH);
+        uint32_t r1[32];
+        tmem_ld32(ta, r1);
+#pragma unroll 1
+        for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+          float bb[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = BIAS_SMEM ? *reinterpret_cast<const float4*>(my_bias + cc * 32 + j4 * 4)
+                                        : __ldg(reinterpret_cast<const float4*>(pr.bias + (c_begin + cc) * 32) + j4);
+            bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+          }
+          tmem_ld_wait();
+          uint32_t yh[16], yl[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x0 = __uint_as_float(r1[2 * j]) + bb[2 * j], x1 = __uint_as_float(r1[2 * j + 1]) + bb[2 * j + 1];
+            x0 = fmaxf(x0, slope * x0);
+            x1 = fmaxf(x1, slope * x1);
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+            yh[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+            yl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          if (cc + 1 < CHUNKS_PER_WARP) tmem_ld32(ta + (cc + 1) * 32, r1);
+          tmem_st16(ta + cc * 32, yh);                       // channels [32c, 32c+32) -> 16 packed columns
+          if (NSPLIT == 2) tmem_st16(ta + cc * 32 + 16, yl);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CL == 1) mbar_arrive(&tempty_bar[0]);
+          else mbar_arrive_cluster(&tempty_bar[0], 0);
+        }
+      }
+      const float* const bias_ptr = FUSED ? pr.bias2 : pr.bias;
+      const int acc_col = FUSED ? BLOCK_N : acc * BLOCK_N;
+      const int fb = FUSED ? 1 : acc;                          // accumulator-full / -empty barrier of this tile
       if (BIAS_SMEM && active) {              // this warp's slice of the folded bias -> smem while the main loop still runs
         __syncwarp();
-        for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(pr.bias + tc.n0 + c_begin * CH + j);
+        for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(bias_ptr + tc.n0 + c_begin * CH + j);
         __syncwarp();
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&tfull_bar[fb], acc_phase);
       tc_fence_after();
       if (active) {
         uint32_t r[32];
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_begin * CH);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c_begin * CH);
         if (CH == 32) tmem_ld32(taddr0, r); else tmem_ld16(taddr0, r);       // chunk 0; later chunks are issued one ahead
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
@@ -530,7 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           } else {
 #pragma unroll
             for (int j4 = 0; j4 < CH / 4; ++j4) {       // folded bias: warp-uniform 16-byte loads
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(pr.bias + n) + j4);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_ptr + n) + j4);
               bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
             }
           }
@@ -626,10 +769,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CL == 1) mbar_arrive(&tempty_bar[acc]);
-        else mbar_arrive_cluster(&tempty_bar[acc], 0);        // the MMA thread lives in the leader CTA
+        if (CL == 1) mbar_arrive(&tempty_bar[fb]);
+        else mbar_arrive_cluster(&tempty_bar[fb], 0);         // the MMA thread lives in the leader CTA
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (FUSED) acc_phase ^= 1;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait0();             // every TMA store issued by this thread has landed
     __syncwarp();
@@ -715,7 +859,19 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
                      (uint64_t)g.dst[t].m.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
-    if (bn >= 32) {   // half-tile W maps for the 2-CTA multicast variant
+    if (h.fused2) {   // second weight matrix of a fused conv pair: full-tile and half-tile (2-SM) boxes
+      CUtensorMap* wm = out + p * kTmapsPerProb + kTmapW2;
+      if (bn != 256 || g.K2 % TBK || g.w2_0 == nullptr) return -5;
+      rc = encode_2d(wm + 0, g.w2_0, (uint64_t)g.K2, 256, (uint64_t)g.K2, 256);
+      if (rc) return rc;
+      rc = encode_2d(wm + 1, precision == R3D_PREC_BF16X3 ? g.w2_1 : nullptr, (uint64_t)g.K2, 256, (uint64_t)g.K2, 256);
+      if (rc) return rc;
+      rc = encode_2d(wm + 2, g.w2_0, (uint64_t)g.K2, 256, (uint64_t)g.K2, 128);
+      if (rc) return rc;
+      rc = encode_2d(wm + 3, precision == R3D_PREC_BF16X3 ? g.w2_1 : nullptr, (uint64_t)g.K2, 256, (uint64_t)g.K2, 128);
+      if (rc) return rc;
+    }
+    if (bn >= 32) {   // half-tile W maps for the 2-SM variant
       rc = encode_2d(out + p * kTmapsPerProb + 4, g.w0, (uint64_t)g.K, (uint64_t)g.n_pad, (uint64_t)g.K, (uint32_t)bn / 2);
       if (rc) return rc;
       rc = encode_2d(out + p * kTmapsPerProb + 5, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
@@ -731,9 +887,17 @@ static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_sta
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS>());
   if (e != cudaSuccess) return e;
-  if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, (BN >= 32 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, (BN >= 32 ? 2 : 1)>());
+  constexpr int CL2 = BN >= 32 ? 2 : 1;
+  if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, CL2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, CL2>());
+  if (e != cudaSuccess) return e;
+  if (BN == 256) {   // fused conv-pair variants
+    constexpr int FB = BN == 256 ? 256 : 256;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 1>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
+  }
   return e;
 }
 
@@ -782,7 +946,8 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
     cfg.gridDim = dim3(units < g_num_sms ? units : g_num_sms);
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, 1>, d_op, d_tmaps, M, units, g_dbg);
+    if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 1, true>, d_op, d_tmaps, M, units, g_dbg);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, 1, false>, d_op, d_tmaps, M, units, g_dbg);
   }
   const int max_clusters = g_num_sms / 2;
   const int clusters = units < max_clusters ? units : max_clusters;
@@ -794,7 +959,8 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   ++na;
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2>, d_op, d_tmaps, M, units, g_dbg);
+  if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, g_dbg);
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2, false>, d_op, d_tmaps, M, units, g_dbg);
 }
 
 cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h, const void* d_tmaps, int M, int precision, cudaStream_t s) {

@@ -43,6 +43,13 @@ struct GemmProb {
   int32_t n_pad;         // rows of the packed weight matrix (multiple of the op's n tile)
   int32_t ndst;
   Dst dst[kMaxDst];
+  // fused second GEMM (op.fused2): out = res + lrelu( lrelu(A*W^T + bias) * W2^T + bias2 ), the k=w conv followed by
+  // the 1x1 conv of one temporal level (rie.py:96-97); the intermediate never leaves tensor memory
+  const void* w2_0;      // [256][K2] K-major bf16 hi
+  const void* w2_1;      // bf16 lo plane or null
+  const float* bias2;
+  int32_t K2;
+  int32_t _pad2;
 };
 
 struct GemmOpDev {
@@ -52,7 +59,7 @@ struct GemmOpDev {
   int32_t n_tile;
   int32_t reverse;       // walk the tiles last-to-first (alternates per layer: the tail of the previous layer's
                          // output is what is still L2 resident when this one starts)
-  int32_t _pad;
+  int32_t fused2;        // 1: every problem carries a second weight matrix (see GemmProb::w2_0)
   GemmProb prob[kMaxProb];
 };
 
@@ -106,7 +113,8 @@ cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h_op, const v
                            cudaStream_t s);
 int tc_build_tmaps(const GemmOpDev& h_op, int precision, int64_t cap_rows, void* h_tmaps_out /* kMaxProb*4 maps */);
 cudaError_t tc_configure();
-constexpr int kTmapsPerProb = 6 + 2 * kMaxDst;   // A hi/lo, W hi/lo, W hi/lo (half tile), then {hi, lo} store maps per destination
+constexpr int kTmapsPerProb = 6 + 2 * kMaxDst + 4;   // A hi/lo, W hi/lo, W hi/lo (half tile), {hi, lo} store maps per destination, W2 hi/lo full + half
+constexpr int kTmapW2 = 6 + 2 * kMaxDst;
 constexpr int kTmapBytes = 128;
 
 }  // namespace r3d

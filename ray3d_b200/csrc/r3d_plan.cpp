@@ -111,7 +111,7 @@ struct OpHost {
   bool side = false;                     // runs on the side stream (independent of the temporal tree)
   bool join_before = false;              // first op that consumes side-stream results
   // symbolic bindings resolved to pointers once the slabs exist
-  struct Bind { int a = -1, a_ld = 0, res = -1, res_ld = 0, res_col = 0; std::string layer;
+  struct Bind { int a = -1, a_ld = 0, res = -1, res_ld = 0, res_col = 0; std::string layer, layer2;
                 std::vector<std::pair<int, int>> dst; std::vector<int> dst_f32; };
   Bind bind[kMaxProb];
 };
@@ -456,11 +456,15 @@ static void build_graph(r3d_plan* p) {
   if (fuse) for (int i = 0; i < 5; ++i) m_fuse[i] = add_mat(p, 1, 4 * L);
 
   // --- temporal tree: ping-pong X buffers, one Y scratch
+  // tensor-core precisions with 256 channels: the k=w conv and the 1x1 conv of a level run as ONE launch whose
+  // intermediate stays in tensor memory (gemm_tc_kernel FUSED); otherwise two launches through the Y scratch.
+  bool fuse_pairs = p->cfg.precision != R3D_PREC_FP32 && C == 256;
+  if (const char* env = getenv("R3D_TC_FUSE")) fuse_pairs = fuse_pairs && atoi(env) != 0;
   std::vector<int> xa(ntb), xb(ntb), yb(ntb);
   for (int q = 0; q < ntb; ++q) {
     xa[q] = add_mat(p, p->lens[0], C);
     xb[q] = nl > 1 ? add_mat(p, p->lens[1], C) : -1;
-    yb[q] = nl > 1 ? add_mat(p, p->lens[1], C) : -1;
+    yb[q] = (nl > 1 && !fuse_pairs) ? add_mat(p, p->lens[1], C) : -1;
   }
   auto lkey = [&](int q, const std::string& s) { return std::to_string(p->tbs[q].net) + ":" + p->tbs[q].prefix + s; };
   {
@@ -475,6 +479,18 @@ static void build_graph(r3d_plan* p) {
   for (int i = 1; i < nl; ++i) {
     const int w = p->widths[i];
     const std::string a = std::to_string(2 * (i - 1)), bb = std::to_string(2 * (i - 1) + 1);
+    if (fuse_pairs) {
+      OpHost& o = add_op(p, "layers_conv." + a + "+" + bb, ntb, p->lens[i], act);       // rie.py:94-97
+      o.dev.fused2 = 1;
+      for (int q = 0; q < ntb; ++q) {
+        auto& b = o.bind[q];
+        b.a = cur[q]; b.a_ld = w * C; b.layer = lkey(q, ".layers_conv." + a); b.layer2 = lkey(q, ".layers_conv." + bb);
+        b.res = cur[q]; b.res_ld = w * C; b.res_col = (w / 2) * C;
+        b.dst = {{nxt[q], 0}};
+      }
+      std::swap(cur, nxt);
+      continue;
+    }
     OpHost& o1 = add_op(p, "layers_conv." + a, ntb, p->lens[i], act);                  // rie.py:96
     for (int q = 0; q < ntb; ++q) {
       auto& b = o1.bind[q];
@@ -700,6 +716,8 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
       const PackedLayer& pl = p->layers.at(b.layer);
       j += std::string(q ? "," : "") + "{\"a\":" + std::to_string(b.a) + ",\"a_ld\":" + std::to_string(b.a_ld) + ",\"n\":" + std::to_string(pl.n) +
            ",\"k\":" + std::to_string(pl.k) + ",\"n_pad\":" + std::to_string(pl.n_pad) + ",\"k_pad\":" + std::to_string(pl.k_pad) + ",\"alg_k\":" + std::to_string(pl.alg_k ? pl.alg_k : pl.k) +
+           (b.layer2.empty() ? std::string() : ",\"layer2\":\"" + b.layer2 + "\",\"n2\":" + std::to_string(p->layers.at(b.layer2).n) +
+                                                    ",\"k2\":" + std::to_string(p->layers.at(b.layer2).k)) +
            ",\"layer\":\"" + b.layer +
            "\",\"res\":" + std::to_string(b.res) + ",\"res_ld\":" + std::to_string(b.res_ld) + ",\"res_col\":" + std::to_string(b.res_col) +
            ",\"dst\":[";
@@ -872,11 +890,19 @@ static int bind_workspace(r3d_plan* p, int cap) {
       g.K = l.k_pad; g.N = l.n; g.n_pad = l.n_pad;
       g.ndst = dsts(b.dst, b.dst_f32, g.dst);
       ntile = std::min(ntile, pick_n_tile(l.n_pad));
+      if (!b.layer2.empty()) {
+        const PackedLayer& l2 = p->layers.at(b.layer2);
+        g.w2_0 = p->d_weights + l2.off_w0;
+        g.w2_1 = (prec == R3D_PREC_BF16X3) ? p->d_weights + l2.off_w1 : nullptr;
+        g.bias2 = reinterpret_cast<const float*>(p->d_weights + l2.off_b);
+        g.K2 = l2.k_pad;
+        g.N = l2.n;
+      }
     }
     // Tile-width heuristic for the tensor path: the widest tile maximises operand reuse, but the small-M launches
     // (upper tree levels, FC chains) then occupy a fraction of the 148 SMs.  Minimise waves x (tile cost) with a
     // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
-    if (prec != R3D_PREC_FP32 && ntile > 64) {
+    if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2) {
       const int64_t m_tiles = ((int64_t)cap * op.dev.rows_per_seq + 127) / 128;
       auto cost = [&](int bn) {
         int64_t tiles = 0;

@@ -42,6 +42,11 @@ def replay(plan, x, param, dtype=np.float32):
             out = A @ w.T.astype(dtype) + b.astype(dtype)
             if op["slope"] != 1:
                 out = lrelu(out, op["slope"])
+            if "layer2" in pr:        # fused conv pair: second (1x1) GEMM on the activated intermediate
+                net2, layer2 = pr["layer2"].split(":", 1)
+                w2, b2 = plan.packed_layer(1 << int(net2), layer2)
+                out = lrelu(out[:, :w2.shape[1]] @ w2.T.astype(dtype) + b2.astype(dtype), op["slope"])
+                npad = w2.shape[0]
             if pr["res"] >= 0:
                 R = mats[pr["res"]].reshape(-1)[: M * pr["res_ld"]].reshape(M, pr["res_ld"])
                 out = out + R[:, pr["res_col"]:pr["res_col"] + npad]

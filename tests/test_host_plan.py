@@ -118,6 +118,21 @@ def test_launch_graph_replay_matches_reference(golden_meta, name):
     assert p.kernel_launches == len(p.describe()["ops"]) + 2
 
 
+@pytest.mark.parametrize("name", ["h36m_s1_t27", "rie15_s3_t27"])
+def test_fused_conv_pair_graph_replay(golden_meta, name):
+    """Tensor-core plans run each level's k=w conv + 1x1 conv as one fused launch: same function, fewer ops."""
+    spec = spec_of(golden_meta, name)
+    g = load_golden(name)
+    p, _, _ = make_plan(spec, precision="bf16x3")
+    ops = p.describe()["ops"]
+    fused = [o for o in ops if "+" in o["name"]]
+    assert len(fused) == len(spec.filter_widths) - 1 and all("layer2" in q for o in fused for q in o["prob"])
+    pos, trj = replay(p, g["x"], g["param"])
+    assert relerr(pos, g["pos64"]) < 5e-6 and relerr(trj, g["trj64"]) < 5e-6
+    p32, _, _ = make_plan(spec, precision="fp32")
+    assert len(p32.describe()["ops"]) == len(ops) + len(fused)
+
+
 @pytest.mark.parametrize("nets", [1, 2])
 def test_single_net_plans_replay(golden_meta, nets):
     spec = spec_of(golden_meta, "h36m_s3_t9")
