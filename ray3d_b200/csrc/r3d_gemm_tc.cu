@@ -742,8 +742,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                   for (int t = 0; t < pr.ndst; ++t) {
                     const Dst& d = pr.dst[t];
                     if (d.f32) continue;
-                    tma_store_2d(dmaps + 2 * t, stage_hi, d.col + n, m_base);
-                    if (d.m.p1 != nullptr) tma_store_2d(dmaps + 2 * t + 1, stage_lo, d.col + n, m_base);
+                    const int srow = (dbg & 16) ? (m_base & 127) : m_base;   // experiment: keep every store in the same L2-resident rows
+                    tma_store_2d(dmaps + 2 * t, stage_hi, d.col + n, srow);
+                    if (d.m.p1 != nullptr) tma_store_2d(dmaps + 2 * t + 1, stage_lo, d.col + n, srow);
                   }
                   bulk_commit();
                 }
@@ -902,7 +903,7 @@ static cudaError_t configure_one() {
 }
 
 static int g_num_sms = 0;
-static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 enable the L2 prefetch cursor (timing experiments only)
+static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 enable the L2 prefetch cursor, 16 fold all stores onto 128 rows (timing experiments only)
 static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
 
