@@ -176,6 +176,13 @@ R3D_API int r3d_forward_video_tta(r3d_plan* plan, const float* seq_dev, const fl
 R3D_API int r3d_ray_encode_f64(const double* uv_dev, double* ray_dev, int64_t n_points, double fx, double fy,
                        double ppx, double ppy, double cos_pitch, double sin_pitch, void* stream);
 
+/* CameraInfoPacket.undistort_point (lib/camera/camera.py:412-421): cv2.undistortPoints(points, K, dist_coeff, P=K) with the
+ * 5-coefficient radial/tangential model (k1, k2, p1, p2, k3; dist5_host is a HOST array).  uv_dev/out_dev (n_points, 2)
+ * float64 pixels; may alias.  Five fixed-point iterations like OpenCV's default for this overload; bit-identical to
+ * opencv-python 4.13 (the reference pins 4.4.0.42, requirements.txt:40). */
+R3D_API int r3d_undistort_points_f64(const double* uv_dev, double* out_dev, int64_t n_points, double fx, double fy, double cx,
+                                     double cy, const double* dist5_host, void* stream);
+
 /* normalize_screen_coordinates (lib/camera/camera.py:11-18) in float64 for the cfg_rie_* (in_features == 2)
  * input encoding: out = xy / w * 2 - [1, h / w].  xy_dev/out_dev (n_points, 2) float64; may alias. */
 R3D_API int r3d_normalize_screen_f64(const double* xy_dev, double* out_dev, int64_t n_points, double w, double h,

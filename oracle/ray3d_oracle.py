@@ -58,6 +58,28 @@ def camera_pitch_height(R: np.ndarray, t: np.ndarray) -> Tuple[float, float]:
     return pitch, height
 
 
+def undistort_points(uv: np.ndarray, K: np.ndarray, dist: Sequence[float]) -> np.ndarray:
+    """camera.py:412-421: cv2.undistortPoints(points, K, dist_coeff, P=K) for the 5-coefficient model.
+    Third-party arithmetic (OpenCV, pinned opencv-python==4.4.0.42 in requirements.txt:40; pinned here against
+    4.13.0 of this image through tests/golden/camera_undistort.npz): x=(u-cx)/fx by reciprocal multiply, 5 fixed-point
+    iterations x <- (x0 - dx(x,y)) / (1 + k1 r2 + k2 r2^2 + k3 r2^3), then back through P=K."""
+    uv = np.asarray(uv, dtype=np.float64)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    k1, k2, p1, p2, k3 = (np.float64(c) for c in dist)
+    ifx, ify = 1.0 / fx, 1.0 / fy
+    x = (uv[..., 0] - cx) * ifx
+    y = (uv[..., 1] - cy) * ify
+    x0, y0 = x.copy(), y.copy()
+    for _ in range(5):
+        r2 = x * x + y * y
+        icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2)
+        dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x)
+        dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y
+        x = (x0 - dx) * icdist
+        y = (y0 - dy) * icdist
+    return np.stack([fx * x + cx, fy * y + cy], axis=-1)
+
+
 def ray_encode(uv: np.ndarray, fx, fy, cx, cy, pitch) -> np.ndarray:
     """camera.py:423-441 + 460-471 (+ Rc2n from 325-345), undistort=False.
 

@@ -60,6 +60,7 @@ EXPORTS = {
     "r3d_forward_rays_tta": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_forward_video_tta": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_ray_encode_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_double] * 6 + [C.c_void_p]),
+    "r3d_undistort_points_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_double] * 4 + [C.POINTER(C.c_double), C.c_void_p]),
     "r3d_normalize_screen_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "r3d_eval_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_selftest_gemm": (C.c_int, [C.c_int32] * 6 + [C.POINTER(C.c_double)] * 3),

@@ -4,7 +4,8 @@ Mirrors the slice of ``CameraInfoPacket`` that is on the hot path (SURVEY 8a row
 
   normalize_screen_coordinates ... lib/camera/camera.py:11-18
   pitch / height / Rc2n .......... lib/camera/camera.py:245-259, 285-345
-  encode_uv_with_intrinsic ....... lib/camera/camera.py:423-441   (undistort=False)
+  encode_uv_with_intrinsic ....... lib/camera/camera.py:423-441
+  undistort_point ................ lib/camera/camera.py:412-421   (cv2.undistortPoints, 5 coefficients)
   get_cam_ray_given_uv ........... lib/camera/camera.py:460-471
 
 The per-camera scalars (pitch, height) are host float64 math, computed once per camera exactly
@@ -52,19 +53,22 @@ def normalize_screen_coordinates(X: ArrayLike, w: float, h: float, device: Optio
 class RayCamera:
     """The subset of CameraInfoPacket (camera.py:208-504) the lifting path needs.
 
-    One must supply K, R, t like the reference (P is never used on this path).  ``undistort=True``
-    (cv2.undistortPoints, camera.py:412-421) is not implemented: it is third-party iterative
-    arithmetic scoped as a later row."""
+    One must supply K, R, t like the reference (P is never used on this path).  With ``undistort=True``
+    keypoints and the principal point first go through the lens undistortion of camera.py:412-421
+    (cv2.undistortPoints(pts, K, dist_coeff, P=K), 5-coefficient model) -- on the device, bit-identical to
+    opencv-python 4.13."""
 
     def __init__(self, K, R, t, res_w=None, res_h=None, undistort=False, dist_coeff=None):
         if undistort:
-            raise NotImplementedError("lens undistortion (cv2.undistortPoints) is out of scope of the ray3d_b200 hot path")
+            if dist_coeff is None or np.asarray(dist_coeff).size != 5:
+                raise ValueError("undistort=True needs the 5 distortion coefficients (k1, k2, p1, p2, k3)")
+        self.dist_coeff = None if dist_coeff is None else np.asarray(dist_coeff, dtype=np.float64).reshape(-1)
         K = np.asarray(K, dtype=np.float64)
         R = np.asarray(R, dtype=np.float64)
         t = np.asarray(t, dtype=np.float64).reshape(3, 1)
         assert K.shape == (3, 3) and R.shape == (3, 3)
         self.K, self.Rw2c, self.Tw2c = K, R, t
-        self.res_w, self.res_h, self.undistort = res_w, res_h, False
+        self.res_w, self.res_h, self.undistort = res_w, res_h, bool(undistort)
         self.Rc2w = R.T
         # camera.py:273-283,308-316: optical axis in world coordinates vs world up
         # (Rc2w @ e_z is exactly the third column of Rc2w: index it instead of going through BLAS)
@@ -75,7 +79,10 @@ class RayCamera:
         self.height = float(self.cam_orig_world[2, 0])                   # trainer.py:297
         c, s = math.cos(self.cam_pitch_rad), math.sin(self.cam_pitch_rad)
         self.Rc2n = np.array([[1.0, 0.0, 0.0], [0.0, c, s], [0.0, -s, c]])   # camera.py:333-338
-        self.pp_cam = np.array([[K[0, 2], K[1, 2]]])                     # camera.py:258-259
+        if self.undistort:                                               # camera.py:253-256
+            self.pp_cam = self._undistort_host(K[0, 2], K[1, 2]).reshape(1, 2)
+        else:
+            self.pp_cam = np.array([[K[0, 2], K[1, 2]]])                 # camera.py:258-259
         # normalised frame <-> world (camera.py:246-256): Tc2n = (0, -height, 0)
         Tc2n = np.array([[0.0], [-self.height], [0.0]])
         self.Rn2w = self.Rc2w @ self.Rc2n.T
@@ -87,13 +94,49 @@ class RayCamera:
         return np.array([self.height, self.cam_pitch_rad], dtype=np.float32)
 
     def table_row(self) -> np.ndarray:
-        """[fx, fy, cx, cy, pitch, height] row for Lifter.forward_uv."""
+        """[fx, fy, cx, cy, pitch, height] row for Lifter.forward_uv (pinhole cameras: a distorted lens goes through
+        get_cam_ray_given_uv + forward_rays, the order the reference's dataset code uses)."""
+        if self.undistort:
+            raise ValueError("forward_uv has no lens model: use get_cam_ray_given_uv() and Lifter.forward_rays for undistort=True")
         return np.array([self.K[0, 0], self.K[1, 1], self.K[0, 2], self.K[1, 2], self.cam_pitch_rad, self.height], dtype=np.float32)
+
+    def _undistort_host(self, u: float, v: float) -> np.ndarray:
+        """One point through the same arithmetic as the device kernel (python floats are IEEE doubles, no FMA):
+        used once per camera for the principal point (camera.py:253-256)."""
+        fx, fy, cx, cy = (float(self.K[0, 0]), float(self.K[1, 1]), float(self.K[0, 2]), float(self.K[1, 2]))
+        k1, k2, p1, p2, k3 = (float(c) for c in self.dist_coeff)
+        ifx, ify = 1.0 / fx, 1.0 / fy
+        x = (u - cx) * ifx
+        y = (v - cy) * ify
+        x0, y0 = x, y
+        for _ in range(5):
+            r2 = x * x + y * y
+            icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2)
+            dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x)
+            dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y
+            x = (x0 - dx) * icdist
+            y = (y0 - dy) * icdist
+        return np.array([fx * x + cx, fy * y + cy], dtype=np.float64)
+
+    def undistort_point(self, points2d: ArrayLike, device: Optional[int] = None):
+        """camera.py:412-421 on the device: (F, J, 2) pixels -> undistorted pixels, float64."""
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        x = _to_cuda_f64(points2d, dev)
+        assert x.shape[-1] == 2 and self.dist_coeff is not None
+        out = torch.empty_like(x)
+        d5 = (_capi.C.c_double * 5)(*[float(c) for c in self.dist_coeff])
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().r3d_undistort_points_f64(x.data_ptr(), out.data_ptr(), x.numel() // 2, float(self.K[0, 0]),
+                                                             float(self.K[1, 1]), float(self.K[0, 2]), float(self.K[1, 2]), d5,
+                                                             torch.cuda.current_stream(dev).cuda_stream))
+        return _back(out, points2d)
 
     def _encode(self, uv: ArrayLike, c: float, s: float, device):
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         x = _to_cuda_f64(uv, dev)
         assert x.shape[-1] == 2
+        if self.undistort:                                               # camera.py:435-436
+            x = self.undistort_point(x, dev.index)
         out = torch.empty(x.shape[:-1] + (3,), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _capi.check(_capi.lib().r3d_ray_encode_f64(x.data_ptr(), out.data_ptr(), x.numel() // 2, float(self.K[0, 0]),

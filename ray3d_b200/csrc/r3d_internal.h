@@ -105,6 +105,8 @@ cudaError_t launch_ray_encode_f64(const double* uv, double* ray, int64_t n, doub
                                   double ppy, double c, double s, cudaStream_t st);
 cudaError_t launch_normalize_screen_f64(const double* xy, double* out, int64_t n, double w, double h, cudaStream_t st);
 cudaError_t launch_eval_metrics(const float* pred, const float* target, int frames, int J, const double* rt, double* acc, cudaStream_t st);
+cudaError_t launch_undistort_points_f64(const double* uv, double* out, int64_t n, double fx, double fy, double cx, double cy,
+                                        const double* dist5, cudaStream_t st);
 cudaError_t prologue_configure(int max_smem_bytes);
 
 // tensor-core path (r3d_gemm_tc.cu)

@@ -1250,6 +1250,13 @@ extern "C" R3D_API int r3d_ray_encode_f64(const double* uv, double* ray, int64_t
   return R3D_OK;
 }
 
+extern "C" R3D_API int r3d_undistort_points_f64(const double* uv, double* out, int64_t n, double fx, double fy, double cx, double cy,
+                                        const double* dist5_host, void* stream) {
+  if (!uv || !out || !dist5_host || n < 0) return fail(R3D_ERR_BAD_ARG, "r3d_undistort_points_f64: bad argument");
+  CUDA_TRY(launch_undistort_points_f64(uv, out, n, fx, fy, cx, cy, dist5_host, (cudaStream_t)stream));
+  return R3D_OK;
+}
+
 extern "C" R3D_API int r3d_normalize_screen_f64(const double* xy, double* out, int64_t n, double w, double h, void* stream) {
   if (!xy || !out || n < 0 || w == 0.0) return fail(R3D_ERR_BAD_ARG, "r3d_normalize_screen_f64: bad argument");
   CUDA_TRY(launch_normalize_screen_f64(xy, out, n, w, h, (cudaStream_t)stream));

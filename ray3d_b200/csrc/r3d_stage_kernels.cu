@@ -233,6 +233,42 @@ cudaError_t launch_ray_encode_f64(const double* uv, double* ray, int64_t n, doub
   return cudaGetLastError();
 }
 
+// ---- lens undistortion: CameraInfoPacket.undistort_point (camera.py:412-421) == cv2.undistortPoints(pts, K, dist, P=K)
+// with the 5-coefficient model (k1, k2, p1, p2, k3).  OpenCV's default termination for this overload is exactly 5
+// fixed-point iterations; the arithmetic below follows cvUndistortPointsInternal operation by operation with
+// round-to-nearest multiplies/adds (no FMA contraction), which reproduces opencv-python 4.13 bit for bit.
+__global__ void undistort_points_f64_kernel(const double2* __restrict__ uv, double2* __restrict__ out, int64_t n, double fx, double fy,
+                                            double cx, double cy, double k1, double k2, double p1, double p2, double k3) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ifx = __ddiv_rn(1.0, fx), ify = __ddiv_rn(1.0, fy);
+  const double2 p = uv[i];
+  double x = __dmul_rn(__dsub_rn(p.x, cx), ifx), y = __dmul_rn(__dsub_rn(p.y, cy), ify);
+  const double x0 = x, y0 = y;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    // numerator 1 + ((k6 r2 + k5) r2 + k4) r2 with k4..k6 = 0 evaluates to exactly 1
+    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
+    const double icdist = __ddiv_rn(1.0, den);
+    const double two_xx = __dmul_rn(__dmul_rn(2.0, x), x), two_yy = __dmul_rn(__dmul_rn(2.0, y), y);
+    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y), __dmul_rn(p2, __dadd_rn(r2, two_xx)));
+    const double dy = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, two_yy)), __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+  }
+  // P = K:  xx = fx*x + 0*y + cx,  ww = 1/(0*x + 0*y + 1) = 1
+  out[i] = make_double2(__dadd_rn(__dmul_rn(fx, x), cx), __dadd_rn(__dmul_rn(fy, y), cy));
+}
+
+cudaError_t launch_undistort_points_f64(const double* uv, double* out, int64_t n, double fx, double fy, double cx, double cy,
+                                        const double* dist5, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  undistort_points_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const double2*>(uv), reinterpret_cast<double2*>(out),
+                                                                          n, fx, fy, cx, cy, dist5[0], dist5[1], dist5[2], dist5[3], dist5[4]);
+  return cudaGetLastError();
+}
+
 // ---- normalize_screen_coordinates (camera.py:11-18): X / w * 2 - [1, h / w], float64 ---------------
 __global__ void normalize_screen_f64_kernel(const double2* __restrict__ xy, double2* __restrict__ out, int64_t n, double w,
                                             double hw) {

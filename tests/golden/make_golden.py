@@ -133,6 +133,14 @@ def main():
     np.savez_compressed(os.path.join(HERE, "camera.npz"),
                         **{f"{k}{i}": np.asarray(c[k]) for i, c in enumerate(cams) for k in c})
 
+    # lens undistortion through the reference class (cv2.undistortPoints, camera.py:412-441, 460-471)
+    dist = np.array([-0.2075, 0.2478, -0.0014, -0.00098, -0.00307])          # H36M-like k1 k2 p1 p2 k3
+    pk = CameraInfoPacket(P=None, K=cams[1]["K"], R=cams[1]["R"], t=cams[1]["t"], dist_coeff=dist, res_w=1000, res_h=1002, undistort=True)
+    uvd = np.random.default_rng(77).uniform(0, 1000, size=(7, 17, 2))
+    np.savez_compressed(os.path.join(HERE, "camera_undistort.npz"), K=cams[1]["K"], R=cams[1]["R"], t=cams[1]["t"], dist=dist, uv=uvd,
+                        und=pk.undistort_point(uvd), pp_cam=pk.pp_cam, enc=pk.encode_uv_with_intrinsic(uvd),
+                        ray=pk.get_cam_ray_given_uv(uvd), cv2_version=np.array(__import__("cv2").__version__))
+
     # evaluation tail: normalized2world (camera.py:401-410) + MPJPE family (lib/loss/loss.py) as evaluate_core uses them
     from lib.loss.loss import mpjpe, n_mpjpe, mean_velocity_error, p_mpjpe  # noqa: E402  (reference)
     pkt = CameraInfoPacket(P=None, K=cams[0]["K"], R=cams[0]["R"], t=cams[0]["t"], dist_coeff=None, res_w=1000, res_h=1002, undistort=False)

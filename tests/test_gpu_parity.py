@@ -125,8 +125,24 @@ def test_camera_encode_bit_exact_vs_reference():
         assert np.allclose(got, c[f"ray{i}"], rtol=0, atol=1e-14)
         assert np.array_equal(cam.encode_uv_with_intrinsic(c[f"uv{i}"]), c[f"enc{i}"])
         assert np.array_equal(ray3d_b200.normalize_screen_coordinates(c[f"uv{i}"], 1000, 1002), c[f"norm{i}"])
-    with pytest.raises(NotImplementedError):
-        RayCamera(c["K0"], c["R0"], c["t0"], undistort=True)
+    with pytest.raises(ValueError):
+        RayCamera(c["K0"], c["R0"], c["t0"], undistort=True)          # no coefficients
+
+
+def test_lens_undistortion_bit_exact():
+    """RayCamera(undistort=True) vs the reference's CameraInfoPacket (cv2.undistortPoints, camera.py:412-441): the
+    device iteration reproduces OpenCV's doubles bit for bit; the ray adds the host-dependent pitch scalar."""
+    g = load_golden("camera_undistort")
+    cam = RayCamera(g["K"], g["R"], g["t"], res_w=1000, res_h=1002, undistort=True, dist_coeff=g["dist"])
+    assert np.array_equal(cam.pp_cam.reshape(-1), g["pp_cam"].reshape(-1))
+    assert np.array_equal(cam.undistort_point(g["uv"]), g["und"])
+    assert np.array_equal(cam.undistort_point(g["uv"]), O.undistort_points(g["uv"], g["K"], g["dist"]))
+    assert np.array_equal(cam.encode_uv_with_intrinsic(g["uv"]), g["enc"])
+    assert np.allclose(cam.get_cam_ray_given_uv(g["uv"]), g["ray"], rtol=0, atol=1e-14)
+    t = torch.from_numpy(g["uv"]).cuda()
+    assert np.array_equal(cam.undistort_point(t).cpu().numpy(), g["und"])
+    with pytest.raises(ValueError):
+        cam.table_row()
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -121,3 +121,16 @@ def test_sharded_lift_all_gather_gloo_world2(batch):
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), res
     assert all(r[2] == (batch, 1, 17, 3) for r in res)
+
+
+def test_camera_undistorted_principal_point_host():
+    """RayCamera(undistort=True) computes pp_cam on the host with the device kernel's arithmetic; it must match the
+    reference's cv2.undistortPoints value bit for bit (camera.py:253-256)."""
+    from conftest import load_golden
+    g = load_golden("camera_undistort")
+    cam = ray3d_b200.RayCamera(g["K"], g["R"], g["t"], undistort=True, dist_coeff=g["dist"])
+    assert np.array_equal(cam.pp_cam.reshape(-1), g["pp_cam"].reshape(-1))
+    with pytest.raises(ValueError):
+        ray3d_b200.RayCamera(g["K"], g["R"], g["t"], undistort=True)
+    with pytest.raises(ValueError):
+        cam.table_row()

@@ -93,3 +93,12 @@ def test_eval_tail_matches_reference_losses():
     got = O.eval_metrics(pw, tw)
     for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve"):
         assert abs(got[k] - float(m[k])) <= 1e-12 * abs(float(m[k])), k
+
+
+def test_undistort_matches_reference_cv2():
+    """oracle.undistort_points vs the reference's CameraInfoPacket(undistort=True) (cv2.undistortPoints): bit-exact."""
+    g = load_golden("camera_undistort")
+    und = O.undistort_points(g["uv"], g["K"], g["dist"])
+    assert np.array_equal(und, g["und"])
+    pp = O.undistort_points(np.array([[g["K"][0, 2], g["K"][1, 2]]]), g["K"], g["dist"])
+    assert np.array_equal(pp.reshape(-1), g["pp_cam"].reshape(-1))
