@@ -191,9 +191,10 @@ R3D_API int r3d_normalize_screen_f64(const double* xy_dev, double* out_dev, int6
 /* --- evaluation tail on the device: cam.normalized2world (lib/camera/camera.py:401-410) followed by the error sums of
  * mpjpe / root mpjpe / n_mpjpe / mean_velocity_error (lib/loss/loss.py:12-18, 72-81, 95-104) as evaluate_core applies
  * them (trainer.py:355-395), in float64 like the reference.  pred_dev/target_dev (frames, joints, 3) float32;
- * rn2w_tn2w_dev: 12 doubles = Rn2w row-major then Tn2w, or NULL to stay in the normalised frame; sums_dev: 4 doubles
- * written with [sum ||p-t||, sum over frames of the root error, sum ||s*p-t||, sum of velocity errors]; the caller
- * divides by frames*joints, frames, frames*joints and (frames-1)*joints.  p_mpjpe (Procrustes/SVD) is not covered. */
+ * rn2w_tn2w_dev: 12 doubles = Rn2w row-major then Tn2w, or NULL to stay in the normalised frame; sums_dev: 5 doubles
+ * written with [sum ||p-t||, sum over frames of the root error, sum ||s*p-t||, sum of velocity errors, sum of the
+ * errors after per-frame Procrustes alignment (p_mpjpe, loss.py:30-69: 3x3 SVD by Jacobi rotations)]; the caller
+ * divides by frames*joints, frames, frames*joints, (frames-1)*joints and frames*joints. */
 R3D_API int r3d_eval_metrics(const float* pred_dev, const float* target_dev, int32_t frames, int32_t joints,
                              const double* rn2w_tn2w_dev, double* sums_dev, void* stream);
 

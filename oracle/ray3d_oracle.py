@@ -261,7 +261,25 @@ def eval_metrics(pred_world: np.ndarray, target_world: np.ndarray) -> Dict[str, 
     nm = torch.mean(torch.norm(norm_t / norm_p * p - t, dim=3)).item()
     pn, tn = p.numpy().reshape(-1, p.shape[-2], 3), t.numpy().reshape(-1, p.shape[-2], 3)
     mv = float(np.mean(np.linalg.norm(np.diff(pn, axis=0) - np.diff(tn, axis=0), axis=2)))
-    return {"mpjpe": mp, "mrpe": mr, "n_mpjpe": nm, "mpjve": mv}
+    return {"mpjpe": mp, "mrpe": mr, "n_mpjpe": nm, "mpjve": mv, "p_mpjpe": p_mpjpe(pn, tn)}
+
+
+def p_mpjpe(predicted: np.ndarray, target: np.ndarray) -> float:
+    """lib/loss/loss.py:30-69: MPJPE after per-frame similarity alignment (orthogonal Procrustes through the SVD of
+    X0^T Y0, reflection fix on the last singular vector, scale = trace * |X0| / |Y0|).  (F, J, 3) float64."""
+    muX, muY = target.mean(axis=1, keepdims=True), predicted.mean(axis=1, keepdims=True)
+    X0, Y0 = target - muX, predicted - muY
+    normX = np.sqrt((X0 ** 2).sum(axis=(1, 2), keepdims=True))
+    normY = np.sqrt((Y0 ** 2).sum(axis=(1, 2), keepdims=True))
+    U, s, Vt = np.linalg.svd(np.matmul((X0 / normX).transpose(0, 2, 1), Y0 / normY))
+    V = Vt.transpose(0, 2, 1).copy()
+    sign = np.sign(np.linalg.det(np.matmul(V, U.transpose(0, 2, 1))))
+    V[:, :, -1] *= sign[:, None]
+    s[:, -1] *= sign
+    R = np.matmul(V, U.transpose(0, 2, 1))
+    a = s.sum(axis=1)[:, None, None] * normX / normY
+    aligned = a * np.matmul(predicted, R) + (muX - a * np.matmul(muY, R))
+    return float(np.mean(np.linalg.norm(aligned - target, axis=2)))
 
 
 def eval_windows(seq: Tensor, receptive_field: int) -> Tensor:

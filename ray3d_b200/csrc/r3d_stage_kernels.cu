@@ -288,7 +288,59 @@ cudaError_t launch_normalize_screen_f64(const double* xy, double* out, int64_t n
 // ---- evaluation tail: normalized2world (camera.py:401-410) + MPJPE / MRPE / N-MPJPE / MPJVE (lib/loss/loss.py) ------
 // One warp per frame, lane = joint (J <= 32), float64 like the reference (numpy promotes the float32 predictions when
 // they are multiplied by the float64 Rn2w).  acc[0..3] += sum of per-joint errors: position, root, scale-normalised
-// position, velocity.  Means are taken by the caller (trainer.py:386-395 weights them by frame count anyway).
+// position, velocity; acc[4] += sum of per-joint errors after the similarity (Procrustes) alignment of p_mpjpe
+// (loss.py:30-69).  Means are taken by the caller (trainer.py:386-395 weights them by frame count anyway).
+
+// Singular value decomposition of a 3x3 matrix (row-major H = U diag(s) V^T, s descending) by one-sided Jacobi
+// rotations on the columns: stands in for np.linalg.svd (loss.py:50).  U, V are only determined up to paired column
+// signs, but R = V U^T and the singular values -- all p_mpjpe uses -- are unique for non-degenerate poses.
+__device__ void svd3x3(const double* H, double* U, double* sv, double* V) {
+  double A[9];
+  for (int i = 0; i < 9; ++i) { A[i] = H[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+#pragma unroll 1
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      double alpha = 0, beta = 0, gamma = 0;
+      for (int i = 0; i < 3; ++i) { alpha += A[3 * i + p] * A[3 * i + p]; beta += A[3 * i + q] * A[3 * i + q]; gamma += A[3 * i + p] * A[3 * i + q]; }
+      if (fabs(gamma) <= 1e-15 * sqrt(alpha * beta) || gamma == 0.0) continue;
+      rotated = true;
+      const double zeta = (beta - alpha) / (2.0 * gamma);
+      const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+      for (int i = 0; i < 3; ++i) {
+        const double ap = A[3 * i + p], aq = A[3 * i + q];
+        A[3 * i + p] = c * ap - sn * aq; A[3 * i + q] = sn * ap + c * aq;
+        const double vp = V[3 * i + p], vq = V[3 * i + q];
+        V[3 * i + p] = c * vp - sn * vq; V[3 * i + q] = sn * vp + c * vq;
+      }
+    }
+    if (!rotated) break;
+  }
+  for (int k = 0; k < 3; ++k) sv[k] = sqrt(A[k] * A[k] + A[3 + k] * A[3 + k] + A[6 + k] * A[6 + k]);
+  auto swap_cols = [&](int a, int b) {
+    for (int i = 0; i < 3; ++i) {
+      double x = A[3 * i + a]; A[3 * i + a] = A[3 * i + b]; A[3 * i + b] = x;
+      x = V[3 * i + a]; V[3 * i + a] = V[3 * i + b]; V[3 * i + b] = x;
+    }
+    const double x = sv[a]; sv[a] = sv[b]; sv[b] = x;
+  };
+  if (sv[0] < sv[1]) swap_cols(0, 1);
+  if (sv[1] < sv[2]) swap_cols(1, 2);
+  if (sv[0] < sv[1]) swap_cols(0, 1);
+  for (int k = 0; k < 2; ++k) {
+    const double inv = sv[k] > 0.0 ? 1.0 / sv[k] : 0.0;
+    for (int i = 0; i < 3; ++i) U[3 * i + k] = A[3 * i + k] * inv;
+  }
+  if (sv[2] > 1e-14 * sv[0]) {
+    for (int i = 0; i < 3; ++i) U[3 * i + 2] = A[3 * i + 2] / sv[2];
+  } else {  // planar pose: complete the basis; the reflection fix below makes R independent of this sign
+    U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+}
+
 __global__ void eval_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target, int frames, int J,
                                     const double* __restrict__ rt /* 9 + 3, or null */, double* __restrict__ acc) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -330,17 +382,53 @@ __global__ void eval_metrics_kernel(const float* __restrict__ pred, const float*
     const double dx = scale * p[0] - t[0], dy = scale * p[1] - t[1], dz = scale * p[2] - t[2];
     e_n = sqrt(dx * dx + dy * dy + dz * dz);
   }
-  const double a0 = wsum(e_pos), a2 = wsum(e_n), a3 = wsum(e_vel);
+  // p_mpjpe (loss.py:30-69): X = target, Y = predicted; every lane carries one joint and the 3x3 algebra redundantly
+  double e_pa = 0;
+  {
+    double muX[3], muY[3], X0[3], Y0[3];
+    for (int i = 0; i < 3; ++i) { muX[i] = wsum(on ? t[i] : 0.0) / J; muY[i] = wsum(on ? p[i] : 0.0) / J; }
+    for (int i = 0; i < 3; ++i) { X0[i] = on ? t[i] - muX[i] : 0.0; Y0[i] = on ? p[i] - muY[i] : 0.0; }
+    const double normX = sqrt(wsum(X0[0] * X0[0] + X0[1] * X0[1] + X0[2] * X0[2]));
+    const double normY = sqrt(wsum(Y0[0] * Y0[0] + Y0[1] * Y0[1] + Y0[2] * Y0[2]));
+    for (int i = 0; i < 3; ++i) { X0[i] /= normX; Y0[i] /= normY; }
+    double H[9], U[9], sv[3], V[9], R[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) H[3 * a + b] = wsum(X0[a] * Y0[b]);                 // H = X0^T Y0   (:49)
+    svd3x3(H, U, sv, V);
+    auto vut = [&]() {                                                            // R = V U^T     (:52, :58)
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = V[3 * i] * U[3 * j] + V[3 * i + 1] * U[3 * j + 1] + V[3 * i + 2] * U[3 * j + 2];
+    };
+    vut();
+    const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+    if (det < 0.0) {                                                              // reflections   (:55-58)
+      for (int i = 0; i < 3; ++i) V[3 * i + 2] = -V[3 * i + 2];
+      sv[2] = -sv[2];
+      vut();
+    }
+    const double a = (sv[0] + sv[1] + sv[2]) * normX / normY;                      // scale         (:60-62)
+    if (on) {
+      double d2 = 0;
+      for (int j = 0; j < 3; ++j) {                                               // a * pred @ R + t - target  (:63-69)
+        const double tj = muX[j] - a * (muY[0] * R[j] + muY[1] * R[3 + j] + muY[2] * R[6 + j]);
+        const double al = a * (p[0] * R[j] + p[1] * R[3 + j] + p[2] * R[6 + j]) + tj;
+        d2 += (al - t[j]) * (al - t[j]);
+      }
+      e_pa = sqrt(d2);
+    }
+  }
+  const double a0 = wsum(e_pos), a2 = wsum(e_n), a3 = wsum(e_vel), a4 = wsum(e_pa);
   if (lane == 0) {
     atomicAdd(acc + 0, a0);
     atomicAdd(acc + 1, e_root);
     atomicAdd(acc + 2, a2);
     atomicAdd(acc + 3, a3);
+    atomicAdd(acc + 4, a4);
   }
 }
 
 cudaError_t launch_eval_metrics(const float* pred, const float* target, int frames, int J, const double* rt, double* acc, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(acc, 0, 4 * sizeof(double), st);
+  cudaError_t e = cudaMemsetAsync(acc, 0, 5 * sizeof(double), st);
   if (e != cudaSuccess || frames <= 0) return e;
   const int warps_per_block = 8;
   eval_metrics_kernel<<<(frames + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(pred, target, frames, J, rt, acc);

@@ -252,10 +252,35 @@ def test_eval_tail_on_device_matches_reference():
     """normalized2world + mpjpe / mrpe / n_mpjpe / mpjve (trainer.py:355-395) vs values computed by the reference."""
     m = load_golden("metrics")
     got = ray3d_b200.metrics.evaluate(torch.from_numpy(m["pred"]).cuda(), torch.from_numpy(m["target"]).cuda(), m["Rn2w"], m["Tn2w"])
-    for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve"):
+    for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve", "p_mpjpe"):
         assert abs(got[k] - float(m[k])) <= 1e-11 * abs(float(m[k])), (k, got[k], float(m[k]))
     cam = RayCamera(m["K"], m["R"], m["t"])
     assert np.allclose(cam.Rn2w, m["Rn2w"], rtol=0, atol=1e-14) and np.allclose(cam.Tn2w, m["Tn2w"], rtol=0, atol=1e-13)
     plain = ray3d_b200.metrics.evaluate(torch.from_numpy(m["pred"]).cuda(), torch.from_numpy(m["target"]).cuda())
     ref = O.eval_metrics(m["pred"].astype(np.float64), m["target"].astype(np.float64))
     assert abs(plain["mpjpe"] - ref["mpjpe"]) < 1e-12 and abs(plain["mpjve"] - ref["mpjve"]) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["mirrored", "planar", "scaled_rotated", "j15"])
+def test_procrustes_alignment_edge_cases(case):
+    """p_mpjpe (loss.py:30-69) on poses that exercise the reflection fix (det R < 0), a rank-2 (planar) pose whose
+    third singular value vanishes, an exact similarity transform (error -> 0) and a 15-joint skeleton."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    J = 15 if case == "j15" else 17
+    target = rng.standard_normal(size=(33, J, 3)).astype(np.float32)
+    if case == "mirrored":
+        pred = target * np.array([-1, 1, 1], np.float32) + 0.05 * rng.standard_normal(size=target.shape).astype(np.float32)
+    elif case == "planar":
+        target[..., 2] = 0.25
+        pred = target + 0.05 * rng.standard_normal(size=target.shape).astype(np.float32)
+        pred[..., 2] = -0.5
+    elif case == "scaled_rotated":
+        c, s = np.cos(0.7), np.sin(0.7)
+        pred = (1.7 * target @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32) + np.float32(0.3)).astype(np.float32)
+    else:
+        pred = target + 0.1 * rng.standard_normal(size=target.shape).astype(np.float32)
+    got = ray3d_b200.metrics.evaluate(torch.from_numpy(pred).cuda(), torch.from_numpy(target).cuda())["p_mpjpe"]
+    want = O.p_mpjpe(pred.astype(np.float64), target.astype(np.float64))
+    assert abs(got - want) <= 1e-10 * max(abs(want), 1e-3), (case, got, want)
+    if case == "scaled_rotated":
+        assert got < 1e-6

@@ -91,7 +91,7 @@ def test_eval_tail_matches_reference_losses():
     tw = O.normalized2world(m["target"], m["Rn2w"], m["Tn2w"])
     assert np.array_equal(pw, m["pred_world"]) and np.array_equal(tw, m["target_world"])
     got = O.eval_metrics(pw, tw)
-    for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve"):
+    for k in ("mpjpe", "mrpe", "n_mpjpe", "mpjve", "p_mpjpe"):
         assert abs(got[k] - float(m[k])) <= 1e-12 * abs(float(m[k])), k
 
 
