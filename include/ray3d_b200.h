@@ -149,6 +149,18 @@ R3D_API int r3d_forward_rays_host(r3d_plan* plan, const float* x_host, const flo
 R3D_API int r3d_forward_uv_host(r3d_plan* plan, const float* uv_host, const float* cam_host, float* pos_host,
                         float* trj_host, float* sum_host, int32_t batch);
 
+/* Asynchronous form of the two calls above for streaming use (a loader thread feeding batches): the H2D copy, the
+ * launches and the D2H copy are only enqueued -- on the plan's own copy/compute streams with two device staging slots,
+ * so the copy of one submission overlaps the kernels of the previous one -- and *ticket names the submission.  Host
+ * buffers must be page-locked and stay untouched until r3d_wait(plan, ticket) returns; results are then in pos/trj/sum.
+ * Submissions complete in order; at most 8 may be outstanding (the 9th submit blocks on the oldest).
+ * Stands in for the reference's DataLoader(pin_memory) + .cuda() + forward + .cpu() loop body, trainer.py:318-364. */
+R3D_API int r3d_submit_rays_host(r3d_plan* plan, const float* x_host, const float* param_host, float* pos_host, float* trj_host,
+                                 float* sum_host, int32_t batch, uint64_t* ticket);
+R3D_API int r3d_submit_uv_host(r3d_plan* plan, const float* uv_host, const float* cam_host, float* pos_host, float* trj_host,
+                               float* sum_host, int32_t batch, uint64_t* ticket);
+R3D_API int r3d_wait(r3d_plan* plan, uint64_t ticket);
+
 /* Sliding-window evaluation of one video without materialising windows:
  * replaces Trainer.eval_data_prepare + np.tile(cam_param) + forward (trainer.py:47-58, 323-337).
  * seq_dev (F + RF - 1, J, Cin) float32 (already edge-padded like generators.py:209-234);

@@ -55,6 +55,9 @@ EXPORTS = {
     "r3d_forward_uv": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_forward_rays_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
     "r3d_forward_uv_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]),
+    "r3d_submit_rays_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.POINTER(C.c_uint64)]),
+    "r3d_submit_uv_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.POINTER(C.c_uint64)]),
+    "r3d_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "r3d_forward_video": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_plan_set_flip": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "r3d_forward_rays_tta": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
@@ -235,6 +238,19 @@ class Plan:
 
     def forward_uv_host(self, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int) -> None:
         check(lib().r3d_forward_uv_host(self._h, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch))
+
+    def submit_uv_host(self, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int) -> int:
+        t = C.c_uint64(0)
+        check(lib().r3d_submit_uv_host(self._h, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch, C.byref(t)))
+        return int(t.value)
+
+    def submit_rays_host(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int) -> int:
+        t = C.c_uint64(0)
+        check(lib().r3d_submit_rays_host(self._h, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch, C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        check(lib().r3d_wait(self._h, ticket))
 
 
 def selftest_gemm(m: int, n: int, k: int, nprob: int = 1, precision: str = "bf16x3", device: int = 0):

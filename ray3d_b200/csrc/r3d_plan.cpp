@@ -161,6 +161,10 @@ struct r3d_plan {
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  static constexpr int kTicketRing = 8;      // asynchronous host submissions in flight (r3d_submit_*_host / r3d_wait)
+  cudaEvent_t ev_ticket[kTicketRing] = {};
+  uint64_t submit_seq = 0;                   // tickets handed out so far
+  uint64_t slot_seq = 0;                     // staging-slot uses so far (alternates the two slots across calls)
   char* d_stage = nullptr;
   size_t stage_bytes = 0;
   std::mutex mu;
@@ -771,6 +775,10 @@ static void free_device(r3d_plan* p) {
     if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
     p->ev_in[i] = p->ev_done[i] = nullptr;
   }
+  for (int i = 0; i < r3d_plan::kTicketRing; ++i) {
+    if (p->ev_ticket[i]) cudaEventDestroy(p->ev_ticket[i]);
+    p->ev_ticket[i] = nullptr;
+  }
   for (auto& e : p->prof_ev) cudaEventDestroy(e);
   p->prof_ev.clear();
   p->prof_runs = 0;
@@ -837,6 +845,9 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   for (int i = 0; i < 2; ++i) {
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < r3d_plan::kTicketRing; ++i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_ticket[i], cudaEventDisableTiming));
   }
   p->uploaded = true;
   return R3D_OK;
@@ -1135,16 +1146,26 @@ extern "C" R3D_API int r3d_forward_video_tta(r3d_plan* p, const float* seq, cons
 
 // Host-buffer forward: chunks of the batch flow H2D (copy stream) -> compute stream -> D2H (copy stream)
 // with two staging slots so the PCIe transfer of chunk i+1 overlaps the kernels of chunk i.
+// ticket == nullptr: synchronous (results are in host memory on return).  Otherwise the copies and launches are only
+// enqueued (two staging slots: the H2D copy of one submission overlaps the kernels of the previous one) and *ticket
+// identifies the submission for r3d_wait.
 static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                        float* pos, float* trj, float* sum, int batch) {
+                        float* pos, float* trj, float* sum, int batch, uint64_t* ticket = nullptr) {
   int rc = check_forward(p, src, pos, trj, sum, batch);
   if (rc) return rc;
-  if (batch == 0) return R3D_OK;
-  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
+  if (batch == 0 && ticket == nullptr) return R3D_OK;
+  if (batch != 0 && p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   std::lock_guard<std::mutex> lk(p->mu);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  if (batch == 0) {   // empty submission: a ticket that completes with everything enqueued before it
+    if (p->submit_seq >= (uint64_t)r3d_plan::kTicketRing) CUDA_TRY(cudaEventSynchronize(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing]));
+    CUDA_TRY(cudaEventRecord(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing], p->s_comp));
+    *ticket = p->submit_seq++;
+    if (dev != p->device) cudaSetDevice(dev);
+    return R3D_OK;
+  }
   // chunking trades PCIe/compute overlap against per-launch efficiency (small batches under-fill the GPU)
   // measured on B200 (T=243): 1024-sequence chunks keep the kernels efficient; smaller chunks lose more in
   // under-filled launches than they gain in copy/compute overlap (H2D of 1024 windows is 0.6 ms at 55 GB/s)
@@ -1161,16 +1182,17 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
     p->stage_bytes = 2 * slot;
   }
   rc = ensure_capacity(p, chunk);
-  int it = 0;
-  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += chunk, ++it) {
-    const int nb = std::min(chunk, batch - b0), sl = it & 1;
+  if (ticket != nullptr && p->submit_seq >= (uint64_t)r3d_plan::kTicketRing)   // the ring slot's previous owner has completed
+    CUDA_TRY(cudaEventSynchronize(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing]));
+  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += chunk) {
+    const int nb = std::min(chunk, batch - b0), sl = (int)(p->slot_seq++ & 1);
     char* base = p->d_stage + (size_t)sl * slot;
     float* d_in = reinterpret_cast<float*>(base);
     float* d_prm = reinterpret_cast<float*>(base + al(in_b));
     float* d_pos = reinterpret_cast<float*>(base + al(in_b) + al(prm_b));
     float* d_sum = reinterpret_cast<float*>(base + al(in_b) + al(prm_b) + al(out_b));
     float* d_trj = reinterpret_cast<float*>(base + al(in_b) + al(prm_b) + 2 * al(out_b));
-    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(p->s_copy, p->ev_done[sl], 0));   // slot's previous results have left
+    CUDA_TRY(cudaStreamWaitEvent(p->s_copy, p->ev_done[sl], 0));   // slot's previous results have left (no-op on first use)
     CUDA_TRY(cudaMemcpyAsync(d_in, src + (int64_t)b0 * src_stride, (size_t)nb * src_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
     if (prm) CUDA_TRY(cudaMemcpyAsync(d_prm, prm + (int64_t)b0 * prm_stride, (size_t)nb * prm_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
     CUDA_TRY(cudaEventRecord(p->ev_in[sl], p->s_copy));
@@ -1183,12 +1205,43 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
     if (trj) CUDA_TRY(cudaMemcpyAsync(trj + (int64_t)b0 * 3, d_trj, (size_t)nb * 12, cudaMemcpyDeviceToHost, p->s_comp));
     CUDA_TRY(cudaEventRecord(p->ev_done[sl], p->s_comp));
   }
-  if (rc == R3D_OK) {
+  if (rc == R3D_OK && ticket != nullptr) {
+    CUDA_TRY(cudaEventRecord(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing], p->s_comp));
+    *ticket = p->submit_seq++;
+  } else if (rc == R3D_OK) {
     CUDA_TRY(cudaStreamSynchronize(p->s_comp));
     CUDA_TRY(cudaStreamSynchronize(p->s_copy));
   }
   if (dev != p->device) cudaSetDevice(dev);
   return rc;
+}
+
+extern "C" R3D_API int r3d_submit_rays_host(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum, int32_t batch,
+                                            uint64_t* ticket) {
+  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
+  return forward_host(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, ticket);
+}
+
+extern "C" R3D_API int r3d_submit_uv_host(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum, int32_t batch,
+                                          uint64_t* ticket) {
+  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
+  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_submit_uv_host needs in_features == 3");
+  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim must be 2");
+  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
+  return forward_host(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, ticket);
+}
+
+extern "C" R3D_API int r3d_wait(r3d_plan* p, uint64_t ticket) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (ticket >= p->submit_seq) return fail(R3D_ERR_BAD_ARG, "r3d_wait: unknown ticket");
+    if (ticket + r3d_plan::kTicketRing < p->submit_seq) return R3D_OK;   // recycled: its successor in the ring was submitted after it completed
+    ev = p->ev_ticket[ticket % r3d_plan::kTicketRing];
+  }
+  CUDA_TRY(cudaEventSynchronize(ev));
+  return R3D_OK;
 }
 
 extern "C" R3D_API int r3d_forward_rays_host(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum, int32_t batch) {

@@ -191,6 +191,39 @@ class Lifter:
                 raise RuntimeError("forward_uv_host needs the pose net")
         return out
 
+    def submit_uv_host(self, uv: torch.Tensor, cam: torch.Tensor, out: torch.Tensor) -> int:
+        """Asynchronous forward_uv_host for streaming: uv/cam/out are PINNED, contiguous CPU tensors that stay untouched
+        until ``wait(ticket)``; the H2D copy of this submission overlaps the kernels of the previous one."""
+        for t in (uv, cam, out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned():
+                raise ValueError("submit_uv_host needs pinned, contiguous float32 CPU tensors")
+        B = uv.shape[0]
+        assert out.shape == (B, 1, self.spec.num_joints, 3)
+        with torch.cuda.device(self.device):
+            if self.has_pos and self.has_trj:
+                return self.plan.submit_uv_host(_ptr(uv), _ptr(cam), None, None, _ptr(out), B)
+            if self.has_pos:
+                return self.plan.submit_uv_host(_ptr(uv), _ptr(cam), _ptr(out), None, None, B)
+        raise RuntimeError("submit_uv_host needs the pose net")
+
+    def submit_rays_host(self, x: torch.Tensor, param: Optional[torch.Tensor], out: torch.Tensor) -> int:
+        """Asynchronous forward_rays_host (see submit_uv_host)."""
+        self._check_x(x)
+        for t in (x, param, out):
+            if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned()):
+                raise ValueError("submit_rays_host needs pinned, contiguous float32 CPU tensors")
+        B = x.shape[0]
+        assert out.shape == (B, 1, self.spec.num_joints, 3)
+        with torch.cuda.device(self.device):
+            if self.has_pos and self.has_trj:
+                return self.plan.submit_rays_host(_ptr(x), _ptr(param), None, None, _ptr(out), B)
+            return self.plan.submit_rays_host(_ptr(x), _ptr(param), _ptr(out), None, None, B)
+
+    def wait(self, ticket: int) -> None:
+        """Block until the submission named by ``ticket`` has its results in host memory."""
+        with torch.cuda.device(self.device):
+            self.plan.wait(ticket)
+
     def forward_rays_host(self, x: torch.Tensor, param: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
         assert not x.is_cuda and x.dtype == torch.float32
         self._check_x(x)

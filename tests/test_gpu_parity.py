@@ -73,6 +73,33 @@ def test_forward_uv_fuses_the_ray_encode(golden_meta, name, precision):
     assert torch.equal(out, both.cpu())
 
 
+def test_streaming_submit_wait_matches_blocking_call(golden_meta):
+    """r3d_submit_uv_host / r3d_submit_rays_host / r3d_wait: many submissions in flight (more than the ticket ring and
+    the two staging slots), ragged batch sizes, results identical to the blocking host call."""
+    name = "h36m_s1_t27"
+    spec, lf, _, _ = lifter_for(golden_meta, name, "bf16x3")
+    rng = np.random.Generator(np.random.PCG64(5))
+    jobs = []
+    for i, B in enumerate([5, 130, 1, 64, 300, 7, 33, 2, 129, 65, 17, 256]):
+        uv, cam = synth.make_inputs(spec, B, seed=900 + i)
+        uv_t, cam_t = torch.from_numpy(uv).pin_memory(), torch.from_numpy(cam).pin_memory()
+        out = torch.full((B, 1, spec.num_joints, 3), float("nan")).pin_memory()
+        jobs.append((uv_t, cam_t, out, lf.submit_uv_host(uv_t, cam_t, out)))
+    assert [j[3] for j in jobs] == list(range(jobs[0][3], jobs[0][3] + len(jobs)))      # tickets are consecutive
+    for uv_t, cam_t, out, tk in reversed(jobs):                                         # waiting out of order is fine
+        lf.wait(tk)
+        assert torch.equal(out, lf.forward_uv_host(uv_t, cam_t))
+    g = load_golden(name)
+    x, prm = torch.from_numpy(g["x"]).pin_memory(), torch.from_numpy(g["param"]).pin_memory()
+    out = torch.empty((x.shape[0], 1, spec.num_joints, 3)).pin_memory()
+    lf.wait(lf.submit_rays_host(x, prm, out))
+    assert relerr(out.numpy(), g["pos64"] + g["trj64"]) < TOL["bf16x3"]
+    with pytest.raises(RuntimeError):
+        lf.wait(10 ** 9)                                                                # never handed out
+    with pytest.raises(ValueError):
+        lf.submit_uv_host(torch.from_numpy(g["uv"]), torch.from_numpy(g["cam"]).pin_memory(), out)   # pageable input
+
+
 def test_modules_drop_in_forward(golden_meta, monkeypatch):
     monkeypatch.setenv("RAY3D_B200_PRECISION", "fp32")
     name = "h36m_s3_t9"
