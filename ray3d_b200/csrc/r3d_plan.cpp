@@ -839,7 +839,14 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
+  {   // experiment knobs: R3D_SIDE_STREAM=0 serialises the GlobalInfo chain; R3D_SIDE_PRIO=-1/0/1 sets its stream priority
+    int prio = 0;
+    if (const char* env = getenv("R3D_SIDE_PRIO")) prio = atoi(env);
+    if (const char* env = getenv("R3D_SIDE_STREAM")) p->use_side_stream = atoi(env) != 0;
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least urgent (numerically largest)
+    CUDA_TRY(cudaStreamCreateWithPriority(&p->s_side, cudaStreamNonBlocking, prio > 0 ? lo : prio < 0 ? hi : 0));
+  }
   CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
@@ -1021,7 +1028,11 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
   // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
   // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.
   const bool use_side = p->use_side_stream;
-  bool forked = false;
+  bool forked = false, fork_recorded = false;
+  if (use_side) {
+    for (const OpHost& oh : p->ops) fork_recorded |= oh.side;
+    if (fork_recorded) CUDA_TRY(cudaEventRecord(p->ev_fork, s));   // right after the input stage, before any GEMM is enqueued
+  }
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const OpHost& oh = p->ops[i];
     const GemmOpDev* d_op = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops) + i;
@@ -1029,7 +1040,6 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
     cudaStream_t st = s;
     if (use_side && oh.side) {
       if (!forked) {
-        CUDA_TRY(cudaEventRecord(p->ev_fork, s));      // recorded right after the input stage in stream order
         CUDA_TRY(cudaStreamWaitEvent(p->s_side, p->ev_fork, 0));
         forked = true;
       }

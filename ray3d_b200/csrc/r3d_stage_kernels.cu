@@ -38,6 +38,19 @@ __device__ __forceinline__ void store_act2(const Mat& m, int precision, int64_t 
   }
 }
 
+// IEEE-754 correctly rounded a / b from rb = RN(1 / b) with five FMA-pipe operations instead of the ~30-instruction
+// __ddiv_rn sequence: after one residual correction q is faithful, and with a correctly rounded reciprocal the second
+// correction rounds to RN(a / b) (Markstein's theorem; scripts/check_fma_division.c compares 4e8 operand pairs of
+// this path's ranges with the hardware quotient: no mismatch).  No overflow/underflow handling: operands are pixel
+// offsets and focal lengths.
+__device__ __forceinline__ double div_by(double a, double b, double rb) {
+  double q = __dmul_rn(a, rb);
+  double r = __fma_rn(-q, b, a);
+  q = __fma_rn(r, rb, q);
+  r = __fma_rn(-q, b, a);
+  return __fma_rn(r, rb, q);
+}
+
 // One CTA per sequence (window).  Dynamic smem: T*J*Cin floats (+ embed scratch).
 __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
                                                        const float* __restrict__ src, int64_t src_batch_stride,
@@ -59,6 +72,7 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     // camera.py:438-439,471 in float64, then .astype(float32) (trainer.py:298)
     const float* cam = cam_or_param + (int64_t)bs * param_stride;
     const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const double rfx = __ddiv_rn(1.0, fx), rfy = __ddiv_rn(1.0, fy);
     double sp, cp;
     sincos((double)cam[4], &sp, &cp);
     const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
@@ -78,8 +92,8 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * blockDim.x;
         if (i < T * J) {
-          const double xn = __ddiv_rn(__dsub_rn((double)pv[u].x, cx), fx);
-          const double yn = __ddiv_rn(__dsub_rn((double)pv[u].y, cy), fy);
+          const double xn = div_by(__dsub_rn((double)pv[u].x, cx), fx, rfx);
+          const double yn = div_by(__dsub_rn((double)pv[u].y, cy), fy, rfy);
           xs[i * 3 + 0] = flip ? -(float)xn : (float)xn;
           xs[i * 3 + 1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
           xs[i * 3 + 2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);

@@ -38,7 +38,7 @@ def child_forward(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    n = 10
+    n = 100
     for _ in range(n):
         out = lf.forward_uv(uvc, camc)[2]
     e1.record()
