@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* yready_bar = bars + 2 * STAGES + 4; // [2]  FUSED: channels [0,128) / [128,256) of the intermediate are in tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
   uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][sets][2 planes][32 rows x 64 B]
   float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes + 8 * 4096 * (CL == 2 ? 2 : 1));   // CL == 2: [EPI_WARPS][128]
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EPI_WARPS * CL);                // CL == 2: the peer's epilogue warps arrive remotely
+      mbar_init(&yready_bar[a], EPI_WARPS * CL);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
+        const int k_steps = op.prob[tc.p].k_steps > 0 ? op.prob[tc.p].k_steps : nkb * (TBK / UMMA_K);
         if (!FUSED) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
           tc_fence_after();
@@ -493,8 +496,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + NSPLIT * A_BYTES);
           const uint64_t a_lo = make_smem_desc(st + A_BYTES), w_lo = make_smem_desc(st + 2 * A_BYTES + W_BYTES);
+          const int steps_here = k_steps - kb * (TBK / UMMA_K);           // < 4 only in a zero-padded last block
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
+            if (k >= steps_here) break;
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // 32 bytes per K step inside the swizzle atom
             if (CL == 1) {
               umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
@@ -522,12 +527,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         }
         if (FUSED) {
           // second GEMM: Y (bf16 hi/lo, written in place over acc1 by the epilogue warps) x W2^T -> acc2
-          mbar_wait(&tempty_bar[0], acc_phase);               // Y complete in both CTAs
+          // The epilogue warps convert Y in two halves; the K blocks over channels [0,128) start while the second
+          // half is still being converted.
+          mbar_wait(&yready_bar[0], acc_phase);               // first half of Y complete in both CTAs
+          if (op.flags & 1) mbar_wait(&yready_bar[1], acc_phase);
           mbar_wait(&tempty_bar[1], acc_phase ^ 1);           // previous tile's epilogue has drained acc2
           tc_fence_after();
           const uint32_t d2 = tmem_base + BLOCK_N;
           const int nkb2 = op.prob[tc.p].K2 / TBK;
           for (int kb = 0; kb < nkb2; ++kb) {
+            if (kb == nkb2 / 2) {
+              mbar_wait(&yready_bar[1], acc_phase);           // second half of Y
+              tc_fence_after();
+            }
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
@@ -601,23 +613,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       float* my_bias = bias_s + ew * 128;
       if (FUSED) {
         // ---- epilogue of the first GEMM: acc1 -> Y = lrelu(acc1 + bias) as bf16 hi/lo, in place in tensor memory
+        // This warp converts chunks {2*half, 2*half+1} of the first 128 channels, signals, then the same two chunks of
+        // the second 128 channels: the MMA thread starts the second GEMM on the first half meanwhile.
+        auto chunk_of = [&](int cc) { return (cc >> 1) * 4 + half * 2 + (cc & 1); };
         if (BIAS_SMEM) {
           __syncwarp();
-          for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(pr.bias + c_begin * CH + j);
+          for (int j = lane; j < 4 * 32; j += 32) my_bias[j] = __ldg(pr.bias + chunk_of(j >> 5) * 32 + (j & 31));
           __syncwarp();
         }
         mbar_wait(&tfull_bar[0], acc_phase);
         tc_fence_after();
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin * CH);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t r1[32];
-        tmem_ld32(ta, r1);
+        tmem_ld32(ta + chunk_of(0) * 32, r1);
 #pragma unroll 1
-        for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
+          const int g = chunk_of(cc);
           float bb[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b4 = BIAS_SMEM ? *reinterpret_cast<const float4*>(my_bias + cc * 32 + j4 * 4)
-                                        : __ldg(reinterpret_cast<const float4*>(pr.bias + (c_begin + cc) * 32) + j4);
+                                        : __ldg(reinterpret_cast<const float4*>(pr.bias + g * 32) + j4);
             bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
           }
           tmem_ld_wait();
@@ -633,16 +649,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
             yl[j] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-          if (cc + 1 < CHUNKS_PER_WARP) tmem_ld32(ta + (cc + 1) * 32, r1);
-          tmem_st16(ta + cc * 32, yh);                       // channels [32c, 32c+32) -> 16 packed columns
-          if (NSPLIT == 2) tmem_st16(ta + cc * 32 + 16, yl);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CL == 1) mbar_arrive(&tempty_bar[0]);
-          else mbar_arrive_cluster(&tempty_bar[0], 0);
+          if (cc + 1 < 4) tmem_ld32(ta + chunk_of(cc + 1) * 32, r1);
+          tmem_st16(ta + g * 32, yh);                        // channels [32g, 32g+32) -> 16 packed columns
+          if (NSPLIT == 2) tmem_st16(ta + g * 32 + 16, yl);
+          if (cc & 1) {                                      // a 128-channel half of Y is complete for this warp's rows
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CL == 1) mbar_arrive(&yready_bar[cc >> 1]);
+              else mbar_arrive_cluster(&yready_bar[cc >> 1], 0);
+            }
+          }
         }
       }
       const float* const bias_ptr = FUSED ? pr.bias2 : pr.bias;

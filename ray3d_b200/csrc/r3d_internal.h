@@ -49,7 +49,7 @@ struct GemmProb {
   const void* w2_1;      // bf16 lo plane or null
   const float* bias2;
   int32_t K2;
-  int32_t _pad2;
+  int32_t k_steps;       // 16-wide K steps of the first GEMM that hold non-zero weights (ceil(real K / 16)); 0 => K / 16
 };
 
 struct GemmOpDev {
@@ -60,6 +60,8 @@ struct GemmOpDev {
   int32_t reverse;       // walk the tiles last-to-first (alternates per layer: the tail of the previous layer's
                          // output is what is still L2 resident when this one starts)
   int32_t fused2;        // 1: every problem carries a second weight matrix (see GemmProb::w2_0)
+  int32_t flags;         // bit 0: fused pair waits for the whole intermediate before the second GEMM (experiments)
+  int32_t _pad;
   GemmProb prob[kMaxProb];
 };
 

@@ -464,11 +464,21 @@ static void build_graph(r3d_plan* p) {
   // intermediate stays in tensor memory (gemm_tc_kernel FUSED); otherwise two launches through the Y scratch.
   bool fuse_pairs = p->cfg.precision != R3D_PREC_FP32 && C == 256;
   if (const char* env = getenv("R3D_TC_FUSE")) fuse_pairs = fuse_pairs && atoi(env) != 0;
+  // Levels with few rows per window (the top of the tree) are one-wave launches: a fused tile there serialises
+  // GEMM -> convert -> GEMM -> store on a fraction of the SMs, while two narrow-tile launches spread over all of them.
+  int fuse_min_rows = 3;
+  if (const char* env = getenv("R3D_TC_FUSE_MIN_ROWS")) fuse_min_rows = atoi(env);
+  std::vector<char> lvl_fused(nl, 0);
+  int y_len = 0;
+  for (int i = 1; i < nl; ++i) {
+    lvl_fused[i] = fuse_pairs && p->lens[i] >= fuse_min_rows;
+    if (!lvl_fused[i]) y_len = std::max(y_len, p->lens[i]);
+  }
   std::vector<int> xa(ntb), xb(ntb), yb(ntb);
   for (int q = 0; q < ntb; ++q) {
     xa[q] = add_mat(p, p->lens[0], C);
     xb[q] = nl > 1 ? add_mat(p, p->lens[1], C) : -1;
-    yb[q] = (nl > 1 && !fuse_pairs) ? add_mat(p, p->lens[1], C) : -1;
+    yb[q] = y_len > 0 ? add_mat(p, y_len, C) : -1;
   }
   auto lkey = [&](int q, const std::string& s) { return std::to_string(p->tbs[q].net) + ":" + p->tbs[q].prefix + s; };
   {
@@ -483,7 +493,7 @@ static void build_graph(r3d_plan* p) {
   for (int i = 1; i < nl; ++i) {
     const int w = p->widths[i];
     const std::string a = std::to_string(2 * (i - 1)), bb = std::to_string(2 * (i - 1) + 1);
-    if (fuse_pairs) {
+    if (lvl_fused[i]) {
       OpHost& o = add_op(p, "layers_conv." + a + "+" + bb, ntb, p->lens[i], act);       // rie.py:94-97
       o.dev.fused2 = 1;
       for (int q = 0; q < ntb; ++q) {
@@ -906,6 +916,8 @@ static int bind_workspace(r3d_plan* p, int cap) {
       g.res = mat(b.res, b.res_ld);
       g.res_col = b.res_col;
       g.K = l.k_pad; g.N = l.n; g.n_pad = l.n_pad;
+      g.k_steps = (l.k + 15) / 16;                 // the zero-padded tail of the last K block is never multiplied
+      if (const char* env = getenv("R3D_TC_KTRIM")) if (atoi(env) == 0) g.k_steps = 0;
       g.ndst = dsts(b.dst, b.dst_f32, g.dst);
       ntile = std::min(ntile, pick_n_tile(l.n_pad));
       if (!b.layer2.empty()) {
@@ -941,6 +953,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
       op.dev.reverse = (i % 2 == 0) ? 1 : 0;
       ++i;
     }
+    if (const char* env = getenv("R3D_TC_YSPLIT")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.flags |= 1;
     if (const char* env = getenv("R3D_TC_REVERSE")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.reverse = 0;
   }
   // prologue
