@@ -191,13 +191,25 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
       : "memory");
 }
 // arrive on the barrier at the same smem offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-      "r"(rank)
-      : "memory");
+// Arrive on a barrier of CTA `rank` of the cluster.  These arrivals only hand tensor-memory columns back and forth
+// (the tcgen05.wait / tcgen05.fence pair around them orders those accesses), no shared/global data is published, so
+// the arrive is .relaxed: the .release.cluster form costs a MEMBAR.ALL.CTA + ERRBAR per arrival, which ncu showed as
+// 17% of all stall samples of the first-layer launch (22% of the epilogue warps' time).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank, bool release = false) {
+  if (release)
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -658,7 +670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             __syncwarp();
             if (lane == 0) {
               if (CL == 1) mbar_arrive(&yready_bar[cc >> 1]);
-              else mbar_arrive_cluster(&yready_bar[cc >> 1], 0);
+              else mbar_arrive_cluster(&yready_bar[cc >> 1], 0, (op.flags & 2) != 0);
             }
           }
         }
@@ -789,7 +801,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       __syncwarp();
       if (lane == 0) {
         if (CL == 1) mbar_arrive(&tempty_bar[fb]);
-        else mbar_arrive_cluster(&tempty_bar[fb], 0);         // the MMA thread lives in the leader CTA
+        else mbar_arrive_cluster(&tempty_bar[fb], 0, (op.flags & 2) != 0);         // the MMA thread lives in the leader CTA
       }
       if (FUSED) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }

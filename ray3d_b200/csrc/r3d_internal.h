@@ -60,7 +60,8 @@ struct GemmOpDev {
   int32_t reverse;       // walk the tiles last-to-first (alternates per layer: the tail of the previous layer's
                          // output is what is still L2 resident when this one starts)
   int32_t fused2;        // 1: every problem carries a second weight matrix (see GemmProb::w2_0)
-  int32_t flags;         // bit 0: fused pair waits for the whole intermediate before the second GEMM (experiments)
+  int32_t flags;         // experiments: bit 0 fused pair waits for the whole intermediate before the second GEMM;
+                         // bit 1 release (instead of relaxed) remote barrier arrivals
   int32_t _pad;
   GemmProb prob[kMaxProb];
 };

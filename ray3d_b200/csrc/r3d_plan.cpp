@@ -954,6 +954,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
       ++i;
     }
     if (const char* env = getenv("R3D_TC_YSPLIT")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.flags |= 1;
+    if (const char* env = getenv("R3D_TC_RELEASE_ARRIVE")) if (atoi(env) != 0) for (auto& op : p->ops) op.dev.flags |= 2;
     if (const char* env = getenv("R3D_TC_REVERSE")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.reverse = 0;
   }
   // prologue
