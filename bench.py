@@ -179,13 +179,15 @@ def main():
     dsets = [(u.to(dev), c.to(dev)) for u, c in sets]
     hsets = [(u.pin_memory(), c.pin_memory()) for u, c in sets]
     total_B = B * world
-    gathered = torch.empty((total_B, spec.num_joints + 1, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    # N > 1: the (B, J+1, 3) results of every step are all-gathered; the collective of step i runs on NCCL's stream
+    # under the kernels of step i+1 (two buffer pairs), and the timed region ends only after the last one has landed
+    gatherer = rdist.OverlappedGather(B, spec.num_joints, dev, depth=2) if world > 1 else None
 
     def step(i):
         uv, cam = dsets[i % NSETS]
         pos, trj, both = lifter.forward_uv(uv, cam, want_pos=False)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rdist.pack_outputs(both, trj))
+            gatherer.submit(both, trj)
         return both
 
     def barrier():
@@ -206,6 +208,8 @@ def main():
     e0.record()
     for i in range(args.steps):
         out = step(i)
+    if world > 1:
+        gatherer.drain()          # the current stream waits for the collectives still in flight
     e1.record()
     barrier()
     t1 = time.time()

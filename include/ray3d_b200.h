@@ -112,7 +112,11 @@ R3D_API int r3d_plan_describe(const r3d_plan* plan, char* out, int64_t cap, int6
 R3D_API int64_t r3d_plan_weight_bytes(const r3d_plan* plan);     /* device bytes of packed weights */
 R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* plan);  /* device bytes of activations at current capacity */
 R3D_API int r3d_plan_receptive_field(const r3d_plan* plan);       /* rie.py:278-282 */
-R3D_API int r3d_plan_kernel_launches(const r3d_plan* plan);       /* kernels one forward enqueues */
+R3D_API int r3d_plan_kernel_launches(const r3d_plan* plan);
+/* Forward calls on device pointers with batch <= 64 (R3D_GRAPH_MAX_BATCH) replay a CUDA graph of the launch sequence,
+ * captured once per (batch, input kind, output set): one cudaGraphLaunch instead of ~20 launches on two streams.
+ * Returns how many forwards of this plan went through a graph (instrumentation). */
+R3D_API int64_t r3d_plan_graph_launches(const r3d_plan* plan);       /* kernels one forward enqueues */
 
 /* Per-launch device timing (benchmark instrumentation): when enabled every forward records CUDA events on the
  * launch stream around each kernel.  r3d_plan_launch_times synchronises on the recorded events and returns the

@@ -48,6 +48,7 @@ EXPORTS = {
     "r3d_plan_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "r3d_plan_receptive_field": (C.c_int, [C.c_void_p]),
     "r3d_plan_kernel_launches": (C.c_int, [C.c_void_p]),
+    "r3d_plan_graph_launches": (C.c_int64, [C.c_void_p]),
     "r3d_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "r3d_plan_launch_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "r3d_plan_launch_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
@@ -198,6 +199,11 @@ class Plan:
     @property
     def kernel_launches(self) -> int:
         return int(lib().r3d_plan_kernel_launches(self._h))
+
+    @property
+    def graph_launches(self) -> int:
+        """forwards of this plan that replayed a captured CUDA graph (small batches)"""
+        return int(lib().r3d_plan_graph_launches(self._h))
 
     def set_profiling(self, enable: bool) -> None:
         check(lib().r3d_plan_set_profiling(self._h, 1 if enable else 0))

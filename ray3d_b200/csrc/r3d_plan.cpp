@@ -167,8 +167,28 @@ struct r3d_plan {
   uint64_t slot_seq = 0;                     // staging-slot uses so far (alternates the two slots across calls)
   char* d_stage = nullptr;
   size_t stage_bytes = 0;
+  // small batches are launch-latency bound (~20 launches, 2 streams): their launch sequence is captured once into a
+  // CUDA graph per (batch, input kind, output set) and replayed with one cudaGraphLaunch
+  struct GraphEntry {
+    int batch = 0, is_uv = 0, mask = 0;
+    int64_t src_stride = 0, prm_stride = 0;
+    cudaGraphExec_t exec = nullptr;
+    char* buf = nullptr;                         // static input/output buffers the captured kernels point at
+    size_t off_prm = 0, off_pos = 0, off_sum = 0, off_trj = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  int graph_max_batch = 64;                      // R3D_GRAPH_MAX_BATCH; 0 disables
+  uint64_t graph_launches = 0;
   std::mutex mu;
 };
+
+static void clear_graphs(r3d_plan* p) {
+  for (auto& g : p->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.buf) cudaFree(g.buf);
+  }
+  p->graphs.clear();
+}
 
 
 // ---- expected state_dict entries ---------------------------------------------------------------
@@ -755,6 +775,7 @@ extern "C" R3D_API int64_t r3d_plan_weight_bytes(const r3d_plan* p) { return p ?
 extern "C" R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* p) { return p ? (int64_t)p->ws_bytes : 0; }
 extern "C" R3D_API int r3d_plan_receptive_field(const r3d_plan* p) { return p ? p->T : 0; }
 extern "C" R3D_API int r3d_plan_kernel_launches(const r3d_plan* p) { return p ? (int)p->ops.size() + 2 : 0; }
+extern "C" R3D_API int64_t r3d_plan_graph_launches(const r3d_plan* p) { return p ? (int64_t)p->graph_launches : 0; }
 
 // ---- device upload -------------------------------------------------------------------------------
 static uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn (finite inputs)
@@ -772,6 +793,7 @@ static float bf2f(uint16_t h) {
 }
 
 static void free_device(r3d_plan* p) {
+  clear_graphs(p);
   if (p->device < 0) return;
   int prev = 0;
   cudaGetDevice(&prev);
@@ -853,6 +875,7 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
     int prio = 0;
     if (const char* env = getenv("R3D_SIDE_PRIO")) prio = atoi(env);
     if (const char* env = getenv("R3D_SIDE_STREAM")) p->use_side_stream = atoi(env) != 0;
+    if (const char* env = getenv("R3D_GRAPH_MAX_BATCH")) p->graph_max_batch = std::max(0, atoi(env));
     int lo = 0, hi = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least urgent (numerically largest)
     CUDA_TRY(cudaStreamCreateWithPriority(&p->s_side, cudaStreamNonBlocking, prio > 0 ? lo : prio < 0 ? hi : 0));
@@ -874,6 +897,7 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
 static int bind_workspace(r3d_plan* p, int cap) {
   const int prec = p->cfg.precision;
   if (p->d_ws) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(p->d_ws)); p->d_ws = nullptr; }
+  clear_graphs(p);                               // captured launches point into the old workspace / descriptors
   if (p->d_desc) { CUDA_TRY(cudaFree(p->d_desc)); p->d_desc = nullptr; }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
@@ -1092,6 +1116,57 @@ static int check_forward(r3d_plan* p, const void* src, float* pos, float* trj, f
   return R3D_OK;
 }
 
+// Small-batch path: replay the captured launch sequence.  Returns 1 when the graph route is not available (the caller
+// then launches directly), R3D_OK / an error code otherwise.  Caller holds p->mu and has selected the device.
+static int forward_graph(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                         float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
+  const int mask = (prm ? 1 : 0) | (pos ? 2 : 0) | (trj ? 4 : 0) | (sum ? 8 : 0);
+  int rc = ensure_capacity(p, batch);           // may rebind the workspace and drop every captured graph
+  if (rc) return rc;
+  r3d_plan::GraphEntry* g = nullptr;
+  for (auto& e : p->graphs)
+    if (e.batch == batch && e.is_uv == is_uv && e.mask == mask && e.src_stride == src_stride && e.prm_stride == prm_stride) g = &e;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  // windows may overlap (video: batch stride of one frame) and the parameter row may be shared (stride 0)
+  const int64_t win_len = is_uv ? (int64_t)p->T * p->J * 2 : (int64_t)p->T * p->JC, prm_len = is_uv ? 6 : p->ext;
+  const size_t in_b = (size_t)((batch - 1) * src_stride + win_len) * 4, prm_b = (size_t)((batch - 1) * prm_stride + prm_len) * 4;
+  const size_t out_b = (size_t)batch * p->J * 3 * 4, trj_b = (size_t)batch * 3 * 4;
+  if (g == nullptr) {
+    if (p->graphs.size() >= 16) clear_graphs(p);
+    r3d_plan::GraphEntry e;
+    e.batch = batch; e.is_uv = is_uv; e.mask = mask; e.src_stride = src_stride; e.prm_stride = prm_stride;
+    e.off_prm = al(in_b); e.off_pos = e.off_prm + al(prm_b); e.off_sum = e.off_pos + al(out_b); e.off_trj = e.off_sum + al(out_b);
+    CUDA_TRY(cudaMalloc(&e.buf, e.off_trj + al(trj_b)));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(p->s_comp, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      rc = run_chunk(p, reinterpret_cast<float*>(e.buf), src_stride, is_uv, prm ? reinterpret_cast<float*>(e.buf + e.off_prm) : nullptr,
+                     prm_stride, pos ? reinterpret_cast<float*>(e.buf + e.off_pos) : nullptr,
+                     trj ? reinterpret_cast<float*>(e.buf + e.off_trj) : nullptr, sum ? reinterpret_cast<float*>(e.buf + e.off_sum) : nullptr,
+                     batch, p->s_comp);
+      ce = cudaStreamEndCapture(p->s_comp, &graph);          // always ends the capture, also after a failed launch
+      if (rc == R3D_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&e.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (rc != R3D_OK || ce != cudaSuccess || e.exec == nullptr) {   // capture unsupported here: launch directly from now on
+      cudaGetLastError();
+      cudaFree(e.buf);
+      p->graph_max_batch = 0;
+      return 1;
+    }
+    p->graphs.push_back(e);
+    g = &p->graphs.back();
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->buf, src, in_b, cudaMemcpyDeviceToDevice, s));
+  if (prm) CUDA_TRY(cudaMemcpyAsync(g->buf + g->off_prm, prm, prm_b, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGraphLaunch(g->exec, s));
+  ++p->graph_launches;
+  if (pos) CUDA_TRY(cudaMemcpyAsync(pos, g->buf + g->off_pos, out_b, cudaMemcpyDeviceToDevice, s));
+  if (sum) CUDA_TRY(cudaMemcpyAsync(sum, g->buf + g->off_sum, out_b, cudaMemcpyDeviceToDevice, s));
+  if (trj) CUDA_TRY(cudaMemcpyAsync(trj, g->buf + g->off_trj, trj_b, cudaMemcpyDeviceToDevice, s));
+  return R3D_OK;
+}
+
 static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
                        float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta = false) {
   int rc = check_forward(p, src, pos, trj, sum, batch);
@@ -1103,6 +1178,13 @@ static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  if (!tta && !p->profiling && batch <= p->graph_max_batch) {
+    rc = forward_graph(p, src, src_stride, is_uv, prm, prm_stride, pos, trj, sum, batch, s);
+    if (rc != 1) {
+      if (dev != p->device) cudaSetDevice(dev);
+      return rc;
+    }
+  }
   const int max_in = tta ? kMaxChunk / 2 : kMaxChunk;     // the mirrored copies double the rows in flight
   rc = ensure_capacity(p, std::min(batch, max_in) * (tta ? 2 : 1));
   for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += max_in) {

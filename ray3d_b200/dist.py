@@ -56,6 +56,48 @@ def gather_outputs(local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
     return torch.cat([recv[r, : sizes[r]] for r in range(world)], dim=0)
 
 
+class OverlappedGather:
+    """Streaming form of ``gather_outputs`` for a loop of steps: the all-gather of step i runs on the backend's own
+    communication stream while step i+1 is being computed.  ``depth`` send/receive buffer pairs rotate; ``submit``
+    returns a ticket, ``result(ticket)`` makes the current stream (NCCL) or the host (gloo) wait for that collective
+    and returns the full (batch, J+1, 3) tensor -- valid until ``depth`` further submissions.  All shards must have the
+    same size (world divides batch); use ``gather_outputs`` for ragged batches."""
+
+    def __init__(self, local_rows: int, joints: int, device, depth: int = 2, group=None, dtype=torch.float32):
+        self.group, self.depth = group, depth
+        world = dist.get_world_size(group)
+        self.send = [torch.empty((local_rows, joints + 1, 3), dtype=dtype, device=device) for _ in range(depth)]
+        self.recv = [torch.empty((world * local_rows, joints + 1, 3), dtype=dtype, device=device) for _ in range(depth)]
+        self.work = [None] * depth
+        self.seq = 0
+
+    def submit(self, both: torch.Tensor, trj: torch.Tensor) -> int:
+        k = self.seq % self.depth
+        if self.work[k] is not None:          # the collective that last used this buffer pair
+            self.work[k].wait()
+        J = self.send[k].shape[1] - 1
+        self.send[k][:, :J].copy_(both.reshape(-1, J, 3))
+        self.send[k][:, J:].copy_(trj.reshape(-1, 1, 3))
+        self.work[k] = dist.all_gather_into_tensor(self.recv[k], self.send[k], group=self.group, async_op=True)
+        self.seq += 1
+        return self.seq - 1
+
+    def result(self, ticket: int) -> torch.Tensor:
+        if not (self.seq - self.depth <= ticket < self.seq):
+            raise ValueError(f"ticket {ticket} is not in flight (next {self.seq}, depth {self.depth})")
+        k = ticket % self.depth
+        if self.work[k] is not None:
+            self.work[k].wait()
+            self.work[k] = None
+        return self.recv[k]
+
+    def drain(self) -> None:
+        for k in range(self.depth):
+            if self.work[k] is not None:
+                self.work[k].wait()
+                self.work[k] = None
+
+
 def lift_sharded(lift_fn: Callable[[torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]], uv_local: torch.Tensor,
                  cam_local: torch.Tensor, batch: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Lift this rank's shard with `lift_fn(uv, cam) -> (pos+trj, trj)` and all-gather the results.

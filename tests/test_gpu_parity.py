@@ -100,6 +100,32 @@ def test_streaming_submit_wait_matches_blocking_call(golden_meta):
         lf.submit_uv_host(torch.from_numpy(g["uv"]), torch.from_numpy(g["cam"]).pin_memory(), out)   # pageable input
 
 
+@pytest.mark.parametrize("name", ["h36m_s1_t27", "h36m_s3_t9"])
+def test_small_batches_replay_a_cuda_graph(golden_meta, name, monkeypatch):
+    """Batches <= 64 go through a captured CUDA graph (one launch): bit-identical to the direct launch sequence, for the
+    uv, ray and sliding-window entry points, across repeated calls and changing batch sizes."""
+    spec, lf, sp, st = lifter_for(golden_meta, name, "bf16x3")
+    monkeypatch.setenv("R3D_GRAPH_MAX_BATCH", "0")
+    direct = Lifter(spec, sp, st, precision="bf16x3")
+    monkeypatch.delenv("R3D_GRAPH_MAX_BATCH")
+    g0 = lf.plan.graph_launches
+    for rep in range(2):
+        for B in (1, 3, 64, 65, 2):
+            uv, cam = synth.make_inputs(spec, B, seed=50 + B + rep)
+            uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
+            a, b = lf.forward_uv(uvc, camc), direct.forward_uv(uvc, camc)
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+            x = torch.randn(B, spec.receptive_field, spec.num_joints, 3, device="cuda")
+            prm = torch.rand(B, 2, device="cuda")
+            a, b = lf.forward_rays(x, prm), direct.forward_rays(x, prm)
+            assert all(torch.equal(p, q) for p, q in zip(a, b))
+    seq = torch.randn(20 + spec.receptive_field - 1, spec.num_joints, 3, device="cuda")
+    prm = torch.tensor([1.5, -0.3], device="cuda")
+    a, b = lf.forward_video(seq, prm), direct.forward_video(seq, prm)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+    assert lf.plan.graph_launches - g0 == 2 * 2 * 4 + 1 and direct.plan.graph_launches == 0
+
+
 def test_modules_drop_in_forward(golden_meta, monkeypatch):
     monkeypatch.setenv("RAY3D_B200_PRECISION", "fp32")
     name = "h36m_s3_t9"

@@ -101,7 +101,24 @@ def _rank_main(rank, world, port, batch, out_q):
         lo, hi = rdist.shard_bounds(batch, rank, world)
         both, trj = rdist.lift_sharded(fake_lift, uv[lo:hi], cam[lo:hi], batch)
         ref_both, ref_trj = fake_lift(uv, cam)
-        out_q.put((rank, bool(torch.equal(both, ref_both) and torch.equal(trj, ref_trj)), tuple(both.shape)))
+        ok = bool(torch.equal(both, ref_both) and torch.equal(trj, ref_trj))
+        if batch % world == 0:     # streaming gather: several collectives in flight, results in submission order
+            og = rdist.OverlappedGather(hi - lo, J, "cpu", depth=2)
+            tickets = []
+            for step in range(5):
+                b, t = fake_lift(uv[lo:hi] + step, cam[lo:hi])
+                tickets.append(og.submit(b, t))
+                if step >= 1:
+                    got_b, got_t = rdist.unpack_outputs(og.result(tickets[step - 1]))
+                    want_b, want_t = fake_lift(uv + (step - 1), cam)
+                    ok = ok and bool(torch.equal(got_b, want_b) and torch.equal(got_t, want_t))
+            og.drain()
+            try:
+                og.result(0)
+                ok = False
+            except ValueError:
+                pass
+        out_q.put((rank, ok, tuple(both.shape)))
     finally:
         dist.destroy_process_group()
 
