@@ -219,6 +219,11 @@ R3D_API int r3d_eval_metrics(const float* pred_dev, const float* target_dev, int
 R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
                       double* rel_err, double* ms_tc, double* ms_ffma);
 
+/* Diagnostics: out == NULL arms a per-tile SM-clock trace for the tensor-core GEMM launch `arm_after_launches` launches
+ * from now; out != NULL synchronises the device and copies the last trace ([3 roles: TMA producer, MMA thread, first
+ * epilogue warp][64 tiles][8 events] clock64 stamps of CTA 0).  Used by scripts/tile_trace.py only. */
+R3D_API int r3d_debug_tc_trace(int32_t arm_after_launches, int64_t* out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

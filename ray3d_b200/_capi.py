@@ -68,6 +68,7 @@ EXPORTS = {
     "r3d_normalize_screen_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "r3d_eval_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_selftest_gemm": (C.c_int, [C.c_int32] * 6 + [C.POINTER(C.c_double)] * 3),
+    "r3d_debug_tc_trace": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.c_int32]),
 }
 
 

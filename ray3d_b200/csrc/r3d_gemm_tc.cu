@@ -110,6 +110,9 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tmap_prefetch(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -254,7 +257,7 @@ struct TileCoord {
 // `cl` consecutive m tiles (one per CTA of the pair).
 __device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int m_groups, int block_n, int cl, int rank, int total) {
   if (op.reverse) unit = total - 1 - unit;
-  const int per_m = total / m_groups;            // sum over problems of their n tiles
+  const int per_m = total / m_groups;            // sum over problems of their n tiles (loop invariant: hoisted by the compiler)
   const int mg = unit / per_m;
   int rem = unit - mg * per_m;
   int p = 0, n_tiles = 1;
@@ -324,6 +327,13 @@ __device__ __forceinline__ void residual_consume(uint4* stg, const ResidualRegs&
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 
+// Diagnostics (R3D_TC_DEBUG bit 32 / r3d_debug_tc_trace): CTA 0 records SM clock stamps per tile for its producer (role 0),
+// MMA thread (role 1) and first epilogue warp (role 2): [role][tile index < 64][event < 8].
+constexpr int kTraceTiles = 64, kTraceEvents = 8;
+__device__ long long g_tc_trace[3 * kTraceTiles * kTraceEvents];
+#define R3D_TRACE(role, ti, ev) \
+  do { if (trace && (ti) < kTraceTiles) g_tc_trace[((role) * kTraceTiles + (ti)) * kTraceEvents + (ev)] = clock64(); } while (0)
+
 // FUSED: every tile runs two GEMMs back to back -- acc1 = A*W^T (K = w*C), Y = lrelu(acc1 + bias) re-split to bf16
 // hi/lo IN PLACE in tensor memory (each 32-column fp32 chunk becomes 16 hi + 16 lo packed columns), acc2 = Y*W2^T with
 // the A operand read from tensor memory (TS-mode tcgen05.mma), then the usual epilogue on acc2.  TMEM: columns
@@ -360,6 +370,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* yready_bar = bars + 2 * STAGES + 4; // [2]  FUSED: channels [0,128) / [128,256) of the intermediate are in tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
+  // epilogue warp <-> store thread hand-off, per epilogue warp and staging set: "staged tile ready" / "staging set free"
+  static_assert(sizeof(GemmOpDev) % 8 == 0 && 256 + sizeof(GemmOpDev) + 8 * 8 <= 256 + kOpSmemBytes, "no room for the store barriers");
+  uint64_t* sready_bar = reinterpret_cast<uint64_t*>(aux + 256 + sizeof(GemmOpDev));   // [column half][staging set], 4 arrivals
+  uint64_t* sfree_bar = sready_bar + 4;                                                 // [column half][staging set]
   uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][sets][2 planes][32 rows x 64 B]
   float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes + 8 * 4096 * (CL == 2 ? 2 : 1));   // CL == 2: [EPI_WARPS][128]
 
@@ -370,6 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA stages
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   const bool leader = crank == 0;
+  const bool trace = (dbg & 32) && blockIdx.x == 0 && lane == 0;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its own setup early
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
@@ -386,6 +401,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EPI_WARPS * CL);                // CL == 2: the peer's epilogue warps arrive remotely
       mbar_init(&yready_bar[a], EPI_WARPS * CL);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&sready_bar[i], 4);                             // the four epilogue warps (TMEM lane quarters) of a column half
+      mbar_init(&sfree_bar[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -437,11 +456,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           }
         }
       };
-      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+      int ti = 0;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
+        const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
+        R3D_TRACE(0, ti, 0);
+        if ((dbg & 256) && tile + unit_step < total_tiles) {     // experiment: next tile's load descriptors -> descriptor cache
+          const TileCoord tn = decode_tile(op, tile + unit_step, m_tiles, BLOCK_N, CL, crank, total_tiles);
+          const CUtensorMap* nm = tmaps + tn.p * kTmapsPerProb;
+          tmap_prefetch(nm + 0); tmap_prefetch(nm + 1);
+          tmap_prefetch(nm + (CL == 1 ? 2 : 4)); tmap_prefetch(nm + (CL == 1 ? 3 : 5));
+        }
         for (int kb = 0; kb < nkb; ++kb) {
+          if (((kmask >> (kb * (TBK / UMMA_K))) & 0xFull) == 0) continue;      // K block without weights: never staged
           if (dbg & 8) {   // measured on B200: the extra L2 prefetch stream costs more DRAM traffic than it hides -> off
             while (pf_ahead < PF_DIST + 1) { prefetch_step(); ++pf_ahead; }
             --pf_ahead;
@@ -465,6 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        R3D_TRACE(0, ti, 1);
         if (FUSED) {   // second GEMM: only W2 K blocks flow through the ring (its A operand is in tensor memory)
           const CUtensorMap* tw = tm + kTmapW2;
           const int nkb2 = op.prob[tc.p].K2 / TBK;
@@ -493,50 +523,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       constexpr uint32_t idesc = make_idesc(BLOCK_N, TBM * CL);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+      int ti = 0;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
-        const int k_steps = op.prob[tc.p].k_steps > 0 ? op.prob[tc.p].k_steps : nkb * (TBK / UMMA_K);
+        const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
+        R3D_TRACE(1, ti, 0);
+        int last_kb = nkb - 1;                                  // last K block that is staged at all (the mask is never empty)
+        while (last_kb > 0 && ((kmask >> (last_kb * (TBK / UMMA_K))) & 0xFull) == 0) --last_kb;
+        uint32_t accumulate = 0;                                // first MMA of the tile overwrites the accumulator
         if (!FUSED) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
           tc_fence_after();
         }   // FUSED: acc1 is free again once the previous tile's second GEMM was issued (same thread, in order)
         const uint32_t d_tmem = tmem_base + (FUSED ? 0 : acc * BLOCK_N);
-        for (int kb = 0; kb < nkb; ++kb) {
+        R3D_TRACE(1, ti, 1);
+        for (int kb = 0; kb <= last_kb; ++kb) {
+          const uint32_t steps = (uint32_t)(kmask >> (kb * (TBK / UMMA_K))) & 0xFu;   // K steps of this block with weights
+          if (steps == 0) continue;                            // the producer skipped it too
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0) R3D_TRACE(1, ti, 2);
           const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + NSPLIT * A_BYTES);
           const uint64_t a_lo = make_smem_desc(st + A_BYTES), w_lo = make_smem_desc(st + 2 * A_BYTES + W_BYTES);
-          const int steps_here = k_steps - kb * (TBK / UMMA_K);           // < 4 only in a zero-padded last block
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
-            if (k >= steps_here) break;
+            if (!((steps >> k) & 1u)) continue;
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // 32 bytes per K step inside the swizzle atom
             if (CL == 1) {
-              umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+              umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, accumulate);
               if (NSPLIT == 2) {
                 umma_bf16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
                 umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
               }
             } else {
-              umma_bf16_2sm(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+              umma_bf16_2sm(d_tmem, a_hi + koff, w_hi + koff, idesc, accumulate);
               if (NSPLIT == 2) {
                 umma_bf16_2sm(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
                 umma_bf16_2sm(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
               }
             }
+            accumulate = 1;
           }
           const int tf = FUSED ? 0 : acc;
           if (CL == 1) {
             umma_commit(&empty_bar[stage]);                    // smem stage free once these MMAs retire
-            if (kb == nkb - 1) umma_commit(&tfull_bar[tf]);    // accumulator complete
+            if (kb == last_kb) umma_commit(&tfull_bar[tf]);    // accumulator complete
           } else {                                             // ... signalled in both CTAs of the pair
             umma_commit_2sm(&empty_bar[stage], MC_MASK);
-            if (kb == nkb - 1) umma_commit_2sm(&tfull_bar[tf], MC_MASK);
+            if (kb == last_kb) umma_commit_2sm(&tfull_bar[tf], MC_MASK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        R3D_TRACE(1, ti, 3);
         if (FUSED) {
           // second GEMM: Y (bf16 hi/lo, written in place over acc1 by the epilogue warps) x W2^T -> acc2
           // The epilogue warps convert Y in two halves; the K blocks over channels [0,128) start while the second
@@ -584,9 +624,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          R3D_TRACE(1, ti, 4);
           acc_phase ^= 1;
         } else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+    }
+    __syncwarp();
+  } else if (warp < EPI_WARP0) {
+    // =============================== store threads ===============================
+    // Lane 0 of warp 2 / warp 3 issues the TMA tensor stores for the epilogue warps of column half 0 / 1.  Issuing a
+    // tensor store costs its thread ~300 cycles (more under write back-pressure); inside the epilogue warps that was
+    // ~600 cycles per 32-column chunk on their critical path.  The four warps of a column half (one TMEM lane quarter
+    // each) stage their 32-row slices into ONE 128-row x 32-column tile per plane, so a single store per destination
+    // plane moves all of it (4x fewer store instructions), and the epilogue warps convert the next chunk meanwhile.
+    // Protocol per (column half, staging set): the four warps fill their slices, fence, arrive on sready (count 4);
+    // this thread issues the stores, commits, and arrives on sfree once the store engine has read the set (with two
+    // sets: when the following round has been issued).
+    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;
+    const int half = warp - 2;
+    if (CH == 32 && lane == 0 && half >= 0 && half < COL_SPLIT) {
+      const int c_begin = half * CHUNKS_PER_WARP;
+      uint32_t round = 0;                                       // staged chunks so far (the client warps count the same)
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+        const GemmProb& pr = op.prob[tc.p];
+        const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
+        bool any_bf = false;
+        for (int t = 0; t < pr.ndst; ++t) any_bf |= pr.dst[t].f32 == 0;
+        if (!any_bf || (dbg & 4)) continue;
+        for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+          const int n = tc.n0 + (c_begin + cc) * CH;
+          if (n >= pr.N) continue;
+          const int b = EPI_BUFS == 2 ? (int)(round & 1) : 0;
+          const uint32_t uses = EPI_BUFS == 2 ? round >> 1 : round;
+          mbar_wait(&sready_bar[half * 2 + b], uses & 1);
+          if (!(dbg & 1)) {
+            const uint4* tile_hi = stage_s + (half * EPI_BUFS + b) * 1024;
+            const uint4* tile_lo = tile_hi + 512;
+            const int srow = (dbg & 16) ? 0 : tc.m0;                       // experiment: keep every store in the same L2-resident rows
+            for (int t = 0; t < pr.ndst; ++t) {
+              const Dst& d = pr.dst[t];
+              if (d.f32) continue;
+              tma_store_2d(dmaps + 2 * t, tile_hi, d.col + n, srow);
+              if (d.m.p1 != nullptr) tma_store_2d(dmaps + 2 * t + 1, tile_lo, d.col + n, srow);
+            }
+          }
+          bulk_commit();
+          if (EPI_BUFS == 2) {              // the previous round's stores have read their set: it is free again
+            bulk_wait_read1();
+            if (round > 0) mbar_arrive(&sfree_bar[half * 2 + (b ^ 1)]);
+          } else {
+            bulk_wait_read0();
+            mbar_arrive(&sfree_bar[half * 2]);
+          }
+          ++round;
+        }
+      }
+      bulk_wait0();                          // every TMA store issued by this thread has landed
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
@@ -596,41 +690,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     const int half = ew >> 2;                                 // which half of the columns
     const bool active = half < COL_SPLIT;
     constexpr int EPI_BUFS = CL == 2 ? 2 : 1;                 // staging tile sets per warp (hi + lo each)
-    uint4* const stage_base = stage_s + ew * 256 * EPI_BUFS;  // each tile: 32 rows x 64 B, 64B-swizzled
-    int sbuf = 0;
+    // staging: [column half][set][plane] tiles of 128 rows x 64 B (64B-swizzled); this warp owns rows [32 q, 32 q + 32)
+    uint4* const stage_base = stage_s + half * EPI_BUFS * 1024 + q * 128;
+    uint32_t sround = 0;                                      // chunks this warp has handed to its store thread
     int acc = 0;
     uint32_t acc_phase = 0;
     const float slope = op.slope;
-    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-      const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+    const bool etrace = trace && ew == 0;
+    int ti = 0;
+    constexpr bool BIAS_SMEM = CL == 2;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
+    constexpr int PB = (CHUNKS_PER_WARP * CH + 31) / 32;          // bias words per lane for this warp's columns
+    const int c_begin = half * CHUNKS_PER_WARP;
+    auto chunk_of = [&](int cc) { return (cc >> 1) * 4 + half * 2 + (cc & 1); };     // FUSED: first-GEMM chunk order
+    // The epilogue warps are the critical path of the short-K launches: the coordinates and the folded bias of the NEXT
+    // tile are fetched while the current tile is processed (registers), so no tile starts with an L2 round trip.
+    float pb[PB], pa[4];
+    auto prefetch_bias = [&](const TileCoord& t) {
+      const GemmProb& g = op.prob[t.p];
+      const float* bp = (FUSED ? g.bias2 : g.bias) + t.n0 + c_begin * CH;
+#pragma unroll
+      for (int i = 0; i < PB; ++i) pb[i] = (lane + 32 * i < CHUNKS_PER_WARP * CH) ? __ldg(bp + lane + 32 * i) : 0.f;
+      if (FUSED) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pa[i] = __ldg(g.bias + chunk_of(i) * 32 + lane);
+      }
+    };
+    TileCoord tc = decode_tile(op, unit0 < total_tiles ? unit0 : 0, m_tiles, BLOCK_N, CL, crank, total_tiles);
+    if (BIAS_SMEM && active && unit0 < total_tiles) prefetch_bias(tc);
+    uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
+    for (int p = 0; p < op.nprob; ++p) {
+      const GemmProb& g = op.prob[p];
+      uint32_t f = (g.res.p0 != nullptr && !(dbg & 2)) ? 8u : 0u;
+      for (int t = 0; t < g.ndst; ++t) {
+        f |= g.dst[t].f32 != 0 ? 1u : 2u;
+        if (g.dst[t].f32 == 0 && g.dst[t].m.p1 != nullptr) f |= 4u;
+      }
+      pflags |= f << (4 * p);
+    }
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
       const GemmProb& pr = op.prob[tc.p];
+      if (etrace) R3D_TRACE(2, ti, 0);
+      const bool has_next = tile + unit_step < total_tiles;
+      TileCoord tn = tc;
+      if (has_next) tn = decode_tile(op, tile + unit_step, m_tiles, BLOCK_N, CL, crank, total_tiles);
+      const bool ttrace = etrace && (dbg & 128);                 // stamps of the per-tile preamble
+      if (ttrace) R3D_TRACE(2, ti, 1);
+      if ((dbg & 256) && has_next && lane == 0) {                // experiment: next tile's store descriptors -> descriptor cache
+        const CUtensorMap* nm = tmaps + tn.p * kTmapsPerProb + 6;
+        for (int t = 0; t < op.prob[tn.p].ndst; ++t) { tmap_prefetch(nm + 2 * t); tmap_prefetch(nm + 2 * t + 1); }
+      }
       const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
       const int m_base = tc.m0 + q * 32;
       const int row = m_base + lane;
       const bool row_ok = row < M;
-      const int c_begin = half * CHUNKS_PER_WARP;
-      bool any_f32 = false, any_bf = false, any_lo = false;
-      for (int t = 0; t < pr.ndst; ++t) {
-        any_f32 |= pr.dst[t].f32 != 0;
-        any_bf |= pr.dst[t].f32 == 0;
-        any_lo |= pr.dst[t].f32 == 0 && pr.dst[t].m.p1 != nullptr;
-      }
-      const bool has_res = pr.res.p0 != nullptr && !(dbg & 2);
+      const uint32_t pf = pflags >> (4 * tc.p);
+      const bool any_f32 = pf & 1u, any_bf = pf & 2u, any_lo = pf & 4u, has_res = pf & 8u;
+      if (ttrace) R3D_TRACE(2, ti, 2);
       const __nv_bfloat16* res_hi = reinterpret_cast<const __nv_bfloat16*>(pr.res.p0);
       const __nv_bfloat16* res_lo = reinterpret_cast<const __nv_bfloat16*>(pr.res.p1);
       ResidualRegs rr;
       if (active && has_res && CH == 32)      // first chunk's residual: in flight while the main loop still runs
         residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + c_begin * CH, lane, m_base, M);
-      constexpr bool BIAS_SMEM = CL == 2;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
       float* my_bias = bias_s + ew * 128;
       if (FUSED) {
         // ---- epilogue of the first GEMM: acc1 -> Y = lrelu(acc1 + bias) as bf16 hi/lo, in place in tensor memory
         // This warp converts chunks {2*half, 2*half+1} of the first 128 channels, signals, then the same two chunks of
         // the second 128 channels: the MMA thread starts the second GEMM on the first half meanwhile.
-        auto chunk_of = [&](int cc) { return (cc >> 1) * 4 + half * 2 + (cc & 1); };
         if (BIAS_SMEM) {
           __syncwarp();
-          for (int j = lane; j < 4 * 32; j += 32) my_bias[j] = __ldg(pr.bias + chunk_of(j >> 5) * 32 + (j & 31));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) my_bias[lane + 32 * i] = pa[i];
           __syncwarp();
         }
         mbar_wait(&tfull_bar[0], acc_phase);
@@ -678,13 +807,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       const float* const bias_ptr = FUSED ? pr.bias2 : pr.bias;
       const int acc_col = FUSED ? BLOCK_N : acc * BLOCK_N;
       const int fb = FUSED ? 1 : acc;                          // accumulator-full / -empty barrier of this tile
-      if (BIAS_SMEM && active) {              // this warp's slice of the folded bias -> smem while the main loop still runs
+      if (BIAS_SMEM && active) {              // this warp's slice of the folded bias (prefetched during the previous tile)
         __syncwarp();
-        for (int j = lane; j < CHUNKS_PER_WARP * CH; j += 32) my_bias[j] = __ldg(bias_ptr + tc.n0 + c_begin * CH + j);
+#pragma unroll
+        for (int i = 0; i < PB; ++i)
+          if (lane + 32 * i < CHUNKS_PER_WARP * CH) my_bias[lane + 32 * i] = pb[i];
         __syncwarp();
+        if (ttrace) R3D_TRACE(2, ti, 3);
+        if (has_next) prefetch_bias(tn);      // in flight while this tile's chunks are processed
       }
+      if (ttrace) R3D_TRACE(2, ti, 4);
+      if (etrace && !ttrace) R3D_TRACE(2, ti, 1);
       mbar_wait(&tfull_bar[fb], acc_phase);
       tc_fence_after();
+      if (ttrace) R3D_TRACE(2, ti, 5);
+      if (etrace && !ttrace) R3D_TRACE(2, ti, 2);
       if (active) {
         uint32_t r[32];
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c_begin * CH);
@@ -708,6 +845,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             }
           }
           tmem_ld_wait();
+          const bool strace = etrace && (dbg & 64) && !(dbg & 128) && cc == 1;     // sub-step stamps of one steady-state chunk
+          if (strace) R3D_TRACE(2, ti, 3);
           float v[32];
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
@@ -720,12 +859,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
-            uint4* const stage_hi = stage_base + sbuf * 256;
-            uint4* const stage_lo = stage_hi + 128;
-            if (CH == 32) {
-              if (lane == 0) { if (EPI_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0(); }
-              __syncwarp();
-              sbuf ^= (EPI_BUFS - 1);
+            const int sbuf = EPI_BUFS == 2 ? (int)(sround & 1) : 0;
+            uint4* const stage_hi = stage_base + sbuf * 1024;
+            uint4* const stage_lo = stage_hi + 512;
+            if (CH == 32) {    // the store thread has released this staging set (its previous stores have read it)
+              mbar_wait(&sfree_bar[half * 2 + sbuf], (((EPI_BUFS == 2 ? sround >> 1 : sround) & 1) ^ 1));
+              if (strace) R3D_TRACE(2, ti, 4);
             }
             if (has_res) {
               if (CH == 32) {
@@ -766,18 +905,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                 // rows in [M, capacity) receive don't-care values nobody reads)
                 stage_write(stage_hi, hi, lane);
                 if (any_lo) stage_write(stage_lo, lo, lane);
+                if (strace) R3D_TRACE(2, ti, 5);
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0 && !(dbg & 1)) {
-                  for (int t = 0; t < pr.ndst; ++t) {
-                    const Dst& d = pr.dst[t];
-                    if (d.f32) continue;
-                    const int srow = (dbg & 16) ? (m_base & 127) : m_base;   // experiment: keep every store in the same L2-resident rows
-                    tma_store_2d(dmaps + 2 * t, stage_hi, d.col + n, srow);
-                    if (d.m.p1 != nullptr) tma_store_2d(dmaps + 2 * t + 1, stage_lo, d.col + n, srow);
-                  }
-                  bulk_commit();
-                }
+                if (strace) R3D_TRACE(2, ti, 6);
+                if (lane == 0) mbar_arrive(&sready_bar[half * 2 + sbuf]);    // the store thread takes it from here
+                ++sround;
               } else if (row_ok) {
                 for (int t = 0; t < pr.ndst; ++t) {
                   const Dst& d = pr.dst[t];
@@ -795,18 +928,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
               }
             }
           }
+          if (etrace && !(dbg & (64 | 128)) && cc < 4) R3D_TRACE(2, ti, 3 + cc);
+          if (ttrace && cc == 0) R3D_TRACE(2, ti, 6);
+          if (strace) R3D_TRACE(2, ti, 7);
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (etrace && !(dbg & 64)) R3D_TRACE(2, ti, 7);       // (dbg & 128: stamp 7 = tile done as well)
       if (lane == 0) {
         if (CL == 1) mbar_arrive(&tempty_bar[fb]);
         else mbar_arrive_cluster(&tempty_bar[fb], 0, (op.flags & 2) != 0);         // the MMA thread lives in the leader CTA
       }
       if (FUSED) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      tc = tn;
     }
-    if (lane == 0) bulk_wait0();             // every TMA store issued by this thread has landed
     __syncwarp();
   }
 
@@ -880,14 +1017,14 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
     rc = encode_2d(out + p * kTmapsPerProb + 3, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
                    (uint64_t)g.K, (uint32_t)bn);
     if (rc) return rc;
-    // epilogue store maps: 32-column x 32-row boxes of every bf16 destination plane, 64B swizzle (the staging layout)
+    // epilogue store maps: 32-column x 128-row boxes of every bf16 destination plane, 64B swizzle (the staging layout)
     for (int t = 0; t < g.ndst; ++t) {
       CUtensorMap* dm = out + p * kTmapsPerProb + 6 + 2 * t;
       if (g.dst[t].f32 || bn < 32) { memset(dm, 0, 2 * sizeof(*dm)); continue; }
-      rc = encode_2d(dm, g.dst[t].m.p0, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows, (uint64_t)g.dst[t].m.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      rc = encode_2d(dm, g.dst[t].m.p0, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows, (uint64_t)g.dst[t].m.ld, TBM, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
       rc = encode_2d(dm + 1, precision == R3D_PREC_BF16X3 ? g.dst[t].m.p1 : nullptr, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows,
-                     (uint64_t)g.dst[t].m.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+                     (uint64_t)g.dst[t].m.ld, TBM, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
     if (h.fused2) {   // second weight matrix of a fused conv pair: full-tile and half-tile (2-SM) boxes
@@ -936,6 +1073,16 @@ static int g_num_sms = 0;
 static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 enable the L2 prefetch cursor, 16 fold all stores onto 128 rows (timing experiments only)
 static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
+static int g_trace_arm = -1;     // >= 0: the launch that many GEMM launches from now records the per-tile clock trace
+
+void tc_trace_arm(int launches_from_now) { g_trace_arm = launches_from_now; }
+cudaError_t tc_trace_read(long long* out, int cap) {
+  long long h[3 * kTraceTiles * kTraceEvents];
+  cudaError_t e = cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h));
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < cap && i < 3 * kTraceTiles * kTraceEvents; ++i) out[i] = h[i];
+  return cudaSuccess;
+}
 
 cudaError_t tc_configure() {
   cudaError_t e;
@@ -962,6 +1109,8 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   const int m_groups = (m_tiles + cl - 1) / cl;
   int units = 0;
   for (int p = 0; p < h.nprob; ++p) units += m_groups * (h.prob[p].n_pad / BN);
+  int dbg = g_dbg;               // this launch's debug mask
+  if (g_trace_arm >= 0 && g_trace_arm-- == 0) dbg |= 32;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = use_cl ? tc_smem_bytes<BN, NS, CL2>() : tc_smem_bytes<BN, NS, 1>();
@@ -977,8 +1126,8 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
     cfg.gridDim = dim3(units < g_num_sms ? units : g_num_sms);
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 1, true>, d_op, d_tmaps, M, units, g_dbg);
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, 1, false>, d_op, d_tmaps, M, units, g_dbg);
+    if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 1, true>, d_op, d_tmaps, M, units, dbg);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, 1, false>, d_op, d_tmaps, M, units, dbg);
   }
   const int max_clusters = g_num_sms / 2;
   const int clusters = units < max_clusters ? units : max_clusters;
@@ -990,8 +1139,8 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   ++na;
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, g_dbg);
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2, false>, d_op, d_tmaps, M, units, g_dbg);
+  if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, dbg);
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2, false>, d_op, d_tmaps, M, units, dbg);
 }
 
 cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h, const void* d_tmaps, int M, int precision, cudaStream_t s) {

@@ -49,7 +49,10 @@ struct GemmProb {
   const void* w2_1;      // bf16 lo plane or null
   const float* bias2;
   int32_t K2;
-  int32_t k_steps;       // 16-wide K steps of the first GEMM that hold non-zero weights (ceil(real K / 16)); 0 => K / 16
+  int32_t _pad2;
+  uint64_t kmask;        // bit s set: the 16-wide K step s of the first GEMM holds non-zero weights and is multiplied;
+                         // clear steps (zero padding, joints outside the problem's group in the shared first-layer
+                         // operand) are neither loaded nor issued.  0 => every step (K > 1024 or elision disabled)
 };
 
 struct GemmOpDev {
@@ -80,7 +83,9 @@ struct EmbedDev {
 struct PrologueDev {
   int32_t T, J, Cin, JC, tc, w0, L0;
   int32_t k_pad;         // row pitch of a0
-  Mat a0;                // first-layer operand shared by all problems: [B*L0][k_pad] = [w0 frames | x[tc] | 0]
+  Mat a0;                // first-layer operand shared by all problems: [B*L0][k_pad], columns per a0_map
+  const int16_t* a0_map; // [k_pad] source of every operand column: s < w0*JC -> x[w0*t' + s / JC, s % JC];
+                         // s >= w0*JC -> x[tc, s - w0*JC]; -1 -> 0 (see A0Layout in r3d_plan.cpp)
   Mat inc;               // in_current, [B][roundup(J*Cin,64)]
   int32_t n_embed, ext_dim, emb_mid, emb_dim;
   EmbedDev embed[2];
@@ -118,6 +123,8 @@ cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h_op, const v
                            cudaStream_t s);
 int tc_build_tmaps(const GemmOpDev& h_op, int precision, int64_t cap_rows, void* h_tmaps_out /* kMaxProb*4 maps */);
 cudaError_t tc_configure();
+void tc_trace_arm(int launches_from_now);              // diagnostics: per-tile clock trace of one GEMM launch
+cudaError_t tc_trace_read(long long* out, int cap);     // 3 roles x 64 tiles x 8 events
 constexpr int kTmapsPerProb = 6 + 2 * kMaxDst + 4;   // A hi/lo, W hi/lo, W hi/lo (half tile), {hi, lo} store maps per destination, W2 hi/lo full + half
 constexpr int kTmapW2 = 6 + 2 * kMaxDst;
 constexpr int kTmapBytes = 128;

@@ -96,6 +96,7 @@ struct PackedLayer {
   size_t off_w0 = 0, off_w1 = 0, off_b = 0;   // offsets in the device weight slab
   bool plain = false;             // embedder matrices: no padding, fp32 only
   int alg_k = 0;                  // K of the reference's own op (flop accounting); 0 => k
+  uint64_t kmask = 0;             // 16-column K steps holding at least one non-zero weight (0: K > 1024, no elision)
 };
 
 struct MatReq {          // one activation matrix in the workspace slab
@@ -123,6 +124,15 @@ struct r3d_plan {
   bool embed = false, has_pos = false, has_trj = false;
   std::vector<int> widths, lens;
   int feat_pos = 0, feat_trj = 0;
+  // Column layout of the first-layer operand shared by all problems (build_a0_layout).  Slot 0 = the Torso joints
+  // (root first), slots 1..4 = [copy of the root joint | the limb's joints]; inside a slot the columns are frame-major
+  // [frame w0*t' | ... | frame w0*t'+w0-1 | frame tc] x joints x Cin; every slot starts on a 16-column K step.
+  std::vector<int> a0_src;        // [a0_kpad] column -> source index (see PrologueDev::a0_map), -1 = zero
+  std::vector<int> a0_home;       // [J] column of the joint's (tap 0, coordinate 0) entry
+  std::vector<int> a0_tap;        // [5] columns per frame inside slot g (tap stride)
+  int a0_slot_of[32] = {};        // joint -> slot
+  int a0_root[5] = {0, 0, 0, 0, 0};   // column of the root joint's (tap 0, coordinate 0) entry in slot g
+  int a0_k = 0, a0_kpad = 0;
 
   std::map<std::string, TensorEntry> tensors[2];     // expected entries per net (0 pos, 1 trj)
   std::map<std::string, PackedLayer> layers;         // key "<net>:<module path>"
@@ -237,6 +247,42 @@ static void expect_embed(r3d_plan* p, int net) {
   expect_bn(p, net, "embedder.b2", p->E);
 }
 
+// The folded expand_conv weights of a joint group (pack_expand_folded) are non-zero only in the columns of the group's
+// own joints and of the root joint.  Ordering the shared operand's columns group by group turns that sparsity into
+// whole 16-column K steps that the tensor-core GEMM neither loads nor multiplies (GemmProb::kmask): at J=17, Cin=3,
+// w0=3 a limb problem issues 3 of 16 K steps, the Torso 4, the trajectory net (all joints) 16.
+static void build_a0_layout(r3d_plan* p) {
+  const int Cin = p->Cin, JC = p->JC, w0 = p->widths[0];
+  p->a0_src.clear();
+  p->a0_home.assign(p->J, -1);
+  p->a0_tap.assign(5, 0);
+  // one slot: frame-major [tap 0: joints x Cin | tap 1 | ... | tap w0-1 | frame tc], so consecutive columns mostly
+  // read consecutive input words (the input stage gathers them from shared memory)
+  auto put_slot = [&](const std::vector<int>& js, int g) {
+    while (p->a0_src.size() % 16) p->a0_src.push_back(-1);            // every slot starts on a 16-column K step
+    const int first = (int)p->a0_src.size(), per_tap = (int)js.size() * Cin;
+    for (int tap = 0; tap <= w0; ++tap)
+      for (int j : js)
+        for (int c = 0; c < Cin; ++c) p->a0_src.push_back(tap * JC + j * Cin + c);   // tap == w0: frame tc
+    p->a0_tap[g] = per_tap;
+    return first;
+  };
+  for (int g = 0; g < 5; ++g) {
+    std::vector<int> js = p->groups.joints[g];
+    if (g != 0) js.insert(js.begin(), 0);                              // limb slots carry their own copy of the root joint
+    const int first = put_slot(js, g);
+    for (size_t i = 0; i < js.size(); ++i) {
+      if (g != 0 && i == 0) continue;
+      p->a0_home[js[i]] = first + (int)i * Cin;
+      p->a0_slot_of[js[i]] = g;
+    }
+    p->a0_root[g] = first;                                             // root (joint 0) is the first joint of every slot
+  }
+  p->a0_k = (int)p->a0_src.size();
+  p->a0_kpad = round_up(p->a0_k, kKAlign);
+  p->a0_src.resize(p->a0_kpad, -1);
+}
+
 extern "C" R3D_API int r3d_plan_create(const r3d_config* cfg, r3d_plan** out) {
   if (!cfg || !out) return fail(R3D_ERR_BAD_ARG, "r3d_plan_create: null argument");
   *out = nullptr;
@@ -272,6 +318,8 @@ extern "C" R3D_API int r3d_plan_create(const r3d_config* cfg, r3d_plan** out) {
   p->feat_pos = p->L * (cfg->stage == 1 ? 2 : 3) + p->E;     // rie.py:241-242
   p->feat_trj = p->L * 2 + p->E;                              // rie.py:491-492
   if ((size_t)p->T * p->JC * 4 > 200 * 1024) return fail(R3D_ERR_UNSUPPORTED, "receptive field %d too large for the input stage", p->T);
+  build_a0_layout(p.get());
+  if ((p->widths[0] + 1) * p->JC > 32767) return fail(R3D_ERR_UNSUPPORTED, "first filter width %d too large for the input stage", p->widths[0]);
 
   if (p->has_pos) {
     for (int g = 0; g < 5; ++g) {
@@ -379,18 +427,23 @@ struct Folder {
 //     = sum_{tap,s} Wf[o,tap,s] * x[s, w0*t'+tap]  +  sum_s Wc[o,s] * x[s, tc]
 //   Wf[o,tap,(j,c)] = [j in group] (Wx+Wd+Wt)[o,(jj,c),tap]  -  [j == root] sum_jj Wd[o,(jj,c),tap]
 //   Wc[o,(j,c)]     = -[j in group] sum_tap Wt[o,(jj,c),tap]
-// Every problem then reads the SAME compact operand row  [x[:, w0*t' .. w0*t'+w0-1] | x[:, tc]]  (K = (w0+1)*J*Cin
-// instead of w0*3*|group|*Cin per group: 4.75x fewer bytes at T=243), summed in float64 with the BatchNorm scale.
-static PackedLayer pack_expand_folded(r3d_plan* p, int net, const std::string& pre, const std::vector<int>& joints) {
+// Every problem then reads the SAME compact operand row  {x[:, w0*t' .. w0*t'+w0-1], x[:, tc]}  (K = (w0+1)*(J+4)*Cin
+// instead of w0*3*|group|*Cin per group: ~4x fewer bytes at T=243), summed in float64 with the BatchNorm scale.  The
+// columns are ordered by build_a0_layout so that a group's non-zero weights sit in a few 16-column K steps.
+static PackedLayer pack_expand_folded(r3d_plan* p, int net, const std::string& pre, const std::vector<int>& joints, int group) {
   Folder f{p, net};
-  const int C = p->C, Cin = p->Cin, JC = p->JC, w0 = p->widths[0], nj = (int)joints.size(), cg = 3 * nj * Cin;
+  const int C = p->C, Cin = p->Cin, w0 = p->widths[0], nj = (int)joints.size(), cg = 3 * nj * Cin;
   PackedLayer pl;
-  pl.n = C; pl.k = (w0 + 1) * JC; pl.n_pad = round_up(C, 16); pl.k_pad = round_up(pl.k, kKAlign);
+  pl.n = C; pl.k = p->a0_k; pl.n_pad = round_up(C, 16); pl.k_pad = p->a0_kpad;
   pl.alg_k = cg * w0;
   pl.w.assign((size_t)pl.n_pad * pl.k_pad, 0.f); pl.b.assign(pl.n_pad, 0.f);
   std::vector<double> sc, sh;
   f.bn(pre + ".expand_bn", C, sc, sh);
   const float* W = f.get(pre + ".expand_conv.weight");     // (C, cg, w0), channel = part*nj*Cin + jj*Cin + c
+  // operand columns (build_a0_layout): joint j, frame tap (tap == w0: frame tc), coordinate c
+  const int root = group >= 0 ? p->a0_root[group] : p->a0_home[0];
+  const int root_tap = p->a0_tap[group >= 0 ? group : 0];
+  auto col = [&](int j, int tap, int c) { return p->a0_home[j] + tap * p->a0_tap[p->a0_slot_of[j]] + c; };
   std::vector<double> row(pl.k_pad);
   for (int o = 0; o < C; ++o) {
     std::fill(row.begin(), row.end(), 0.0);
@@ -398,9 +451,9 @@ static PackedLayer pack_expand_folded(r3d_plan* p, int net, const std::string& p
     for (int jj = 0; jj < nj; ++jj)
       for (int c = 0; c < Cin; ++c)
         for (int tap = 0; tap < w0; ++tap) {
-          row[tap * JC + joints[jj] * Cin + c] += w(0, jj, c, tap) + w(1, jj, c, tap) + w(2, jj, c, tap);
-          row[tap * JC + c] -= w(1, jj, c, tap);                       // root joint 0, same coordinate (rie.py:301)
-          row[w0 * JC + joints[jj] * Cin + c] -= w(2, jj, c, tap);     // x[:, tc] term (rie.py:304)
+          row[col(joints[jj], tap, c)] += w(0, jj, c, tap) + w(1, jj, c, tap) + w(2, jj, c, tap);
+          row[root + tap * root_tap + c] -= w(1, jj, c, tap);            // root joint 0, same coordinate (rie.py:301)
+          row[col(joints[jj], w0, c)] -= w(2, jj, c, tap);               // x[:, tc] term (rie.py:304)
         }
     for (int k = 0; k < pl.k; ++k) pl.w[(size_t)o * pl.k_pad + k] = (float)(row[k] * sc[o]);
     pl.b[o] = (float)sh[o];
@@ -408,11 +461,11 @@ static PackedLayer pack_expand_folded(r3d_plan* p, int net, const std::string& p
   return pl;
 }
 
-static void pack_tblock(r3d_plan* p, int net, const std::string& pre, const std::vector<int>& joints) {
+static void pack_tblock(r3d_plan* p, int net, const std::string& pre, const std::vector<int>& joints, int group) {
   Folder f{p, net};
   const std::string key = std::to_string(net) + ":" + pre;
   const int C = p->C;
-  p->layers[key + ".expand_conv"] = pack_expand_folded(p, net, pre, joints);
+  p->layers[key + ".expand_conv"] = pack_expand_folded(p, net, pre, joints, group);
   for (size_t i = 1; i < p->widths.size(); ++i) {
     const std::string a = std::to_string(2 * (i - 1)), b = std::to_string(2 * (i - 1) + 1);
     p->layers[key + ".layers_conv." + a] = f.conv(pre + ".layers_conv." + a + ".weight", C, C, p->widths[i], pre + ".layers_bn." + a, "");
@@ -464,7 +517,7 @@ static void build_graph(r3d_plan* p) {
 
   // --- first-layer operand shared by every problem: row (b, t') = [x[b, w0*t' .. w0*t'+w0-1, :] | x[b, tc, :] | 0-pad]
   {
-    const int a0 = add_mat(p, p->lens[0], round_up((p->widths[0] + 1) * p->JC, kKAlign));
+    const int a0 = add_mat(p, p->lens[0], p->a0_kpad);
     for (int q = 0; q < ntb; ++q) p->m_a0.push_back(a0);
   }
   p->m_inc = add_mat(p, 1, round_up(p->JC, kKAlign));
@@ -659,7 +712,7 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
   p->layers.clear();
   if (p->has_pos) {
     for (int g = 0; g < 5; ++g)
-      pack_tblock(p, 0, std::string("LocalLayer_") + kGroupNames[g], p->groups.joints[g]);
+      pack_tblock(p, 0, std::string("LocalLayer_") + kGroupNames[g], p->groups.joints[g], g);
     pack_fcblock(p, 0, "GlobalInfo", p->JC, p->L, 2);
     if (p->cfg.stage != 1)
       for (int i = 0; i < 5; ++i) pack_fcblock(p, 0, "FuseBlocks." + std::to_string(i), 4 * p->L, p->L, 1);
@@ -671,7 +724,7 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
     {
       std::vector<int> all;
       for (int j = 0; j < p->J; ++j) all.push_back(j);
-      pack_tblock(p, 1, "LocalLayer", all);
+      pack_tblock(p, 1, "LocalLayer", all, -1);
     }
     pack_fcblock(p, 1, "GlobalInfo", p->JC, p->L, 2);
     if (p->embed) pack_embed(p, 1);
@@ -684,6 +737,13 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   for (auto& kv : p->layers) {
     PackedLayer& l = kv.second;
+    l.kmask = 0;
+    if (!l.plain && l.k_pad <= 1024) {           // which 16-column K steps carry weight at all
+      for (int o = 0; o < l.n_pad; ++o)
+        for (int k = 0; k < l.k_pad; ++k)
+          if (l.w[(size_t)o * l.k_pad + k] != 0.f) l.kmask |= 1ull << (k / 16);
+      if (l.kmask == 0) l.kmask = 1ull;          // an all-zero layer still has to write its accumulator
+    }
     const size_t ne = l.w.size();
     if (l.plain || prec == R3D_PREC_FP32) { l.off_w0 = take(ne * 4); l.off_w1 = 0; }
     else { l.off_w0 = take(ne * 2); l.off_w1 = prec == R3D_PREC_BF16X3 ? take(ne * 2) : 0; }
@@ -726,6 +786,8 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
          std::to_string((int)p->mats[i].f32) + "]";
   j += "],\"a0\":[";
   for (size_t i = 0; i < p->m_a0.size(); ++i) j += std::string(i ? "," : "") + std::to_string(p->m_a0[i]);
+  j += "],\"a0_map\":[";
+  for (size_t i = 0; i < p->a0_src.size(); ++i) j += std::string(i ? "," : "") + std::to_string(p->a0_src[i]);
   j += "],\"heads\":[";
   for (int q = 0; q < kMaxProb; ++q) j += std::string(q ? "," : "") + std::to_string(p->m_heads[q]);
   j += "],\"slots\":[";
@@ -749,7 +811,7 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
       const auto& b = op.bind[q];
       const PackedLayer& pl = p->layers.at(b.layer);
       j += std::string(q ? "," : "") + "{\"a\":" + std::to_string(b.a) + ",\"a_ld\":" + std::to_string(b.a_ld) + ",\"n\":" + std::to_string(pl.n) +
-           ",\"k\":" + std::to_string(pl.k) + ",\"n_pad\":" + std::to_string(pl.n_pad) + ",\"k_pad\":" + std::to_string(pl.k_pad) + ",\"alg_k\":" + std::to_string(pl.alg_k ? pl.alg_k : pl.k) +
+           ",\"k\":" + std::to_string(pl.k) + ",\"n_pad\":" + std::to_string(pl.n_pad) + ",\"k_pad\":" + std::to_string(pl.k_pad) + ",\"alg_k\":" + std::to_string(pl.alg_k ? pl.alg_k : pl.k) + ",\"k_steps\":" + std::to_string(pl.kmask ? __builtin_popcountll(pl.kmask) : pl.k_pad / 16) +
            (b.layer2.empty() ? std::string() : ",\"layer2\":\"" + b.layer2 + "\",\"n2\":" + std::to_string(p->layers.at(b.layer2).n) +
                                                     ",\"k2\":" + std::to_string(p->layers.at(b.layer2).k)) +
            ",\"layer\":\"" + b.layer +
@@ -940,8 +1002,8 @@ static int bind_workspace(r3d_plan* p, int cap) {
       g.res = mat(b.res, b.res_ld);
       g.res_col = b.res_col;
       g.K = l.k_pad; g.N = l.n; g.n_pad = l.n_pad;
-      g.k_steps = (l.k + 15) / 16;                 // the zero-padded tail of the last K block is never multiplied
-      if (const char* env = getenv("R3D_TC_KTRIM")) if (atoi(env) == 0) g.k_steps = 0;
+      g.kmask = l.kmask;                           // K steps whose weights are all zero are never loaded or multiplied
+      if (const char* env = getenv("R3D_TC_KMASK")) if (atoi(env) == 0) g.kmask = 0;
       g.ndst = dsts(b.dst, b.dst_f32, g.dst);
       ntile = std::min(ntile, pick_n_tile(l.n_pad));
       if (!b.layer2.empty()) {
@@ -987,6 +1049,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
   pd.T = p->T; pd.J = p->J; pd.Cin = p->Cin; pd.JC = p->JC; pd.tc = p->tc; pd.w0 = p->widths[0]; pd.L0 = p->lens[0];
   pd.a0 = mat(p->m_a0[0], 0);
   pd.k_pad = p->mats[p->m_a0[0]].ld;
+  pd.a0_map = nullptr;                           // patched below once the descriptor slab's address is known
   for (int j = 0; j < 32; ++j) pd.flip_perm[j] = (int8_t)(j < (int)p->flip_in.size() ? p->flip_in[j] : j);
   pd.inc = mat(p->m_inc, 0);
   pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;
@@ -1018,7 +1081,11 @@ static int bind_workspace(r3d_plan* p, int cap) {
   p->off_pro = take(sizeof(PrologueDev));
   p->off_asm = take(sizeof(AssembleDev));
   p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
+  const size_t off_map = take(p->a0_src.size() * sizeof(int16_t));
+  CUDA_TRY(cudaMalloc(&p->d_desc, off));
+  pd.a0_map = reinterpret_cast<const int16_t*>(p->d_desc + off_map);
   std::vector<char> h(off, 0);
+  for (size_t k = 0; k < p->a0_src.size(); ++k) reinterpret_cast<int16_t*>(h.data() + off_map)[k] = (int16_t)p->a0_src[k];
   for (size_t i = 0; i < nops; ++i) memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
   memcpy(h.data() + p->off_pro, &pd, sizeof(pd));
   memcpy(h.data() + p->off_asm, &ad, sizeof(ad));
@@ -1029,7 +1096,6 @@ static int bind_workspace(r3d_plan* p, int cap) {
       if (rc != 0) return fail(R3D_ERR_CUDA, "cuTensorMapEncodeTiled failed for op %s (code %d)", p->ops[i].name.c_str(), rc);
     }
   }
-  CUDA_TRY(cudaMalloc(&p->d_desc, off));
   CUDA_TRY(cudaMemcpy(p->d_desc, h.data(), off, cudaMemcpyHostToDevice));
   return R3D_OK;
 }
@@ -1065,7 +1131,9 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
   // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
   // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.
-  const bool use_side = p->use_side_stream;
+  // per-launch timing serialises the launches on one stream: a side-stream launch's start/end events would also span the
+  // time it spends waiting for SMs held by the main stream's kernels
+  const bool use_side = p->use_side_stream && !p->profiling;
   bool forked = false, fork_recorded = false;
   if (use_side) {
     for (const OpHost& oh : p->ops) fork_recorded |= oh.side;
@@ -1430,6 +1498,14 @@ extern "C" R3D_API int r3d_eval_metrics(const float* pred, const float* target, 
 }
 
 // ---- on-device self test: tensor-core GEMM vs FP32 FFMA GEMM -----------------------------------------
+extern "C" R3D_API int r3d_debug_tc_trace(int32_t arm_after_launches, int64_t* out, int32_t cap) {
+  if (out == nullptr) { tc_trace_arm(arm_after_launches); return R3D_OK; }
+  static_assert(sizeof(long long) == sizeof(int64_t), "trace word");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(tc_trace_read(reinterpret_cast<long long*>(out), cap));
+  return R3D_OK;
+}
+
 extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
                                  double* rel_err, double* ms_tc, double* ms_ffma) {
   if (m <= 0 || n <= 0 || k <= 0 || k % kKAlign || n % 16 || nprob < 1 || nprob > kMaxProb)

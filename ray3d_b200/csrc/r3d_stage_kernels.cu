@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   const int T = d.T, J = d.J, JC = d.JC;
   float* xs = smem;                    // [T][JC]
   float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
+  if (threadIdx.x == 0) xs[T * JC] = 0.f;   // zero word read for the padding columns of the first-layer operand
 
   // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
   if (src_is_uv) {
@@ -116,24 +117,49 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   __syncthreads();
 
   // ---- 2. first-layer operand, shared by every joint group (the x-root / x-x[tc] differences are folded into the
-  // weights, see pack_expand_folded): row (b, tq) = [x[b, w0*tq .. w0*tq+w0-1, :] | x[b, tc, :] | 0].  A lane
-  // produces 2 adjacent columns, so warp stores cover 128 contiguous bytes per bf16 plane and the smem reads are
-  // conflict free.
+  // weights, see pack_expand_folded): row (b, tq) holds the w0 frames [w0*tq, w0*tq+w0) and frame tc of the window,
+  // columns ordered joint group by joint group (a0_map) so that each group's weights are non-zero in a few 16-column
+  // K steps only.  A lane produces 2 adjacent columns: warp stores cover 128 contiguous bytes per bf16 plane.
   {
-    const int kp = d.k_pad, k_frames = d.w0 * JC, k_all = k_frames + JC;
+    const int kp = d.k_pad, k_frames = d.w0 * JC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const float* xtc = xs + d.tc * JC;
-    for (int tq = warp; tq < d.L0; tq += nwarp) {          // one warp per row: no index division, 128-byte warp stores
-      const float* xrow = xs + tq * k_frames;
-      const int64_t row = (int64_t)b * d.L0 + tq;
-      for (int kk = lane * 2; kk < kp; kk += 64) {
-        float v[2];
+    const int tc_shift = d.tc * JC - k_frames;                 // map entries >= k_frames address frame tc
+    const int zero_at = T * JC;                                // a shared-memory word that holds 0.f (padding columns)
+    // column k -> (offset into xs, 1 if the offset is relative to the row's first frame)
+    auto decode = [&](int k, int& rel) {
+      const int s = k < kp ? (int)d.a0_map[k] : -1;
+      rel = (s >= 0 && s < k_frames) ? 1 : 0;
+      return s < 0 ? zero_at : (s < k_frames ? s : s + tc_shift);
+    };
+    if (kp <= 512) {                                           // every configuration the reference ships: map in registers
+      int off[16];
+      uint32_t relbits = 0;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int k = kk + j;
-          v[j] = k < k_frames ? xrow[k] : (k < k_all ? xtc[k - k_frames] : 0.f);
+      for (int u = 0; u < 16; ++u) {
+        int rel;
+        off[u] = decode(lane * 2 + (u >> 1) * 64 + (u & 1), rel);
+        relbits |= (uint32_t)rel << u;
+      }
+      for (int tq = warp; tq < d.L0; tq += nwarp) {          // one warp per row: no index division, 128-byte warp stores
+        const int base = tq * k_frames;
+        const int64_t row = (int64_t)b * d.L0 + tq;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int kk = lane * 2 + g * 64;
+          if (kk < kp)
+            store_act2(d.a0, precision, row, kk, xs[off[2 * g] + base * (int)((relbits >> (2 * g)) & 1u)],
+                       xs[off[2 * g + 1] + base * (int)((relbits >> (2 * g + 1)) & 1u)]);
         }
-        store_act2(d.a0, precision, row, kk, v[0], v[1]);
+      }
+    } else {
+      for (int tq = warp; tq < d.L0; tq += nwarp) {
+        const int base = tq * k_frames;
+        const int64_t row = (int64_t)b * d.L0 + tq;
+        for (int kk = lane * 2; kk < kp; kk += 64) {
+          int r0, r1;
+          const int o0 = decode(kk, r0), o1 = decode(kk + 1, r1);
+          store_act2(d.a0, precision, row, kk, xs[o0 + base * r0], xs[o1 + base * r1]);
+        }
       }
     }
   }

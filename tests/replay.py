@@ -8,6 +8,17 @@ by the product package.
 import numpy as np
 
 
+def first_layer_operand(xs, g):
+    """(B, T, J*Cin) window -> (B, L0, k_pad) shared first-layer operand, columns per the plan's a0_map."""
+    B, T, JC = xs.shape
+    tc, w0, L0 = g["tc"], g["w0"], g["L0"]
+    src = np.concatenate([xs.reshape(B, L0, w0 * JC), np.repeat(xs[:, tc][:, None, :], L0, axis=1)], axis=2)
+    amap = np.asarray(g["a0_map"])
+    out = src[:, :, np.maximum(amap, 0)]
+    out[:, :, amap < 0] = 0
+    return out
+
+
 def replay(plan, x, param, dtype=np.float32):
     g = plan.describe()
     B, T, J, Cin = x.shape
@@ -16,11 +27,11 @@ def replay(plan, x, param, dtype=np.float32):
     mats = [np.zeros((B * r, ld), dtype=dtype) for r, ld, _ in g["mats"]]
     xs = x.reshape(B, T, JC).astype(dtype)
     tc, w0, L0 = g["tc"], g["w0"], g["L0"]
-    # ---- input stage: one operand shared by all first-layer problems, row (b, tq) = [w0 frames | x[tc] | 0 pad]
-    # (the x - root / x - x[tc] differences live in the folded expand_conv weights)
+    # ---- input stage: one operand shared by all first-layer problems; row (b, tq) draws its columns from
+    # [w0 frames | x[tc]] through the plan's column map (-1 = zero; the x - root / x - x[tc] differences live in the
+    # folded expand_conv weights, the column order groups each joint group's columns into few K steps)
     A0 = mats[g["a0"][0]].reshape(B, L0, -1)
-    A0[:, :, :w0 * JC] = xs.reshape(B, L0, w0 * JC)
-    A0[:, :, w0 * JC:(w0 + 1) * JC] = xs[:, tc][:, None, :]
+    A0[...] = first_layer_operand(xs, g)
     mats[g["inc"]][:, :JC] = xs[:, tc]
     lrelu = lambda v, s: np.where(v > 0, v, v * dtype(s))
     for e in g["embed"]:
