@@ -157,13 +157,27 @@ R3D_API int r3d_forward_uv_host(r3d_plan* plan, const float* uv_host, const floa
  * launches and the D2H copy are only enqueued -- on the plan's own copy/compute streams with two device staging slots,
  * so the copy of one submission overlaps the kernels of the previous one -- and *ticket names the submission.  Host
  * buffers must be page-locked and stay untouched until r3d_wait(plan, ticket) returns; results are then in pos/trj/sum.
- * Submissions complete in order; at most 8 may be outstanding (the 9th submit blocks on the oldest).
+ * Consecutive submissions alternate between the plan's two lanes (each with its own workspace and streams, sharing
+ * the weights), so besides the copy/compute overlap the under-filled tail launches of one batch run beside the large
+ * launches of the next; they may therefore complete out of order.  At most 8 may be outstanding (the 9th submit
+ * blocks on the oldest).
  * Stands in for the reference's DataLoader(pin_memory) + .cuda() + forward + .cpu() loop body, trainer.py:318-364. */
 R3D_API int r3d_submit_rays_host(r3d_plan* plan, const float* x_host, const float* param_host, float* pos_host, float* trj_host,
                                  float* sum_host, int32_t batch, uint64_t* ticket);
 R3D_API int r3d_submit_uv_host(r3d_plan* plan, const float* uv_host, const float* cam_host, float* pos_host, float* trj_host,
                                float* sum_host, int32_t batch, uint64_t* ticket);
 R3D_API int r3d_wait(r3d_plan* plan, uint64_t ticket);
+
+/* Asynchronous DEVICE-buffer form of r3d_forward_rays / r3d_forward_uv: the launch sequence is ordered after the work
+ * already enqueued on `stream` and runs on one of the plan's two lanes (alternating per submission); `*ticket` names
+ * it.  r3d_join makes `stream` wait for it on the device (no host blocking), r3d_wait blocks the host.  All buffers
+ * must stay valid and untouched until then.  Keeping two submissions in flight is what a loop over independent
+ * batches of windows (trainer.py:318-364) should do: throughput is then bounded by the large launches only. */
+R3D_API int r3d_submit_rays(r3d_plan* plan, const float* x_dev, const float* param_dev, float* pos_dev, float* trj_dev,
+                            float* sum_dev, int32_t batch, void* stream, uint64_t* ticket);
+R3D_API int r3d_submit_uv(r3d_plan* plan, const float* uv_dev, const float* cam_dev, float* pos_dev, float* trj_dev,
+                          float* sum_dev, int32_t batch, void* stream, uint64_t* ticket);
+R3D_API int r3d_join(r3d_plan* plan, uint64_t ticket, void* stream);
 
 /* Sliding-window evaluation of one video without materialising windows:
  * replaces Trainer.eval_data_prepare + np.tile(cam_param) + forward (trainer.py:47-58, 323-337).

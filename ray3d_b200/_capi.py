@@ -59,6 +59,9 @@ EXPORTS = {
     "r3d_submit_rays_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.POINTER(C.c_uint64)]),
     "r3d_submit_uv_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.POINTER(C.c_uint64)]),
     "r3d_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "r3d_submit_rays": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "r3d_submit_uv": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "r3d_join": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "r3d_forward_video": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "r3d_plan_set_flip": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "r3d_forward_rays_tta": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
@@ -258,6 +261,19 @@ class Plan:
 
     def wait(self, ticket: int) -> None:
         check(lib().r3d_wait(self._h, ticket))
+
+    def submit_uv(self, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> int:
+        t = C.c_uint64(0)
+        check(lib().r3d_submit_uv(self._h, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch, stream, C.byref(t)))
+        return int(t.value)
+
+    def submit_rays(self, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> int:
+        t = C.c_uint64(0)
+        check(lib().r3d_submit_rays(self._h, x_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, batch, stream, C.byref(t)))
+        return int(t.value)
+
+    def join(self, ticket: int, stream: int) -> None:
+        check(lib().r3d_join(self._h, ticket, stream))
 
 
 def selftest_gemm(m: int, n: int, k: int, nprob: int = 1, precision: str = "bf16x3", device: int = 0):

@@ -170,9 +170,12 @@ struct r3d_plan {
   // host-call staging
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  static constexpr int kSlots = 4;           // device staging slots of the host-buffer path (slot & 1 = lane)
+  cudaEvent_t ev_in[kSlots] = {}, ev_done[kSlots] = {};
   static constexpr int kTicketRing = 8;      // asynchronous host submissions in flight (r3d_submit_*_host / r3d_wait)
-  cudaEvent_t ev_ticket[kTicketRing] = {};
+  cudaEvent_t ev_ticket[kTicketRing][2] = {};   // per lane
+  uint8_t ticket_lanes[kTicketRing] = {};        // lanes a submission ran on (bit mask)
+  bool use_lanes = true;                         // R3D_LANES=1 keeps every submission on lane 0
   uint64_t submit_seq = 0;                   // tickets handed out so far
   uint64_t slot_seq = 0;                     // staging-slot uses so far (alternates the two slots across calls)
   char* d_stage = nullptr;
@@ -189,7 +192,13 @@ struct r3d_plan {
   std::vector<GraphEntry> graphs;
   int graph_max_batch = 64;                      // R3D_GRAPH_MAX_BATCH; 0 disables
   uint64_t graph_launches = 0;
-  std::mutex mu;
+  std::shared_ptr<std::mutex> mu = std::make_shared<std::mutex>();
+  // Second lane: a twin plan with its own workspace, descriptors and streams that shares this plan's weight slab.
+  // Asynchronous submissions (r3d_submit_*) alternate between the two lanes, so the under-filled tail launches of one
+  // batch (upper tree levels, FC heads) run while the other batch's large launches keep the remaining SMs busy.
+  r3d_plan* twin = nullptr;
+  bool is_twin = false;
+  cudaEvent_t ev_sub = nullptr;                // orders a device submission after the caller's stream
 };
 
 static void clear_graphs(r3d_plan* p) {
@@ -860,19 +869,28 @@ static void free_device(r3d_plan* p) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
-  if (p->d_weights) cudaFree(p->d_weights);
+  if (p->twin) {                                 // the second lane goes with the state it was cloned from
+    cudaDeviceSynchronize();
+    free_device(p->twin);
+    delete p->twin;
+    p->twin = nullptr;
+  }
+  if (p->ev_sub) cudaEventDestroy(p->ev_sub);
+  p->ev_sub = nullptr;
+  if (p->d_weights && !p->is_twin) cudaFree(p->d_weights);
   if (p->d_ws) cudaFree(p->d_ws);
   if (p->d_desc) cudaFree(p->d_desc);
   if (p->d_stage) cudaFree(p->d_stage);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < r3d_plan::kSlots; ++i) {
     if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
     if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
     p->ev_in[i] = p->ev_done[i] = nullptr;
   }
-  for (int i = 0; i < r3d_plan::kTicketRing; ++i) {
-    if (p->ev_ticket[i]) cudaEventDestroy(p->ev_ticket[i]);
-    p->ev_ticket[i] = nullptr;
-  }
+  for (int i = 0; i < r3d_plan::kTicketRing; ++i)
+    for (int l = 0; l < 2; ++l) {
+      if (p->ev_ticket[i][l]) cudaEventDestroy(p->ev_ticket[i][l]);
+      p->ev_ticket[i][l] = nullptr;
+    }
   for (auto& e : p->prof_ev) cudaEventDestroy(e);
   p->prof_ev.clear();
   p->prof_runs = 0;
@@ -896,6 +914,15 @@ extern "C" R3D_API void r3d_plan_destroy(r3d_plan* p) {
   delete p;
 }
 
+static int create_side_stream(r3d_plan* p) {
+  int prio = 0;
+  if (const char* env = getenv("R3D_SIDE_PRIO")) prio = atoi(env);
+  int lo = 0, hi = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least urgent (numerically largest)
+  CUDA_TRY(cudaStreamCreateWithPriority(&p->s_side, cudaStreamNonBlocking, prio > 0 ? lo : prio < 0 ? hi : 0));
+  return R3D_OK;
+}
+
 extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   if (!p->finalized) return fail(R3D_ERR_STATE, "r3d_plan_upload before r3d_plan_finalize");
@@ -907,7 +934,7 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(R3D_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> lk(*p->mu);
   free_device(p);
   p->device = device;
   CUDA_TRY(cudaSetDevice(device));
@@ -934,24 +961,52 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
   {   // experiment knobs: R3D_SIDE_STREAM=0 serialises the GlobalInfo chain; R3D_SIDE_PRIO=-1/0/1 sets its stream priority
-    int prio = 0;
-    if (const char* env = getenv("R3D_SIDE_PRIO")) prio = atoi(env);
     if (const char* env = getenv("R3D_SIDE_STREAM")) p->use_side_stream = atoi(env) != 0;
     if (const char* env = getenv("R3D_GRAPH_MAX_BATCH")) p->graph_max_batch = std::max(0, atoi(env));
-    int lo = 0, hi = 0;
-    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least urgent (numerically largest)
-    CUDA_TRY(cudaStreamCreateWithPriority(&p->s_side, cudaStreamNonBlocking, prio > 0 ? lo : prio < 0 ? hi : 0));
+    const int rc = create_side_stream(p);
+    if (rc) return rc;
   }
   CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < r3d_plan::kSlots; ++i) {
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
   }
-  for (int i = 0; i < r3d_plan::kTicketRing; ++i) {
-    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_ticket[i], cudaEventDisableTiming));
-  }
+  for (int i = 0; i < r3d_plan::kTicketRing; ++i)
+    for (int l = 0; l < 2; ++l) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_ticket[i][l], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&p->ev_sub, cudaEventDisableTiming));
+  if (const char* env = getenv("R3D_LANES")) p->use_lanes = atoi(env) >= 2;
   p->uploaded = true;
+  return R3D_OK;
+}
+
+// Lane `lane` of an uploaded plan (0 = the plan itself).  The twin is cloned on first use: same packed layers / launch
+// graph / weight slab, its own workspace, descriptors, compute + side streams.  Caller holds p->mu.
+static int get_lane(r3d_plan* p, int lane, r3d_plan** out) {
+  *out = p;
+  if (lane == 0) return R3D_OK;
+  if (!p->twin) {
+    std::unique_ptr<r3d_plan> t(new r3d_plan(*p));
+    t->mu = std::make_shared<std::mutex>();
+    t->is_twin = true;
+    t->twin = nullptr;
+    for (int net = 0; net < 2; ++net) t->tensors[net].clear();
+    for (auto& kv : t->layers) { std::vector<float>().swap(kv.second.w); std::vector<float>().swap(kv.second.b); }
+    t->d_ws = nullptr; t->ws_bytes = 0; t->cap = 0; t->d_desc = nullptr; t->d_stage = nullptr; t->stage_bytes = 0;
+    t->graphs.clear(); t->graph_max_batch = 0; t->graph_launches = 0;
+    t->prof_ev.clear(); t->prof_runs = 0; t->profiling = false;
+    t->s_copy = t->s_comp = t->s_side = nullptr;
+    t->ev_fork = t->ev_join = t->ev_sub = nullptr;
+    for (int i = 0; i < r3d_plan::kSlots; ++i) t->ev_in[i] = t->ev_done[i] = nullptr;
+    for (int i = 0; i < r3d_plan::kTicketRing; ++i) t->ev_ticket[i][0] = t->ev_ticket[i][1] = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&t->s_comp, cudaStreamNonBlocking));
+    int rc = create_side_stream(t.get());
+    if (rc) return rc;
+    CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+    p->twin = t.release();
+  }
+  *out = p->twin;
   return R3D_OK;
 }
 
@@ -1235,6 +1290,26 @@ static int forward_graph(r3d_plan* p, const float* src, int64_t src_stride, int 
   return R3D_OK;
 }
 
+// ---- tickets: one ring slot per asynchronous submission, one event per lane it ran on -------------------------------
+static int ticket_slot_reuse(r3d_plan* p) {          // the ring slot's previous owner has completed
+  const int idx = (int)(p->submit_seq % r3d_plan::kTicketRing);
+  if (p->submit_seq >= (uint64_t)r3d_plan::kTicketRing)
+    for (int l = 0; l < 2; ++l)
+      if (p->ticket_lanes[idx] & (1 << l)) CUDA_TRY(cudaEventSynchronize(p->ev_ticket[idx][l]));
+  return R3D_OK;
+}
+static int ticket_issue(r3d_plan* p, int lanes, uint64_t* ticket) {
+  const int idx = (int)(p->submit_seq % r3d_plan::kTicketRing);
+  for (int l = 0; l < 2; ++l)
+    if (lanes & (1 << l)) CUDA_TRY(cudaEventRecord(p->ev_ticket[idx][l], l == 0 ? p->s_comp : p->twin->s_comp));
+  p->ticket_lanes[idx] = (uint8_t)lanes;
+  *ticket = p->submit_seq++;
+  return R3D_OK;
+}
+
+static int forward_dev_core(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                            float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta);
+
 static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
                        float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta = false) {
   int rc = check_forward(p, src, pos, trj, sum, batch);
@@ -1242,7 +1317,39 @@ static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is
   if (tta && p->flip_in.empty()) return fail(R3D_ERR_STATE, "flip augmentation requested before r3d_plan_set_flip");
   if (batch == 0) return R3D_OK;
   if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> lk(*p->mu);
+  return forward_dev_core(p, src, src_stride, is_uv, prm, prm_stride, pos, trj, sum, batch, s, tta);
+}
+
+// Asynchronous device-buffer submission: ordered after the work already enqueued on `stream`, executed on one of the
+// plan's two lanes (alternating), completion observed through r3d_join / r3d_wait.  Inputs and outputs must stay valid
+// until then.  Two submissions in flight keep the GPU busy across the under-filled tail launches of each batch.
+static int submit_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                      float* pos, float* trj, float* sum, int batch, cudaStream_t stream, uint64_t* ticket) {
+  int rc = check_forward(p, src, pos, trj, sum, batch);
+  if (rc) return rc;
+  if (batch != 0 && p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
+  std::lock_guard<std::mutex> lk(*p->mu);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  rc = ticket_slot_reuse(p);
+  r3d_plan* lp = p;
+  if (rc == R3D_OK) rc = get_lane(p, p->use_lanes ? (int)(p->slot_seq++ & 1) : 0, &lp);
+  if (rc == R3D_OK) {
+    CUDA_TRY(cudaEventRecord(p->ev_sub, stream));
+    CUDA_TRY(cudaStreamWaitEvent(lp->s_comp, p->ev_sub, 0));
+    if (batch > 0) rc = forward_dev_core(lp, src, src_stride, is_uv, prm, prm_stride, pos, trj, sum, batch, lp->s_comp, false);
+  }
+  if (rc == R3D_OK) rc = ticket_issue(p, lp == p ? 1 : 2, ticket);
+  if (dev != p->device) cudaSetDevice(dev);
+  return rc;
+}
+
+// caller holds the lane owner's mutex
+static int forward_dev_core(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
+                            float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta) {
+  int rc = R3D_OK;
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
@@ -1280,6 +1387,21 @@ extern "C" R3D_API int r3d_forward_uv(r3d_plan* p, const float* uv, const float*
   return forward_dev(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, (cudaStream_t)stream);
 }
 
+extern "C" R3D_API int r3d_submit_rays(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
+                                       int32_t batch, void* stream, uint64_t* ticket) {
+  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
+  return submit_dev(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, (cudaStream_t)stream, ticket);
+}
+
+extern "C" R3D_API int r3d_submit_uv(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum,
+                                     int32_t batch, void* stream, uint64_t* ticket) {
+  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
+  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_submit_uv needs in_features == 3 (ray encoding, utils.py:91-96)");
+  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "r3d_submit_uv derives param=[height,pitch]: extrinsic_dim must be 2");
+  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
+  return submit_dev(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, (cudaStream_t)stream, ticket);
+}
+
 extern "C" R3D_API int r3d_forward_video(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
                                  int32_t frames_out, void* stream) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
@@ -1292,9 +1414,15 @@ extern "C" R3D_API int r3d_plan_set_flip(r3d_plan* p, const int32_t* in_perm, co
   std::vector<int> a(in_perm, in_perm + p->J), b(out_perm, out_perm + p->J);
   for (int j = 0; j < p->J; ++j)
     if (a[j] < 0 || a[j] >= p->J || b[j] < 0 || b[j] >= p->J) return fail(R3D_ERR_BAD_ARG, "flip permutation entry out of range at joint %d", j);
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> lk(*p->mu);
   p->flip_in = a;
   p->flip_out = b;
+  if (p->twin) {               // the second lane is re-cloned (with the new tables) on its next use
+    cudaDeviceSynchronize();
+    free_device(p->twin);
+    delete p->twin;
+    p->twin = nullptr;
+  }
   if (p->cap > 0) {            // descriptors already on the device: rebuild them with the new tables
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -1329,16 +1457,15 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
   if (rc) return rc;
   if (batch == 0 && ticket == nullptr) return R3D_OK;
   if (batch != 0 && p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> lk(*p->mu);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
-  if (batch == 0) {   // empty submission: a ticket that completes with everything enqueued before it
-    if (p->submit_seq >= (uint64_t)r3d_plan::kTicketRing) CUDA_TRY(cudaEventSynchronize(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing]));
-    CUDA_TRY(cudaEventRecord(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing], p->s_comp));
-    *ticket = p->submit_seq++;
+  if (batch == 0) {   // empty submission: a ticket that completes with everything enqueued before it (on both lanes)
+    rc = ticket_slot_reuse(p);
+    if (rc == R3D_OK) rc = ticket_issue(p, p->twin ? 3 : 1, ticket);
     if (dev != p->device) cudaSetDevice(dev);
-    return R3D_OK;
+    return rc;
   }
   // chunking trades PCIe/compute overlap against per-launch efficiency (small batches under-fill the GPU)
   // measured on B200 (T=243): 1024-sequence chunks keep the kernels efficient; smaller chunks lose more in
@@ -1350,17 +1477,24 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
   const size_t out_b = (size_t)chunk * p->J * 3 * 4, trj_b = (size_t)chunk * 3 * 4;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t slot = al(in_b) + al(prm_b) + 2 * al(out_b) + al(trj_b);
-  if (p->stage_bytes < 2 * slot) {
+  if (p->stage_bytes < r3d_plan::kSlots * slot) {
     if (p->d_stage) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(p->d_stage)); p->d_stage = nullptr; }
-    CUDA_TRY(cudaMalloc(&p->d_stage, 2 * slot));
-    p->stage_bytes = 2 * slot;
+    CUDA_TRY(cudaMalloc(&p->d_stage, r3d_plan::kSlots * slot));
+    p->stage_bytes = r3d_plan::kSlots * slot;
   }
-  rc = ensure_capacity(p, chunk);
-  if (ticket != nullptr && p->submit_seq >= (uint64_t)r3d_plan::kTicketRing)   // the ring slot's previous owner has completed
-    CUDA_TRY(cudaEventSynchronize(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing]));
+  if (ticket != nullptr) rc = ticket_slot_reuse(p);
+  int lanes_used = 0;
   for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += chunk) {
-    const int nb = std::min(chunk, batch - b0), sl = (int)(p->slot_seq++ & 1);
-    char* base = p->d_stage + (size_t)sl * slot;
+    // four staging slots, lane = slot & 1: consecutive chunks / submissions alternate between the two lanes, so the
+    // copy of one overlaps the kernels of the others AND the under-filled tail launches of one batch overlap the
+    // large launches of the next
+    const int nb = std::min(chunk, batch - b0), sl = (int)(p->slot_seq++ % r3d_plan::kSlots);
+    r3d_plan* lp = p;
+    rc = get_lane(p, p->use_lanes ? (sl & 1) : 0, &lp);
+    if (rc == R3D_OK) rc = ensure_capacity(lp, chunk);
+    if (rc) break;
+    lanes_used |= lp == p ? 1 : 2;
+    char* base = p->d_stage + (size_t)sl * (p->stage_bytes / r3d_plan::kSlots);   // fixed stride: submissions of other sizes may be in flight
     float* d_in = reinterpret_cast<float*>(base);
     float* d_prm = reinterpret_cast<float*>(base + al(in_b));
     float* d_pos = reinterpret_cast<float*>(base + al(in_b) + al(prm_b));
@@ -1370,20 +1504,21 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
     CUDA_TRY(cudaMemcpyAsync(d_in, src + (int64_t)b0 * src_stride, (size_t)nb * src_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
     if (prm) CUDA_TRY(cudaMemcpyAsync(d_prm, prm + (int64_t)b0 * prm_stride, (size_t)nb * prm_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
     CUDA_TRY(cudaEventRecord(p->ev_in[sl], p->s_copy));
-    CUDA_TRY(cudaStreamWaitEvent(p->s_comp, p->ev_in[sl], 0));
-    rc = run_chunk(p, d_in, src_stride, is_uv, prm ? d_prm : nullptr, prm_stride, pos ? d_pos : nullptr, trj ? d_trj : nullptr,
-                   sum ? d_sum : nullptr, nb, p->s_comp);
+    cudaStream_t sc = lp->s_comp;
+    CUDA_TRY(cudaStreamWaitEvent(sc, p->ev_in[sl], 0));
+    rc = run_chunk(lp, d_in, src_stride, is_uv, prm ? d_prm : nullptr, prm_stride, pos ? d_pos : nullptr, trj ? d_trj : nullptr,
+                   sum ? d_sum : nullptr, nb, sc);
     if (rc) break;
-    if (pos) CUDA_TRY(cudaMemcpyAsync(pos + (int64_t)b0 * p->J * 3, d_pos, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, p->s_comp));
-    if (sum) CUDA_TRY(cudaMemcpyAsync(sum + (int64_t)b0 * p->J * 3, d_sum, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, p->s_comp));
-    if (trj) CUDA_TRY(cudaMemcpyAsync(trj + (int64_t)b0 * 3, d_trj, (size_t)nb * 12, cudaMemcpyDeviceToHost, p->s_comp));
-    CUDA_TRY(cudaEventRecord(p->ev_done[sl], p->s_comp));
+    if (pos) CUDA_TRY(cudaMemcpyAsync(pos + (int64_t)b0 * p->J * 3, d_pos, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, sc));
+    if (sum) CUDA_TRY(cudaMemcpyAsync(sum + (int64_t)b0 * p->J * 3, d_sum, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, sc));
+    if (trj) CUDA_TRY(cudaMemcpyAsync(trj + (int64_t)b0 * 3, d_trj, (size_t)nb * 12, cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(cudaEventRecord(p->ev_done[sl], sc));
   }
   if (rc == R3D_OK && ticket != nullptr) {
-    CUDA_TRY(cudaEventRecord(p->ev_ticket[p->submit_seq % r3d_plan::kTicketRing], p->s_comp));
-    *ticket = p->submit_seq++;
+    rc = ticket_issue(p, lanes_used, ticket);
   } else if (rc == R3D_OK) {
     CUDA_TRY(cudaStreamSynchronize(p->s_comp));
+    if (p->twin) CUDA_TRY(cudaStreamSynchronize(p->twin->s_comp));
     CUDA_TRY(cudaStreamSynchronize(p->s_copy));
   }
   if (dev != p->device) cudaSetDevice(dev);
@@ -1407,14 +1542,29 @@ extern "C" R3D_API int r3d_submit_uv_host(r3d_plan* p, const float* uv, const fl
 
 extern "C" R3D_API int r3d_wait(r3d_plan* p, uint64_t ticket) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  cudaEvent_t ev;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
   {
-    std::lock_guard<std::mutex> lk(p->mu);
+    std::lock_guard<std::mutex> lk(*p->mu);
     if (ticket >= p->submit_seq) return fail(R3D_ERR_BAD_ARG, "r3d_wait: unknown ticket");
     if (ticket + r3d_plan::kTicketRing < p->submit_seq) return R3D_OK;   // recycled: its successor in the ring was submitted after it completed
-    ev = p->ev_ticket[ticket % r3d_plan::kTicketRing];
+    const int idx = (int)(ticket % r3d_plan::kTicketRing);
+    for (int l = 0; l < 2; ++l)
+      if (p->ticket_lanes[idx] & (1 << l)) ev[l] = p->ev_ticket[idx][l];
   }
-  CUDA_TRY(cudaEventSynchronize(ev));
+  for (int l = 0; l < 2; ++l)
+    if (ev[l]) CUDA_TRY(cudaEventSynchronize(ev[l]));
+  return R3D_OK;
+}
+
+// Stream-ordered completion: `stream` waits (on the device) for the submission; the host does not block.
+extern "C" R3D_API int r3d_join(r3d_plan* p, uint64_t ticket, void* stream) {
+  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
+  std::lock_guard<std::mutex> lk(*p->mu);
+  if (ticket >= p->submit_seq) return fail(R3D_ERR_BAD_ARG, "r3d_join: unknown ticket");
+  if (ticket + r3d_plan::kTicketRing < p->submit_seq) return R3D_OK;     // completed before its ring slot was reused
+  const int idx = (int)(ticket % r3d_plan::kTicketRing);
+  for (int l = 0; l < 2; ++l)
+    if (p->ticket_lanes[idx] & (1 << l)) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_ticket[idx][l], 0));
   return R3D_OK;
 }
 
@@ -1433,7 +1583,7 @@ extern "C" R3D_API int r3d_forward_uv_host(r3d_plan* p, const float* uv, const f
 
 extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> lk(*p->mu);
   p->profiling = enable != 0;
   p->prof_runs = 0;
   return R3D_OK;
@@ -1441,7 +1591,7 @@ extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
 
 extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  std::lock_guard<std::mutex> lk(p->mu);
+  std::lock_guard<std::mutex> lk(*p->mu);
   const int nl = (int)p->ops.size() + 2, nev = 2 * nl;
   if (n_launches) *n_launches = nl;
   const int runs = std::min(p->prof_runs, kProfRing);

@@ -26,6 +26,15 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         raise RuntimeError(f"{what} must be a CUDA tensor: ray3d_b200 has no CPU path (got device {t.device})")
 
 
+class Pending:
+    """An asynchronous device submission: its ticket, its output tensors (valid after ``Lifter.join``) and references
+    that keep the input tensors alive while a lane may still read them."""
+    __slots__ = ("ticket", "outputs", "inputs")
+
+    def __init__(self, ticket: int, outputs, inputs):
+        self.ticket, self.outputs, self.inputs = ticket, outputs, inputs
+
+
 class Lifter:
     """Both networks behind one plan.
 
@@ -105,6 +114,44 @@ class Lifter:
         with torch.cuda.device(uv.device):
             self.plan.forward_uv(_ptr(uv), _ptr(cam), _ptr(pos), _ptr(trj), _ptr(both), uv.shape[0], self._stream(uv.device))
         return pos, trj, both
+
+    # -- asynchronous device entry points: two batches in flight on the plan's two lanes ---------------------------
+    def submit_uv(self, uv: torch.Tensor, cam: torch.Tensor, want_pos=True, want_trj=True, want_sum=True) -> "Pending":
+        """forward_uv without blocking the caller's stream: the batch is lifted on one of the plan's two lanes
+        (alternating), ordered after the work already enqueued on the current stream.  ``join(pending)`` makes the
+        current stream wait for it and returns (pos, trj, pos+trj).  Keep two submissions in flight."""
+        _require_cuda(uv, "uv")
+        _require_cuda(cam, "cam")
+        assert uv.dim() == 4 and uv.shape[2] == self.spec.num_joints and uv.shape[3] == 2
+        assert uv.shape[1] == self.spec.receptive_field and cam.shape == (uv.shape[0], 6)
+        uv, cam = uv.contiguous().float(), cam.contiguous().float()
+        outs = self._outputs(uv.shape[0], uv.device, want_pos, want_trj, want_sum)
+        with torch.cuda.device(uv.device):
+            ticket = self.plan.submit_uv(_ptr(uv), _ptr(cam), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), uv.shape[0],
+                                         self._stream(uv.device))
+        return Pending(ticket, outs, (uv, cam))
+
+    def submit_rays(self, x: torch.Tensor, param: Optional[torch.Tensor], want_pos=True, want_trj=True, want_sum=True) -> "Pending":
+        """Asynchronous forward_rays (see submit_uv)."""
+        self._check_x(x)
+        _require_cuda(x, "x")
+        x = x.contiguous().float()
+        if self.spec.camera_embedding:
+            _require_cuda(param, "param")
+            param = param.contiguous().float()
+        outs = self._outputs(x.shape[0], x.device, want_pos, want_trj, want_sum)
+        with torch.cuda.device(x.device):
+            ticket = self.plan.submit_rays(_ptr(x), _ptr(param) if self.spec.camera_embedding else None, _ptr(outs[0]), _ptr(outs[1]),
+                                           _ptr(outs[2]), x.shape[0], self._stream(x.device))
+        return Pending(ticket, outs, (x, param))
+
+    def join(self, pending: "Pending"):
+        """The current stream waits (on the device) for the submission; returns its (pos, trj, pos+trj)."""
+        dev = next(t for t in pending.outputs if t is not None).device
+        with torch.cuda.device(dev):
+            self.plan.join(pending.ticket, self._stream(dev))
+        pending.inputs = None          # the lane has been ordered before anything that could reuse their memory
+        return pending.outputs
 
     def forward_video(self, seq: torch.Tensor, param: Optional[torch.Tensor]):
         """seq (F+RF-1, J, Cin) f32 cuda (edge-padded video), param (extrinsic_dim,) -> F sliding-window outputs.

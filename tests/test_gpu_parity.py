@@ -100,6 +100,42 @@ def test_streaming_submit_wait_matches_blocking_call(golden_meta):
         lf.submit_uv_host(torch.from_numpy(g["uv"]), torch.from_numpy(g["cam"]).pin_memory(), out)   # pageable input
 
 
+def test_device_submit_join_two_lanes(golden_meta):
+    """r3d_submit_uv / r3d_submit_rays / r3d_join: submissions alternate between the plan's two lanes (own workspace and
+    streams, shared weights); many in flight with ragged sizes, joined out of order and from another stream, results
+    bit-identical to the in-stream call; a weight-independent knob (set_flip) re-clones the second lane."""
+    name = "h36m_s1_t27"
+    spec, lf, _, _ = lifter_for(golden_meta, name, "bf16x3")
+    jobs = []
+    for i, B in enumerate([200, 130, 1, 64, 300, 7, 333, 2, 129, 65, 17, 256]):
+        uv, cam = synth.make_inputs(spec, B, seed=700 + i)
+        uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
+        jobs.append((uvc, camc, lf.submit_uv(uvc, camc)))
+    assert [j[2].ticket for j in jobs] == list(range(jobs[0][2].ticket, jobs[0][2].ticket + len(jobs)))
+    side = torch.cuda.Stream()
+    for k, (uvc, camc, pend) in enumerate(reversed(jobs)):
+        if k % 2:
+            with torch.cuda.stream(side):
+                got = lf.join(pend)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            got = lf.join(pend)
+        ref = lf.forward_uv(uvc, camc)
+        assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    g = load_golden(name)
+    x, prm = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["param"]).cuda()
+    p0, p1 = lf.submit_rays(x, prm), lf.submit_rays(x, prm)             # one per lane
+    a, b = lf.join(p0), lf.join(p1)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    assert relerr(a[2].cpu().numpy(), g["pos64"] + g["trj64"]) < TOL["bf16x3"]
+    lf.set_flip([4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16])            # rebuilds descriptors; lane 2 is re-cloned lazily
+    p0, p1 = lf.submit_rays(x, prm), lf.submit_rays(x, prm)
+    assert all(torch.equal(u, v) for u, v in zip(lf.join(p0), lf.join(p1)))
+    assert all(torch.equal(u, v) for u, v in zip(lf.join(lf.submit_rays(x, prm)), a))
+    with pytest.raises(RuntimeError):
+        lf.plan.join(10 ** 9, 0)                                        # never handed out
+
+
 @pytest.mark.parametrize("name", ["h36m_s1_t27", "h36m_s3_t9"])
 def test_small_batches_replay_a_cuda_graph(golden_meta, name, monkeypatch):
     """Batches <= 64 go through a captured CUDA graph (one launch): bit-identical to the direct launch sequence, for the
