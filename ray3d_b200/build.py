@@ -46,7 +46,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+            trace = ["-DR3D_TC_TRACE"] if os.environ.get("R3D_BUILD_TRACE") == "1" else []   # per-tile clock stamps (scripts/tile_trace.py)
+            cmd = [nvcc, *ARCH, *trace, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                    "-Xptxas", "-v" if verbose else "-warn-spills", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                    "-x", "cu", "-c", s, "-o", o]
             if verbose:

@@ -255,9 +255,8 @@ struct TileCoord {
 // from L2 instead of streaming it from HBM once per problem (measured: 575 MB -> DRAM reads for an 85 MB operand when
 // the walk was problem-major, because the 510 MB output stream flushes L2 in between).  With clusters a unit covers
 // `cl` consecutive m tiles (one per CTA of the pair).
-__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int m_groups, int block_n, int cl, int rank, int total) {
-  if (op.reverse) unit = total - 1 - unit;
-  const int per_m = total / m_groups;            // sum over problems of their n tiles (loop invariant: hoisted by the compiler)
+__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int per_m, int block_n, int cl, int rank, int total) {
+  if (op.reverse) unit = total - 1 - unit;       // per_m = total / m_groups: sum over problems of their n tiles
   const int mg = unit / per_m;
   int rem = unit - mg * per_m;
   int p = 0, n_tiles = 1;
@@ -331,8 +330,14 @@ constexpr int EPI_WARP0 = 4;
 // MMA thread (role 1) and first epilogue warp (role 2): [role][tile index < 64][event < 8].
 constexpr int kTraceTiles = 64, kTraceEvents = 8;
 __device__ long long g_tc_trace[3 * kTraceTiles * kTraceEvents];
+#ifdef R3D_TC_TRACE      // built by `R3D_BUILD_TRACE=1 python -m ray3d_b200.build --force`; the stamps cost ~5 % of the epilogue
 #define R3D_TRACE(role, ti, ev) \
   do { if (trace && (ti) < kTraceTiles) g_tc_trace[((role) * kTraceTiles + (ti)) * kTraceEvents + (ev)] = clock64(); } while (0)
+constexpr bool kTraceBuilt = true;
+#else
+#define R3D_TRACE(role, ti, ev) do { } while (0)
+constexpr bool kTraceBuilt = false;
+#endif
 
 // FUSED: every tile runs two GEMMs back to back -- acc1 = A*W^T (K = w*C), Y = lrelu(acc1 + bias) re-split to bf16
 // hi/lo IN PLACE in tensor memory (each 32-column fp32 chunk becomes 16 hi + 16 lo packed columns), acc2 = Y*W2^T with
@@ -379,12 +384,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
+  const int per_m = total_tiles / m_tiles;                      // tiles per m group (all problems' n tiles)
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
   constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA stages
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   const bool leader = crank == 0;
-  const bool trace = (dbg & 32) && blockIdx.x == 0 && lane == 0;
+  const bool trace = kTraceBuilt && (dbg & 32) && blockIdx.x == 0 && lane == 0;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its own setup early
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       constexpr int PF_DIST = 6;
       int pf_tile = unit0, pf_kb = 0, pf_nkb = 0, pf_m0 = 0, pf_p = 0, pf_ahead = 0;
       if (pf_tile < total_tiles) {
-        const TileCoord t0 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord t0 = decode_tile(op, pf_tile, per_m, BLOCK_N, CL, crank, total_tiles);
         pf_p = t0.p; pf_m0 = t0.m0; pf_nkb = op.prob[t0.p].K / TBK;
       }
       auto prefetch_step = [&]() {
@@ -451,20 +457,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           pf_kb = 0;
           pf_tile += unit_step;
           if (pf_tile < total_tiles) {
-            const TileCoord t1 = decode_tile(op, pf_tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+            const TileCoord t1 = decode_tile(op, pf_tile, per_m, BLOCK_N, CL, crank, total_tiles);
             pf_p = t1.p; pf_m0 = t1.m0; pf_nkb = op.prob[t1.p].K / TBK;
           }
         }
       };
       int ti = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
         R3D_TRACE(0, ti, 0);
         if ((dbg & 256) && tile + unit_step < total_tiles) {     // experiment: next tile's load descriptors -> descriptor cache
-          const TileCoord tn = decode_tile(op, tile + unit_step, m_tiles, BLOCK_N, CL, crank, total_tiles);
+          const TileCoord tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
           const CUtensorMap* nm = tmaps + tn.p * kTmapsPerProb;
           tmap_prefetch(nm + 0); tmap_prefetch(nm + 1);
           tmap_prefetch(nm + (CL == 1 ? 2 : 4)); tmap_prefetch(nm + (CL == 1 ? 3 : 5));
@@ -525,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       uint32_t phase = 0, acc_phase = 0;
       int ti = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
         R3D_TRACE(1, ti, 0);
@@ -638,15 +644,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     // each) stage their 32-row slices into ONE 128-row x 32-column tile per plane, so a single store per destination
     // plane moves all of it (4x fewer store instructions), and the epilogue warps convert the next chunk meanwhile.
     // Protocol per (column half, staging set): the four warps fill their slices, fence, arrive on sready (count 4);
-    // this thread issues the stores, commits, and arrives on sfree once the store engine has read the set (with two
-    // sets: when the following round has been issued).
+    // this thread issues the stores, commits, and arrives on sfree once the store engine has read the set.
     constexpr int EPI_BUFS = CL == 2 ? 2 : 1;
     const int half = warp - 2;
     if (CH == 32 && lane == 0 && half >= 0 && half < COL_SPLIT) {
       const int c_begin = half * CHUNKS_PER_WARP;
       uint32_t round = 0;                                       // staged chunks so far (the client warps count the same)
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-        const TileCoord tc = decode_tile(op, tile, m_tiles, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const GemmProb& pr = op.prob[tc.p];
         const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
         bool any_bf = false;
@@ -670,13 +675,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             }
           }
           bulk_commit();
-          if (EPI_BUFS == 2) {              // the previous round's stores have read their set: it is free again
-            bulk_wait_read1();
-            if (round > 0) mbar_arrive(&sfree_bar[half * 2 + (b ^ 1)]);
-          } else {
-            bulk_wait_read0();
-            mbar_arrive(&sfree_bar[half * 2]);
-          }
+          // The set is handed back as soon as the store engine has read it (a few hundred cycles), not one round later:
+          // the client warps then never wait for their slowest peer's NEXT chunk before reusing a set.
+          bulk_wait_read0();
+          mbar_arrive(&sfree_bar[half * 2 + b]);
           ++round;
         }
       }
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         for (int i = 0; i < 4; ++i) pa[i] = __ldg(g.bias + chunk_of(i) * 32 + lane);
       }
     };
-    TileCoord tc = decode_tile(op, unit0 < total_tiles ? unit0 : 0, m_tiles, BLOCK_N, CL, crank, total_tiles);
+    TileCoord tc = decode_tile(op, unit0 < total_tiles ? unit0 : 0, per_m, BLOCK_N, CL, crank, total_tiles);
     if (BIAS_SMEM && active && unit0 < total_tiles) prefetch_bias(tc);
     uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
     for (int p = 0; p < op.nprob; ++p) {
@@ -732,7 +734,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       if (etrace) R3D_TRACE(2, ti, 0);
       const bool has_next = tile + unit_step < total_tiles;
       TileCoord tn = tc;
-      if (has_next) tn = decode_tile(op, tile + unit_step, m_tiles, BLOCK_N, CL, crank, total_tiles);
+      if (has_next) tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
       const bool ttrace = etrace && (dbg & 128);                 // stamps of the per-tile preamble
       if (ttrace) R3D_TRACE(2, ti, 1);
       if ((dbg & 256) && has_next && lane == 0) {                // experiment: next tile's store descriptors -> descriptor cache
