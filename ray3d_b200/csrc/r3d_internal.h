@@ -84,8 +84,9 @@ struct PrologueDev {
   int32_t T, J, Cin, JC, tc, w0, L0;
   int32_t k_pad;         // row pitch of a0
   Mat a0;                // first-layer operand shared by all problems: [B*L0][k_pad], columns per a0_map
-  const int16_t* a0_map; // [k_pad] source of every operand column: s < w0*JC -> x[w0*t' + s / JC, s % JC];
-                         // s >= w0*JC -> x[tc, s - w0*JC]; -1 -> 0 (see A0Layout in r3d_plan.cpp)
+  const int32_t* a0_off; // [k_pad] decoded source of every operand column (r3d_plan.cpp:build_a0_layout): offset into the
+                         // window staged in shared memory, | 1 << 30 when relative to the row's first frame; padding
+                         // columns point at a zero word
   Mat inc;               // in_current, [B][roundup(J*Cin,64)]
   int32_t n_embed, ext_dim, emb_mid, emb_dim;
   EmbedDev embed[2];

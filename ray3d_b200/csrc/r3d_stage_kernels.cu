@@ -118,47 +118,58 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
 
   // ---- 2. first-layer operand, shared by every joint group (the x-root / x-x[tc] differences are folded into the
   // weights, see pack_expand_folded): row (b, tq) holds the w0 frames [w0*tq, w0*tq+w0) and frame tc of the window,
-  // columns ordered joint group by joint group (a0_map) so that each group's weights are non-zero in a few 16-column
-  // K steps only.  A lane produces 2 adjacent columns: warp stores cover 128 contiguous bytes per bf16 plane.
+  // columns ordered joint group by joint group so that each group's weights are non-zero in a few 16-column K steps
+  // only.  a0_off[k] (decoded on the host) = shared-memory offset of column k's source | kRowRel when it is relative to
+  // the row's first frame.  A lane produces 2 adjacent columns: warp stores cover 128 contiguous bytes per plane.
   {
     const int kp = d.k_pad, k_frames = d.w0 * JC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const int tc_shift = d.tc * JC - k_frames;                 // map entries >= k_frames address frame tc
-    const int zero_at = T * JC;                                // a shared-memory word that holds 0.f (padding columns)
-    // column k -> (offset into xs, 1 if the offset is relative to the row's first frame)
-    auto decode = [&](int k, int& rel) {
-      const int s = k < kp ? (int)d.a0_map[k] : -1;
-      rel = (s >= 0 && s < k_frames) ? 1 : 0;
-      return s < 0 ? zero_at : (s < k_frames ? s : s + tc_shift);
+    constexpr int kRowRel = 1 << 30;
+    auto row_out = [&](int tq, auto&& src) {                   // src(g, j) -> value of column lane*2 + 64*g + j
+      const int64_t rb = ((int64_t)b * d.L0 + tq) * d.a0.ld + lane * 2;
+      if (precision == R3D_PREC_FP32) {
+        float* o = reinterpret_cast<float*>(d.a0.p0) + rb;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (lane * 2 + g * 64 < kp) *reinterpret_cast<float2*>(o + g * 64) = make_float2(src(g, 0), src(g, 1));
+      } else {
+        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d.a0.p0) + rb;
+        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d.a0.p1) + rb;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (lane * 2 + g * 64 < kp) {
+            const float v0 = src(g, 0), v1 = src(g, 1);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+            *reinterpret_cast<__nv_bfloat162*>(oh + g * 64) = hi;
+            if (precision == R3D_PREC_BF16X3) {
+              const float2 hf = __bfloat1622float2(hi);
+              *reinterpret_cast<__nv_bfloat162*>(ol + g * 64) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+            }
+          }
+      }
     };
     if (kp <= 512) {                                           // every configuration the reference ships: map in registers
       int off[16];
       uint32_t relbits = 0;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        int rel;
-        off[u] = decode(lane * 2 + (u >> 1) * 64 + (u & 1), rel);
-        relbits |= (uint32_t)rel << u;
+      for (int g = 0; g < 8; ++g) {
+        const int k = lane * 2 + g * 64;
+        const int2 e = k < kp ? __ldg(reinterpret_cast<const int2*>(d.a0_off + k)) : make_int2(T * JC, T * JC);
+        off[2 * g] = e.x & ~kRowRel;
+        off[2 * g + 1] = e.y & ~kRowRel;
+        relbits |= (e.x & kRowRel ? 1u : 0u) << (2 * g) | (e.y & kRowRel ? 1u : 0u) << (2 * g + 1);
       }
       for (int tq = warp; tq < d.L0; tq += nwarp) {          // one warp per row: no index division, 128-byte warp stores
         const int base = tq * k_frames;
-        const int64_t row = (int64_t)b * d.L0 + tq;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int kk = lane * 2 + g * 64;
-          if (kk < kp)
-            store_act2(d.a0, precision, row, kk, xs[off[2 * g] + base * (int)((relbits >> (2 * g)) & 1u)],
-                       xs[off[2 * g + 1] + base * (int)((relbits >> (2 * g + 1)) & 1u)]);
-        }
+        row_out(tq, [&](int g, int j) { return xs[off[2 * g + j] + base * (int)((relbits >> (2 * g + j)) & 1u)]; });
       }
     } else {
       for (int tq = warp; tq < d.L0; tq += nwarp) {
         const int base = tq * k_frames;
-        const int64_t row = (int64_t)b * d.L0 + tq;
         for (int kk = lane * 2; kk < kp; kk += 64) {
-          int r0, r1;
-          const int o0 = decode(kk, r0), o1 = decode(kk + 1, r1);
-          store_act2(d.a0, precision, row, kk, xs[o0 + base * r0], xs[o1 + base * r1]);
+          const int e0 = d.a0_off[kk], e1 = d.a0_off[kk + 1];
+          store_act2(d.a0, precision, (int64_t)b * d.L0 + tq, kk, xs[(e0 & ~kRowRel) + (e0 & kRowRel ? base : 0)],
+                     xs[(e1 & ~kRowRel) + (e1 & kRowRel ? base : 0)]);
         }
       }
     }
@@ -168,9 +179,9 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   for (int i = threadIdx.x; i < d.inc.ld; i += blockDim.x)
     store_act(d.inc, precision, b, i, i < JC ? xs[d.tc * JC + i] : 0.f);
 
-  // ---- 4. camera embedding (embedding.py:15-19), BN folded, fp32 FFMA ----------------------------
-  for (int e = 0; e < d.n_embed; ++e) {
-    const EmbedDev& em = d.embed[e];
+  // ---- 4. camera embedding (embedding.py:15-19), BN folded, fp32 FFMA; both nets' embedders side by side ----------
+  if (d.n_embed > 0) {
+    const int mid = d.emb_mid, ne = d.n_embed;
     float prm[8];
     if (src_is_uv) {   // param = [height, pitch] (trainer.py:297)
       const float* cam = cam_or_param + (int64_t)bs * param_stride;
@@ -179,18 +190,31 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     } else {
       for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)bs * param_stride + i];
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < d.emb_mid; j += blockDim.x) {
+    for (int t = threadIdx.x; t < ne * mid; t += blockDim.x) {           // hidden layer
+      const EmbedDev& em = d.embed[t / mid];
+      const int j = t % mid;
       float acc = em.b1[j];
       for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(em.w1[j * d.ext_dim + i], prm[i], acc);
-      scratch[j] = acc > 0.f ? acc : 0.01f * acc;
+      scratch[t] = acc > 0.f ? acc : 0.01f * acc;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < d.emb_dim; j += blockDim.x) {
+    for (int t = threadIdx.x; t < ne * d.emb_dim; t += blockDim.x) {     // output layer: 8 independent loads per step
+      const int e = t / d.emb_dim, j = t % d.emb_dim;
+      const EmbedDev& em = d.embed[e];
+      const float* w = em.w2 + j * mid;
+      const float* h = scratch + e * mid;
       float acc = em.b2[j];
-      for (int i = 0; i < d.emb_mid; ++i) acc = fmaf(em.w2[j * d.emb_mid + i], scratch[i], acc);
+      int i = 0;
+      for (; i + 8 <= mid; i += 8) {
+        float wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + i + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(wv[u], h[i + u], acc);     // same summation order as before
+      }
+      for (; i < mid; ++i) acc = fmaf(w[i], h[i], acc);
       acc = acc > 0.f ? acc : 0.01f * acc;
-      for (int t = 0; t < em.ndst; ++t) store_act(em.dst[t].m, precision, b, em.dst[t].col + j, acc);
+      for (int q = 0; q < em.ndst; ++q) store_act(em.dst[q].m, precision, b, em.dst[q].col + j, acc);
     }
   }
 }
@@ -208,7 +232,7 @@ cudaError_t prologue_configure(int max_smem_bytes) {
 cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const void* src,
                             int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
                             int64_t param_stride, int batch, int flip_from, cudaStream_t s) {
-  const size_t smem = (size_t)(h.T * h.JC + h.emb_mid + 16) * sizeof(float);
+  const size_t smem = (size_t)(h.T * h.JC + 2 * h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
   const int threads = 320;
   prologue_kernel<<<batch, threads, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
