@@ -1073,7 +1073,9 @@ static int bind_workspace(r3d_plan* p, int cap) {
     // Tile-width heuristic for the tensor path: the widest tile maximises operand reuse, but the small-M launches
     // (upper tree levels, FC chains) then occupy a fraction of the 148 SMs.  Minimise waves x (tile cost) with a
     // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
-    if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2) {
+    bool tile_heuristic = true;
+    if (const char* env = getenv("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
+    if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
       const int64_t m_tiles = ((int64_t)cap * op.dev.rows_per_seq + 127) / 128;
       auto cost = [&](int bn) {
         int64_t tiles = 0;
