@@ -734,13 +734,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       if (etrace) R3D_TRACE(2, ti, 0);
       const bool has_next = tile + unit_step < total_tiles;
       TileCoord tn = tc;
-      if (has_next) tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
+      bool next_ready = false;                                   // next tile decoded + its bias requested (done inside the chunk loop)
+      // the next tile's coordinates and bias are fetched behind the first chunk's TMEM load, where the warp would stall anyway
+      auto look_ahead = [&]() {
+        if (next_ready) return;
+        next_ready = true;
+        if (!has_next) return;
+        tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
+        if (BIAS_SMEM && active) prefetch_bias(tn);
+      };
       const bool ttrace = etrace && (dbg & 128);                 // stamps of the per-tile preamble
       if (ttrace) R3D_TRACE(2, ti, 1);
-      if ((dbg & 256) && has_next && lane == 0) {                // experiment: next tile's store descriptors -> descriptor cache
-        const CUtensorMap* nm = tmaps + tn.p * kTmapsPerProb + 6;
-        for (int t = 0; t < op.prob[tn.p].ndst; ++t) { tmap_prefetch(nm + 2 * t); tmap_prefetch(nm + 2 * t + 1); }
-      }
       const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
       const int m_base = tc.m0 + q * 32;
       const int row = m_base + lane;
@@ -816,7 +820,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           if (lane + 32 * i < CHUNKS_PER_WARP * CH) my_bias[lane + 32 * i] = pb[i];
         __syncwarp();
         if (ttrace) R3D_TRACE(2, ti, 3);
-        if (has_next) prefetch_bias(tn);      // in flight while this tile's chunks are processed
       }
       if (ttrace) R3D_TRACE(2, ti, 4);
       if (etrace && !ttrace) R3D_TRACE(2, ti, 1);
@@ -858,6 +861,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           if (cc + 1 < CHUNKS_PER_WARP) {        // next chunk's accumulator columns: in flight during this chunk's stores
             if (CH == 32) tmem_ld32(taddr0 + (cc + 1) * CH, r); else tmem_ld16(taddr0 + (cc + 1) * CH, r);
           }
+          look_ahead();
           if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
@@ -944,6 +948,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       }
       if (FUSED) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      look_ahead();                            // (warps without chunks in this tile)
       tc = tn;
     }
     __syncwarp();

@@ -1479,7 +1479,9 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
   // chunking trades PCIe/compute overlap against per-launch efficiency (small batches under-fill the GPU)
   // measured on B200 (T=243): 1024-sequence chunks keep the kernels efficient; smaller chunks lose more in
   // under-filled launches than they gain in copy/compute overlap (H2D of 1024 windows is 0.6 ms at 55 GB/s)
-  int parts = std::max(1, batch / 1024);
+  // ... for streamed submissions.  A blocking call has nothing else to overlap with, so it splits into 512-window chunks
+  // that alternate between the two lanes: the second chunk's copy runs under the first chunk's kernels (+16 %).
+  int parts = std::max(1, batch / (ticket != nullptr ? 1024 : 512));
   if (const char* env = getenv("R3D_HOST_CHUNKS")) parts = std::max(1, atoi(env));
   const int chunk = std::min(batch, std::max(64, std::min(kMaxChunk, (batch + parts - 1) / parts)));
   const size_t in_b = (size_t)chunk * src_stride * 4, prm_b = (size_t)chunk * std::max<int64_t>(prm_stride, 1) * 4;
