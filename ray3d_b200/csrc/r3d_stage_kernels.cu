@@ -7,6 +7,8 @@
 //   group gather + cat ......... lib/model/rie.py:306-357 (pose), :540 (trajectory)
 //   Embedding .................. lib/model/embedding.py:15-19 (LeakyReLU slope 0.01)
 //   output joint order ......... lib/model/rie.py:415-432; pos += trj trainer.py:353
+#include <cstdlib>
+
 #include "r3d_internal.h"
 
 namespace r3d {
@@ -234,7 +236,12 @@ cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int
                             int64_t param_stride, int batch, int flip_from, cudaStream_t s) {
   const size_t smem = (size_t)(h.T * h.JC + 2 * h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
-  const int threads = 320;
+  static int threads = 0;
+  if (threads == 0) {
+    threads = 256;      // measured: 4 CTAs x 256 threads per SM (register-limited) beat 3 x 320 (57 vs 64 us at B=1024, T=243)
+    if (const char* env = getenv("R3D_PROLOGUE_THREADS")) threads = atoi(env);
+    if (threads < 64 || threads > 320 || threads % 32) threads = 256;
+  }
   prologue_kernel<<<batch, threads, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
                                            src_is_uv, cam_or_param, param_stride, batch, flip_from);
   return cudaGetLastError();
