@@ -34,13 +34,13 @@ constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 384;            // 4 control warps + 8 epilogue warps
 constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 256;   // keeps the staging tiles 1024-byte aligned
 // barriers, descriptor, per-warp hi/lo store staging tiles (double buffered in 2-SM mode, where the W half-tiles leave room)
-__host__ __device__ constexpr int tc_aux_bytes(int cl) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + (cl == 2 ? 8 * 512 : 0); }
+__host__ __device__ constexpr int tc_aux_bytes(int cl, int ew = 8) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + (cl == 2 ? ew * 512 : 0); }
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // per-CTA bytes of one K block: A tile (128 rows) + this CTA's share of the W tile (all of it, or half in 2-SM mode)
 __host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit, int cl = 1) { return nsplit * (TBM + block_n / cl) * TBK * 2; }
-__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1) {
-  int s = (SMEM_LIMIT - tc_aux_bytes(cl)) / tc_stage_bytes(block_n, nsplit, cl);
+__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1, int ew = 8) {
+  int s = (SMEM_LIMIT - tc_aux_bytes(cl, ew)) / tc_stage_bytes(block_n, nsplit, cl);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
@@ -108,6 +108,17 @@ __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const void* tmap, const void* smem_src, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void tmap_prefetch(const void* tmap) {
@@ -329,7 +340,7 @@ constexpr int EPI_WARP0 = 4;
 // Diagnostics (R3D_TC_DEBUG bit 32 / r3d_debug_tc_trace): CTA 0 records SM clock stamps per tile for its producer (role 0),
 // MMA thread (role 1) and first epilogue warp (role 2): [role][tile index < 64][event < 8].
 constexpr int kTraceTiles = 64, kTraceEvents = 8;
-__device__ long long g_tc_trace[3 * kTraceTiles * kTraceEvents];
+__device__ long long g_tc_trace[4 * kTraceTiles * kTraceEvents];   // role 3: store thread of column half 0
 #ifdef R3D_TC_TRACE      // built by `R3D_BUILD_TRACE=1 python -m ray3d_b200.build --force`; the stamps cost ~5 % of the epilogue
 #define R3D_TRACE(role, ti, ev) \
   do { if (trace && (ti) < kTraceTiles) g_tc_trace[((role) * kTraceTiles + (ti)) * kTraceEvents + (ev)] = clock64(); } while (0)
@@ -343,21 +354,30 @@ constexpr bool kTraceBuilt = false;
 // hi/lo IN PLACE in tensor memory (each 32-column fp32 chunk becomes 16 hi + 16 lo packed columns), acc2 = Y*W2^T with
 // the A operand read from tensor memory (TS-mode tcgen05.mma), then the usual epilogue on acc2.  TMEM: columns
 // [0,256) acc1/Y, [256,512) acc2.  Needs BLOCK_N == 256 == channels.
-template <int BLOCK_N, int NSPLIT, int CL, bool FUSED>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
-                                                                int M, int total_tiles, int dbg) {
+// EW: epilogue warps, 8 or 16.  The 16-warp form (640 threads, <= 102 registers) is for launches whose tiles are short in K
+// and therefore bound by the epilogue (the first layer): four warps per TMEM lane quarter, each converting 64 of the 256
+// columns, twice the latency-hiding of the 8-warp form; it has no residual path and one staging set per column group.
+template <int BLOCK_N, int NSPLIT, int CL, bool FUSED, int EW = 8>
+__global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
+                                                                   int M, int total_tiles, int dbg) {
+  static_assert(EW == 8 || (EW == 16 && !FUSED && CL == 2 && BLOCK_N == 256), "16 epilogue warps: plain 2-SM 256-column tiles only");
+  constexpr int NTHREADS = 128 + 32 * EW;
   // CL == 2: the CTA pair works as one 256-row tile with cta_group::2 MMAs; each CTA stages its own 128 A rows and
   // HALF of the W tile (the tensor cores read the other half from the peer's shared memory), which cuts the bytes
   // every SM has to receive per MMA by a third -- the measured limiter (~74 GB/s per SM from L2) -- and buys a third
   // pipeline stage.
-  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL);
+  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL, EW);
   constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = (BLOCK_N / CL) * TBK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT, CL);
   constexpr int TMEM_COLS = tc_tmem_cols(BLOCK_N);
   constexpr int CH = BLOCK_N >= 32 ? 32 : 16;         // epilogue column chunk
   constexpr int NCHUNK = BLOCK_N / CH;
-  constexpr int COL_SPLIT = NCHUNK >= 2 ? 2 : 1;      // two epilogue warps share a TMEM lane quarter when possible
+  constexpr int COL_SPLIT = NCHUNK >= EW / 4 ? EW / 4 : (NCHUNK >= 2 ? 2 : 1);   // epilogue warps sharing a TMEM lane quarter split the columns
   constexpr int CHUNKS_PER_WARP = NCHUNK / COL_SPLIT;
+  // Column groups are interleaved chunk by chunk (group g converts chunks g, g + COL_SPLIT, ...): the groups then write
+  // neighbouring 64-byte pieces of the same output rows at about the same time, so L2 sees whole 128-byte lines complete
+  // quickly instead of half lines waiting a thousand cycles for their other half.
+  auto chunk_index = [](int grp, int cc) { return cc * COL_SPLIT + grp; };
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(!FUSED || BLOCK_N == 256, "the fused conv pair keeps a full 256-channel row per tile");
 
@@ -376,9 +396,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
   // epilogue warp <-> store thread hand-off, per epilogue warp and staging set: "staged tile ready" / "staging set free"
-  static_assert(sizeof(GemmOpDev) % 8 == 0 && 256 + sizeof(GemmOpDev) + 8 * 8 <= 256 + kOpSmemBytes, "no room for the store barriers");
+  static_assert(sizeof(GemmOpDev) % 8 == 0 && 256 + sizeof(GemmOpDev) + 16 * 8 <= 256 + kOpSmemBytes, "no room for the store barriers");
   uint64_t* sready_bar = reinterpret_cast<uint64_t*>(aux + 256 + sizeof(GemmOpDev));   // [column half][staging set], 4 arrivals
-  uint64_t* sfree_bar = sready_bar + 4;                                                 // [column half][staging set]
+  uint64_t* sfree_bar = sready_bar + 8;                                                 // [column group][staging set]
   uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][sets][2 planes][32 rows x 64 B]
   float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes + 8 * 4096 * (CL == 2 ? 2 : 1));   // CL == 2: [EPI_WARPS][128]
 
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(opp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(sop);
-    for (int i = threadIdx.x; i < (int)(sizeof(GemmOpDev) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < (int)(sizeof(GemmOpDev) / 4); i += NTHREADS) dst[i] = __ldg(src + i);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -405,11 +425,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS * CL);                // CL == 2: the peer's epilogue warps arrive remotely
-      mbar_init(&yready_bar[a], EPI_WARPS * CL);
+      mbar_init(&tempty_bar[a], EW * CL);                // CL == 2: the peer's epilogue warps arrive remotely
+      mbar_init(&yready_bar[a], EW * CL);
     }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&sready_bar[i], 4);                             // the four epilogue warps (TMEM lane quarters) of a column half
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&sready_bar[i], 4);                             // the four epilogue warps (TMEM lane quarters) of a column group
       mbar_init(&sfree_bar[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -463,11 +483,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         }
       };
       int ti = 0;
+      bool shared_a = op.nprob > 1 && !(dbg & 1024);
+      for (int p = 1; p < op.nprob; ++p) shared_a = shared_a && op.prob[p].a.p0 == op.prob[0].a.p0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
+        // activations are streamed once (evict first) -- unless every problem of the launch reads the SAME operand (the
+        // first layer): then it must survive in L2 from one problem's tile to the next while the output stream passes by
+        const uint64_t a_hint = shared_a ? kEvictLast : kEvictFirst;
         R3D_TRACE(0, ti, 0);
         if ((dbg & 256) && tile + unit_step < total_tiles) {     // experiment: next tile's load descriptors -> descriptor cache
           const TileCoord tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
@@ -485,16 +510,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           uint8_t* st = smem + stage * STAGE_BYTES;
           if (CL == 1) {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
-            if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
+            tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, a_hint);
+            if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, a_hint);
             tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
             if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
           } else {
             // both CTAs' loads complete on the leader's barrier, which the (leader-only) MMA thread waits on
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
             const int wrow = tc.n0 + crank * W_PART_ROWS;
-            tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
-            if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, kEvictFirst);
+            tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, a_hint);
+            if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, a_hint);
             tma_load_2d_2sm(st + NSPLIT * A_BYTES, tm + 4, &full_bar[stage], kb * TBK, wrow, kEvictLast);
             if (NSPLIT == 2) tma_load_2d_2sm(st + 2 * A_BYTES + W_BYTES, tm + 5, &full_bar[stage], kb * TBK, wrow, kEvictLast);
           }
@@ -645,12 +670,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     // plane moves all of it (4x fewer store instructions), and the epilogue warps convert the next chunk meanwhile.
     // Protocol per (column half, staging set): the four warps fill their slices, fence, arrive on sready (count 4);
     // this thread issues the stores, commits, and arrives on sfree once the store engine has read the set.
-    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;
-    const int half = warp - 2;
-    if (CH == 32 && lane == 0 && half >= 0 && half < COL_SPLIT) {
-      const int c_begin = half * CHUNKS_PER_WARP;
-      uint32_t round = 0;                                       // staged chunks so far (the client warps count the same)
-      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+    constexpr int EPI_BUFS = (CL == 2 && EW == 8) ? 2 : 1;
+    constexpr int GPS = COL_SPLIT > 2 ? COL_SPLIT / 2 : 1;      // column groups per store thread (2 with 16 epilogue warps)
+    const int st = warp - 2;
+    if (CH == 32 && lane == 0 && st >= 0 && st * GPS < COL_SPLIT) {
+      uint32_t round = 0;                                       // staged chunks per group so far (the client warps count the same)
+      uint64_t* prev_free = nullptr;                            // GPS == 2: set handed back one store later (while the next is read)
+      int ti = 0;
+      const bool strace3 = trace && st == 0;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const GemmProb& pr = op.prob[tc.p];
         const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
@@ -658,28 +686,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         for (int t = 0; t < pr.ndst; ++t) any_bf |= pr.dst[t].f32 == 0;
         if (!any_bf || (dbg & 4)) continue;
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
-          const int n = tc.n0 + (c_begin + cc) * CH;
-          if (n >= pr.N) continue;
           const int b = EPI_BUFS == 2 ? (int)(round & 1) : 0;
           const uint32_t uses = EPI_BUFS == 2 ? round >> 1 : round;
-          mbar_wait(&sready_bar[half * 2 + b], uses & 1);
-          if (!(dbg & 1)) {
-            const uint4* tile_hi = stage_s + (half * EPI_BUFS + b) * 1024;
-            const uint4* tile_lo = tile_hi + 512;
-            const int srow = (dbg & 16) ? 0 : tc.m0;                       // experiment: keep every store in the same L2-resident rows
-            for (int t = 0; t < pr.ndst; ++t) {
-              const Dst& d = pr.dst[t];
-              if (d.f32) continue;
-              tma_store_2d(dmaps + 2 * t, tile_hi, d.col + n, srow);
-              if (d.m.p1 != nullptr) tma_store_2d(dmaps + 2 * t + 1, tile_lo, d.col + n, srow);
+          bool any = false;
+          for (int gi = 0; gi < GPS; ++gi) {
+            const int grp = st * GPS + gi;
+            const int n = tc.n0 + chunk_index(grp, cc) * CH;
+            if (n >= pr.N) continue;                            // (16-warp launches have N == BLOCK_N: never taken there)
+            any = true;
+            mbar_wait(&sready_bar[grp * 2 + b], uses & 1);
+            if (strace3 && gi == 0 && cc < 4) R3D_TRACE(3, ti, 2 * cc);
+            // generic-proxy writes of the four client warps (ordered before this point by their mbarrier arrivals) ->
+            // async proxy: ONE proxy fence here, on the causality path between the writes and the tensor stores, instead
+            // of one per writing warp (the fence drains the SM's shared-memory pipe: 32 of them per tile serialised the
+            // whole epilogue at ~250 cycles each)
+            if (!(dbg & 512)) fence_async_smem();
+            if (!(dbg & 1)) {
+              const uint4* tile_hi = stage_s + (grp * EPI_BUFS + b) * 1024;
+              const int srow = (dbg & 16) ? 0 : tc.m0;                     // experiment: keep every store in the same L2-resident rows
+              for (int t = 0; t < pr.ndst; ++t) {
+                const Dst& d = pr.dst[t];
+                if (d.f32) continue;
+                if (NSPLIT == 2 && (dbg & 2048)) tma_store_3d_hint(dmaps + 2 * t, tile_hi, d.col + n, srow, 0, 0x12F0000000000000ull);   // experiment: evict-first output stream
+                else if (NSPLIT == 2) tma_store_3d(dmaps + 2 * t, tile_hi, d.col + n, srow, 0);    // both planes, one store
+                else tma_store_2d(dmaps + 2 * t, tile_hi, d.col + n, srow);
+              }
+            }
+            bulk_commit();
+            // The set is handed back as soon as the store engine has read it (a few hundred cycles), not one round later:
+            // the client warps then never wait for their slowest peer's NEXT chunk before reusing a set.
+            if (GPS == 1) {
+              bulk_wait_read0();
+              if (strace3 && cc < 4) R3D_TRACE(3, ti, 2 * cc + 1);
+              mbar_arrive(&sfree_bar[grp * 2 + b]);
+            } else {                                            // two groups alternate: wait for the previous group's store only
+              bulk_wait_read1();
+              if (prev_free != nullptr) mbar_arrive(prev_free);
+              prev_free = &sfree_bar[grp * 2 + b];
             }
           }
-          bulk_commit();
-          // The set is handed back as soon as the store engine has read it (a few hundred cycles), not one round later:
-          // the client warps then never wait for their slowest peer's NEXT chunk before reusing a set.
-          bulk_wait_read0();
-          mbar_arrive(&sfree_bar[half * 2 + b]);
-          ++round;
+          if (any) ++round;
         }
       }
       bulk_wait0();                          // every TMA store issued by this thread has landed
@@ -689,11 +735,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     // =============================== epilogue ===============================
     const int ew = warp - EPI_WARP0;
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                                 // which half of the columns
+    const int half = ew >> 2;                                 // column group (half of the columns with 8 epilogue warps)
     const bool active = half < COL_SPLIT;
-    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;                 // staging tile sets per warp (hi + lo each)
-    // staging: [column half][set][plane] tiles of 128 rows x 64 B (64B-swizzled); this warp owns rows [32 q, 32 q + 32)
-    uint4* const stage_base = stage_s + half * EPI_BUFS * 1024 + q * 128;
+    constexpr int EPI_BUFS = (CL == 2 && EW == 8) ? 2 : 1;    // staging tile sets per column group (hi + lo each)
+    // staging: [column group][set][plane] tiles of 128 rows x 64 B (64B-swizzled): the smem image of a (32 columns, 128 rows,
+    // 2 planes) box, so ONE 3-D TMA store writes both planes; this warp owns rows [32 q, 32 q + 32)
+    uint4* const stage_base = stage_s + half * EPI_BUFS * 1024;
     uint32_t sround = 0;                                      // chunks this warp has handed to its store thread
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -701,17 +748,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     const bool etrace = trace && ew == 0;
     int ti = 0;
     constexpr bool BIAS_SMEM = CL == 2;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
-    constexpr int PB = (CHUNKS_PER_WARP * CH + 31) / 32;          // bias words per lane for this warp's columns
-    const int c_begin = half * CHUNKS_PER_WARP;
+    constexpr int PB = CHUNKS_PER_WARP;                           // bias words per lane: one per chunk of this warp
     auto chunk_of = [&](int cc) { return (cc >> 1) * 4 + half * 2 + (cc & 1); };     // FUSED: first-GEMM chunk order
     // The epilogue warps are the critical path of the short-K launches: the coordinates and the folded bias of the NEXT
     // tile are fetched while the current tile is processed (registers), so no tile starts with an L2 round trip.
     float pb[PB], pa[4];
     auto prefetch_bias = [&](const TileCoord& t) {
       const GemmProb& g = op.prob[t.p];
-      const float* bp = (FUSED ? g.bias2 : g.bias) + t.n0 + c_begin * CH;
+      const float* bp = (FUSED ? g.bias2 : g.bias) + t.n0;
 #pragma unroll
-      for (int i = 0; i < PB; ++i) pb[i] = (lane + 32 * i < CHUNKS_PER_WARP * CH) ? __ldg(bp + lane + 32 * i) : 0.f;
+      for (int i = 0; i < PB; ++i) pb[i] = lane < CH ? __ldg(bp + chunk_index(half, i) * CH + lane) : 0.f;   // chunk i of this warp
       if (FUSED) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) pa[i] = __ldg(g.bias + chunk_of(i) * 32 + lane);
@@ -750,13 +796,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       const int row = m_base + lane;
       const bool row_ok = row < M;
       const uint32_t pf = pflags >> (4 * tc.p);
-      const bool any_f32 = pf & 1u, any_bf = pf & 2u, any_lo = pf & 4u, has_res = pf & 8u;
+      const bool any_f32 = pf & 1u, any_bf = pf & 2u, any_lo = pf & 4u, has_res = EW == 8 && (pf & 8u);
       if (ttrace) R3D_TRACE(2, ti, 2);
       const __nv_bfloat16* res_hi = reinterpret_cast<const __nv_bfloat16*>(pr.res.p0);
       const __nv_bfloat16* res_lo = reinterpret_cast<const __nv_bfloat16*>(pr.res.p1);
       ResidualRegs rr;
       if (active && has_res && CH == 32)      // first chunk's residual: in flight while the main loop still runs
-        residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + c_begin * CH, lane, m_base, M);
+        residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + chunk_index(half, 0) * CH, lane, m_base, M);
       float* my_bias = bias_s + ew * 128;
       if (FUSED) {
         // ---- epilogue of the first GEMM: acc1 -> Y = lrelu(acc1 + bias) as bf16 hi/lo, in place in tensor memory
@@ -817,7 +863,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < PB; ++i)
-          if (lane + 32 * i < CHUNKS_PER_WARP * CH) my_bias[lane + 32 * i] = pb[i];
+          if (lane < CH) my_bias[i * CH + lane] = pb[i];
         __syncwarp();
         if (ttrace) R3D_TRACE(2, ti, 3);
       }
@@ -829,12 +875,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       if (etrace && !ttrace) R3D_TRACE(2, ti, 2);
       if (active) {
         uint32_t r[32];
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c_begin * CH);
-        if (CH == 32) tmem_ld32(taddr0, r); else tmem_ld16(taddr0, r);       // chunk 0; later chunks are issued one ahead
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc_col;
+        if (CH == 32) tmem_ld32(taddr0 + chunk_index(half, 0) * CH, r); else tmem_ld16(taddr0 + chunk_index(half, 0) * CH, r);   // later chunks: issued one ahead
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
-          const int c = c_begin + cc;
-          const int n = tc.n0 + c * CH;
+          const int n = tc.n0 + chunk_index(half, cc) * CH;
           float bb[CH];
           if (BIAS_SMEM) {
 #pragma unroll
@@ -859,15 +904,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
           }
           if (cc + 1 < CHUNKS_PER_WARP) {        // next chunk's accumulator columns: in flight during this chunk's stores
-            if (CH == 32) tmem_ld32(taddr0 + (cc + 1) * CH, r); else tmem_ld16(taddr0 + (cc + 1) * CH, r);
+            if (CH == 32) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r); else tmem_ld16(taddr0 + chunk_index(half, cc + 1) * CH, r);
           }
           look_ahead();
           if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
             const int sbuf = EPI_BUFS == 2 ? (int)(sround & 1) : 0;
-            uint4* const stage_hi = stage_base + sbuf * 1024;
-            uint4* const stage_lo = stage_hi + 512;
+            uint4* const stage_hi = stage_base + sbuf * 1024 + q * 128;   // this warp's rows of the hi-plane tile (also its residual scratch)
+            uint4* const stage_lo = stage_hi + 512;                        // lo-plane tile: the next 8 KB
             if (CH == 32) {    // the store thread has released this staging set (its previous stores have read it)
               mbar_wait(&sfree_bar[half * 2 + sbuf], (((EPI_BUFS == 2 ? sround >> 1 : sround) & 1) ^ 1));
               if (strace) R3D_TRACE(2, ti, 4);
@@ -876,7 +921,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
               if (CH == 32) {
                 residual_consume(stage_hi, rr, res_lo != nullptr, lane, v);
                 if (cc + 1 < CHUNKS_PER_WARP)     // next chunk's residual, one chunk ahead
-                  residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + n + CH, lane, m_base, M);
+                  residual_issue(rr, res_hi, res_lo, pr.res.ld, pr.res_col + tc.n0 + chunk_index(half, cc + 1) * CH, lane, m_base, M);
               } else if (row_ok) {
                 const int64_t ro = (int64_t)row * pr.res.ld + pr.res_col + n;
                 for (int j = 0; j < CH; ++j) {
@@ -912,7 +957,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
                 stage_write(stage_hi, hi, lane);
                 if (any_lo) stage_write(stage_lo, lo, lane);
                 if (strace) R3D_TRACE(2, ti, 5);
-                fence_async_smem();
+                if (dbg & 512) fence_async_smem();     // experiment: per-writer fences (the previous scheme)
                 __syncwarp();
                 if (strace) R3D_TRACE(2, ti, 6);
                 if (lane == 0) mbar_arrive(&sready_bar[half * 2 + sbuf]);    // the store thread takes it from here
@@ -994,6 +1039,23 @@ static int encode_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// (32 columns, box_rows rows, 2 planes) box over the hi/lo planes of one destination: the planes live in one allocation
+// (workspace slab), so the lo plane is a constant byte offset from the hi plane -> a tensor dimension.
+static int encode_planes_3d(CUtensorMap* out, const void* hi, const void* lo, uint64_t inner, uint64_t rows, uint64_t row_pitch_elems,
+                            uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  const intptr_t plane = reinterpret_cast<intptr_t>(lo) - reinterpret_cast<intptr_t>(hi);
+  if (plane <= 0 || plane % 16) return -6;
+  cuuint64_t dims[3] = {inner, rows, 2};
+  cuuint64_t strides[2] = {row_pitch_elems * 2, (cuuint64_t)plane};
+  cuuint32_t box[3] = {32, box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hi), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 static int tc_block_n(const GemmOpDev& h) {
   if (const char* env = getenv("R3D_TC_NTILE")) {     // experiments: force a narrower tile when it divides every problem
     const int bn = atoi(env);
@@ -1024,14 +1086,15 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
     rc = encode_2d(out + p * kTmapsPerProb + 3, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
                    (uint64_t)g.K, (uint32_t)bn);
     if (rc) return rc;
-    // epilogue store maps: 32-column x 128-row boxes of every bf16 destination plane, 64B swizzle (the staging layout)
+    // epilogue store maps: 32-column x 128-row boxes of every bf16 destination; bf16x3: (32, 128, 2 planes) boxes; 64B swizzle
     for (int t = 0; t < g.ndst; ++t) {
       CUtensorMap* dm = out + p * kTmapsPerProb + 6 + 2 * t;
       if (g.dst[t].f32 || bn < 32) { memset(dm, 0, 2 * sizeof(*dm)); continue; }
-      rc = encode_2d(dm, g.dst[t].m.p0, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows, (uint64_t)g.dst[t].m.ld, TBM, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
-      rc = encode_2d(dm + 1, precision == R3D_PREC_BF16X3 ? g.dst[t].m.p1 : nullptr, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows,
-                     (uint64_t)g.dst[t].m.ld, TBM, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      memset(dm + 1, 0, sizeof(*dm));
+      if (precision == R3D_PREC_BF16X3)    // one store writes both planes
+        rc = encode_planes_3d(dm, g.dst[t].m.p0, g.dst[t].m.p1, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows, (uint64_t)g.dst[t].m.ld, TBM);
+      else
+        rc = encode_2d(dm, g.dst[t].m.p0, (uint64_t)g.dst[t].m.ld, (uint64_t)cap_rows, (uint64_t)g.dst[t].m.ld, TBM, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
     if (h.fused2) {   // second weight matrix of a fused conv pair: full-tile and half-tile (2-SM) boxes
@@ -1059,6 +1122,8 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
 
 template <int BN, int NS, int CL = 1>
 static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_stage_bytes(BN, NS, CL) + tc_aux_bytes(CL); }
+template <int NS>
+static constexpr int tc_smem_bytes_ew16() { return tc_num_stages(256, NS, 2, 16) * tc_stage_bytes(256, NS, 2) + tc_aux_bytes(2, 16); }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
@@ -1072,6 +1137,8 @@ static cudaError_t configure_one() {
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 1>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<256, NS, 2, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes_ew16<NS>());
   }
   return e;
 }
@@ -1080,14 +1147,15 @@ static int g_num_sms = 0;
 static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 enable the L2 prefetch cursor, 16 fold all stores onto 128 rows (timing experiments only)
 static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
+static int g_epi16 = 0;          // 16-epilogue-warp form for short-K launches (R3D_TC_EPI16=1); measured: no gain, the store path limits them
 static int g_trace_arm = -1;     // >= 0: the launch that many GEMM launches from now records the per-tile clock trace
 
 void tc_trace_arm(int launches_from_now) { g_trace_arm = launches_from_now; }
 cudaError_t tc_trace_read(long long* out, int cap) {
-  long long h[3 * kTraceTiles * kTraceEvents];
+  long long h[4 * kTraceTiles * kTraceEvents];
   cudaError_t e = cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h));
   if (e != cudaSuccess) return e;
-  for (int i = 0; i < cap && i < 3 * kTraceTiles * kTraceEvents; ++i) out[i] = h[i];
+  for (int i = 0; i < cap && i < 4 * kTraceTiles * kTraceEvents; ++i) out[i] = h[i];
   return cudaSuccess;
 }
 
@@ -1100,6 +1168,7 @@ cudaError_t tc_configure() {
 #undef R3D_CFG
   if (const char* env = getenv("R3D_TC_CLUSTER")) g_cluster_mode = atoi(env);
   if (const char* env = getenv("R3D_TC_PDL")) g_pdl = atoi(env);
+  if (const char* env = getenv("R3D_TC_EPI16")) g_epi16 = atoi(env);
   if (const char* env = getenv("R3D_TC_DEBUG")) g_dbg = atoi(env);
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -1147,6 +1216,21 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   cfg.attrs = attr;
   cfg.numAttrs = na;
   if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, dbg);
+  if (BN == 256 && g_epi16) {
+    // Epilogue-bound launch?  Few K steps per tile (the masked first layer: <= 16 of them) against a full 256-column
+    // epilogue, many tiles per CTA, no residual, whole 256-column outputs: run it with 16 epilogue warps.
+    bool wide = clusters == max_clusters && units >= 4 * clusters;
+    for (int p = 0; p < h.nprob && wide; ++p) {
+      const GemmProb& g = h.prob[p];
+      const int steps = g.kmask ? __builtin_popcountll(g.kmask) : g.K / UMMA_K;
+      wide = g.res.p0 == nullptr && g.N == 256 && g.n_pad == 256 && steps <= 16;
+    }
+    if (wide) {
+      cfg.blockDim = dim3(128 + 32 * 16);
+      cfg.dynamicSmemBytes = tc_smem_bytes_ew16<NS>();
+      return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, false, 16>, d_op, d_tmaps, M, units, dbg);
+    }
+  }
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2, false>, d_op, d_tmaps, M, units, dbg);
 }
 

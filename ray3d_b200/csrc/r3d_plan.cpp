@@ -1716,8 +1716,9 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   const bool bf_dst = n % 32 == 0;
   uint16_t *dOh = nullptr, *dOl = nullptr;
   if (bf_dst) {
-    CUDA_TRY(cudaMalloc(&dOh, nc * nprob * 2)); CUDA_TRY(cudaMalloc(&dOl, nc * nprob * 2));
-    CUDA_TRY(cudaMemset(dOh, 0, nc * nprob * 2)); CUDA_TRY(cudaMemset(dOl, 0, nc * nprob * 2));
+    CUDA_TRY(cudaMalloc(&dOh, nc * nprob * 4));       // hi and lo planes in one allocation, like the plan's workspace
+    dOl = dOh + nc * nprob;
+    CUDA_TRY(cudaMemset(dOh, 0, nc * nprob * 4));
   }
   GemmOpDev f{}, t{};
   f.nprob = t.nprob = nprob; f.rows_per_seq = t.rows_per_seq = 1; f.slope = t.slope = 0.2f; f.n_tile = t.n_tile = pick_n_tile(n);
@@ -1777,7 +1778,7 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   }
   if (rel_err) *rel_err = md / std::max(mx, 1e-30);
   for (void* q : {(void*)dA, (void*)dW, (void*)dB, (void*)dR, (void*)dC0, (void*)dC1, (void*)dAh, (void*)dAl, (void*)dWh, (void*)dWl,
-                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps, (void*)dOh, (void*)dOl})
+                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps, (void*)dOh})
     cudaFree(q);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return R3D_OK;

@@ -33,19 +33,20 @@ def main():
     names = [o["name"] for o in lf.plan.describe()["ops"]]
     _capi.check(_capi.lib().r3d_debug_tc_trace(a.op, None, 0))
     lf.forward_uv(uvc, camc)
-    buf = (C.c_int64 * (3 * 64 * 8))()
+    buf = (C.c_int64 * (4 * 64 * 8))()
     _capi.check(_capi.lib().r3d_debug_tc_trace(0, buf, len(buf)))
-    tr = np.array(buf, dtype=np.int64).reshape(3, 64, 8)
+    tr = np.array(buf, dtype=np.int64).reshape(4, 64, 8)
     t0 = tr[tr > 0].min()
     rel = np.where(tr > 0, tr - t0, -1)
     print("op", a.op, names[a.op], "(launch order: main-stream ops interleave with the GlobalInfo side chain)")
     print("producer : [tile start, loads issued]")
     print("mma      : [tile start, accumulator free, first operands landed, MMAs issued, (fused: 2nd GEMM issued)]")
     print("epilogue : [tile start, bias staged, accumulator full, chunk0..3 done, tile done]")
+    print("store thr: per chunk round [staged tile ready, store engine has read it] x 4")
     for ti in range(min(a.tiles, 64)):
         if rel[2, ti, 0] < 0:
             break
-        print(f"tile {ti:2d}  P {rel[0, ti, :2].tolist()}  M {rel[1, ti, :5].tolist()}  E {rel[2, ti, :8].tolist()}")
+        print(f"tile {ti:2d}  P {rel[0, ti, :2].tolist()}  M {rel[1, ti, :5].tolist()}  E {rel[2, ti, :8].tolist()}  S {rel[3, ti, :8].tolist()}")
     e = rel[2]
     n = int((e[:, 0] >= 0).sum())
     if n > 3:
