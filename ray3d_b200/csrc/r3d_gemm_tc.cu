@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // activations: streamed once
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // weights: re-read by every tile of the problem
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;  // activations the epilogue reads again as the residual
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
@@ -492,7 +493,13 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
         // activations are streamed once (evict first) -- unless every problem of the launch reads the SAME operand (the
         // first layer): then it must survive in L2 from one problem's tile to the next while the output stream passes by
-        const uint64_t a_hint = shared_a ? kEvictLast : kEvictFirst;
+        // ... or the problem has several column tiles (the FC layers): each of them reads the operand again
+        const uint64_t a_hint = shared_a ? kEvictLast : ((op.prob[tc.p].n_pad > BLOCK_N && !(dbg & 8192)) ? kEvictNormal : kEvictFirst);
+        // the residual of a strided conv is the middle tap of its own operand (rie.py:94): those K blocks are read again
+        // by the epilogue ~one tile later -> keep them out of the evict-first class so the second read hits L2
+        const GemmProb& pp = op.prob[tc.p];
+        const bool res_in_a = pp.res.p0 != nullptr && pp.res.p0 == pp.a.p0 && !(dbg & 4096);
+        const int res_k0 = pp.res_col, res_k1 = pp.res_col + pp.n_pad;
         R3D_TRACE(0, ti, 0);
         if ((dbg & 256) && tile + unit_step < total_tiles) {     // experiment: next tile's load descriptors -> descriptor cache
           const TileCoord tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
@@ -508,18 +515,19 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
+          const uint64_t a_hint_kb = (res_in_a && kb * TBK < res_k1 && (kb + 1) * TBK > res_k0) ? kEvictNormal : a_hint;
           if (CL == 1) {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, a_hint);
-            if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, a_hint);
+            tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, a_hint_kb);
+            if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, a_hint_kb);
             tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
             if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, tc.n0, kEvictLast);
           } else {
             // both CTAs' loads complete on the leader's barrier, which the (leader-only) MMA thread waits on
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
             const int wrow = tc.n0 + crank * W_PART_ROWS;
-            tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, a_hint);
-            if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, a_hint);
+            tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, tc.m0, a_hint_kb);
+            if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, tc.m0, a_hint_kb);
             tma_load_2d_2sm(st + NSPLIT * A_BYTES, tm + 4, &full_bar[stage], kb * TBK, wrow, kEvictLast);
             if (NSPLIT == 2) tma_load_2d_2sm(st + 2 * A_BYTES + W_BYTES, tm + 5, &full_bar[stage], kb * TBK, wrow, kEvictLast);
           }
