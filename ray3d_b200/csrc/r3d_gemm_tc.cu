@@ -1152,7 +1152,12 @@ static cudaError_t configure_one() {
 }
 
 static int g_num_sms = 0;
-static int g_dbg = 0;            // R3D_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip residual, 4 skip epilogue math, 8 enable the L2 prefetch cursor, 16 fold all stores onto 128 rows (timing experiments only)
+// R3D_TC_DEBUG bit mask (timing experiments only; results are wrong with bits 1/2/4/16): 1 skip the TMA stores, 2 skip the
+// residual, 4 skip the epilogue's staging and stores, 8 L2 prefetch cursor, 16 fold all stores onto the same rows,
+// 32 (set by r3d_debug_tc_trace) per-tile clock stamps, 64 / 128 stamp one chunk's sub-steps / the per-tile preamble
+// instead, 256 prefetch the next tile's tensor maps, 512 per-writer proxy fences, 1024 shared operand evict-first,
+// 2048 evict-first hint on the output stores, 4096 residual K blocks evict-first, 8192 FC operands evict-first
+static int g_dbg = 0;
 static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
 static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
 static int g_epi16 = 0;          // 16-epilogue-warp form for short-K launches (R3D_TC_EPI16=1); measured: no gain, the store path limits them
