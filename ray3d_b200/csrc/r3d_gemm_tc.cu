@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
           if (cc + 1 < CHUNKS_PER_WARP) {        // next chunk's accumulator columns: in flight during this chunk's stores
             if (CH == 32) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r); else tmem_ld16(taddr0 + chunk_index(half, cc + 1) * CH, r);
           }
-          look_ahead();
+          if (cc > 0) look_ahead();              // not in chunk 0: the store thread is waiting for that one
           if (n < pr.N && !(dbg & 4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
