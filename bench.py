@@ -167,6 +167,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (ray3d_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner at communicator
+    # creation) is sent to stderr until the line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -383,8 +388,11 @@ def main():
         "flops_per_sequence": flops_per_sequence(spec), "achieved_tflops_step": flops_per_sequence(spec) * value / 1e12,
         "precision": precision,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
