@@ -113,6 +113,39 @@ def test_folded_expand_conv_equals_grouped_conv():
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_first_layer_layout_and_k_step_masks(golden_meta, name):
+    """Column layout of the shared first-layer operand (a0_map) and the zero-step elision, for every joint set
+    (17/15/14) and input width (rays / pixels): each window column is used exactly once plus one root copy per limb slot,
+    every slot starts on a 16-column K step, and the K-step count the plan reports for a layer is exactly the number of
+    16-column steps of its packed weights that hold a non-zero -- limb problems touch 3-4 steps, never the whole row."""
+    from ray3d_b200.spec import GROUP_JOINTS
+    spec = spec_of(golden_meta, name)
+    p, sp, st = make_plan(spec, precision="bf16x3")
+    g = p.describe()
+    J, C, w0 = g["J"], g["Cin"], g["w0"]
+    amap = np.asarray(g["a0_map"])
+    assert len(amap) % 64 == 0
+    used = amap[amap >= 0]
+    want = list(range((w0 + 1) * J * C)) + [t * J * C + c for t in range(w0 + 1) for c in range(C)] * 4   # + 4 root copies
+    assert sorted(used.tolist()) == sorted(want)
+    slot_starts = [0]
+    for grp in ("Torso", "LArm", "RArm", "LLeg", "RLeg"):
+        n = (len(GROUP_JOINTS[J][grp]) + (grp != "Torso")) * (w0 + 1) * C
+        slot_starts.append((slot_starts[-1] + n + 15) // 16 * 16)
+    assert all(s0 % 16 == 0 for s0 in slot_starts) and slot_starts[-1] <= len(amap)
+    first = g["ops"][0]
+    assert first["name"] == "expand_conv"
+    for op in g["ops"]:
+        for pr in op["prob"]:
+            net, layer = pr["layer"].split(":", 1)
+            pw, _ = p.packed_layer(1 << int(net), layer)
+            steps = int((np.abs(pw).reshape(pw.shape[0], -1, 16).max(axis=(0, 2)) > 0).sum())
+            assert pr["k_steps"] == max(steps, 1), (op["name"], layer)
+    limb_steps = [pr["k_steps"] for pr in first["prob"] if "LocalLayer_L" in pr["layer"] or "LocalLayer_R" in pr["layer"]]
+    assert limb_steps and max(limb_steps) <= -(-(4 * (w0 + 1) * C) // 16) + 1 < len(amap) // 16
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_launch_graph_replay_matches_reference(golden_meta, name):
     """Wiring + packing + gather tables: numpy replay of the native graph vs the reference's outputs."""
     spec = spec_of(golden_meta, name)
