@@ -956,6 +956,7 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
     memcpy(slab.data() + l.off_b, l.b.data(), l.b.size() * 4);
   }
   CUDA_TRY(cudaMemcpy(p->d_weights, slab.data(), p->weight_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaDeviceSynchronize());   // (same: the weights must have landed before any non-blocking stream reads them)
   CUDA_TRY(prologue_configure(200 * 1024 + 1024));
   if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
@@ -1025,7 +1026,10 @@ static int bind_workspace(r3d_plan* p, int cap) {
   }
   p->ws_bytes = off;
   CUDA_TRY(cudaMalloc(&p->d_ws, p->ws_bytes));
+  // zero padding must be in place before the first kernel touches it: cudaMemset runs on the legacy stream and may
+  // return early, while the plan's own streams are non-blocking (no implicit ordering with it) -> wait for it here
   CUDA_TRY(cudaMemset(p->d_ws, 0, p->ws_bytes));
+  CUDA_TRY(cudaDeviceSynchronize());
   p->cap = cap;
   auto mat = [&](int id, int ld) {
     Mat m{};
@@ -1161,6 +1165,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
     }
   }
   CUDA_TRY(cudaMemcpy(p->d_desc, h.data(), off, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaDeviceSynchronize());   // a pageable-memory copy may return before its DMA lands; the plan's streams do not wait for the legacy stream
   return R3D_OK;
 }
 
