@@ -136,6 +136,27 @@ def test_device_submit_join_two_lanes(golden_meta):
         lf.plan.join(10 ** 9, 0)                                        # never handed out
 
 
+def test_first_forward_after_workspace_growth_is_already_right(golden_meta):
+    """The workspace is (re)allocated and zero-filled when a larger batch arrives; the fill and the descriptor upload run
+    on the legacy stream while the lanes use non-blocking streams, so they must be complete before the first launch: the
+    very first result on a fresh / grown workspace equals a repeat, on both lanes and through the host path."""
+    name = "h36m_s1_t27"
+    spec = spec_of(golden_meta, name)
+    sp, st = synth.make_state_dicts(spec)
+    for B in (700, 1500):                                        # fresh plan each time: first use of every buffer
+        lf = Lifter(spec, sp, st, precision="bf16x3")
+        uv, cam = synth.make_inputs(spec, B, seed=40 + B)
+        uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
+        first = [lf.submit_uv(uvc, camc), lf.submit_uv(uvc, camc)]            # lane 0 and lane 1, both on new workspaces
+        got = [tuple(t.clone() for t in lf.join(p)) for p in first]
+        again = lf.forward_uv(uvc, camc)
+        for g in got:
+            assert all(torch.equal(a, b) for a, b in zip(g, again))
+        uvh, camh = torch.from_numpy(uv).pin_memory(), torch.from_numpy(cam).pin_memory()
+        assert torch.equal(lf.forward_uv_host(uvh, camh), again[2].cpu())     # fresh staging slots, chunks on both lanes
+        del lf
+
+
 @pytest.mark.parametrize("name", ["h36m_s1_t27", "h36m_s3_t9"])
 def test_small_batches_replay_a_cuda_graph(golden_meta, name, monkeypatch):
     """Batches <= 64 go through a captured CUDA graph (one launch): bit-identical to the direct launch sequence, for the
