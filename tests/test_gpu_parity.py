@@ -136,6 +136,29 @@ def test_device_submit_join_two_lanes(golden_meta):
         lf.plan.join(10 ** 9, 0)                                        # never handed out
 
 
+def test_weight_reload_with_both_lanes_in_use(golden_meta):
+    """Trainer.test reloads the checkpoint every epoch (trainer.py:161): re-supplying the state_dicts and uploading again
+    rebuilds the device state -- including the second lane, which shares the weight slab -- and both lanes then compute
+    with the new weights."""
+    name = "h36m_s1_t27"
+    spec = spec_of(golden_meta, name)
+    sp, st = synth.make_state_dicts(spec)
+    lf = Lifter(spec, sp, st, precision="bf16x3")
+    uv, cam = synth.make_inputs(spec, 200, seed=77)
+    uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
+    old = [lf.join(p)[2].clone() for p in (lf.submit_uv(uvc, camc), lf.submit_uv(uvc, camc))]     # both lanes exist now
+    assert torch.equal(old[0], old[1])
+    rng = np.random.Generator(np.random.PCG64(3))
+    sp2 = {k: (v + 0.01 * rng.standard_normal(v.shape).astype(v.dtype) if k.endswith("weight") and v.ndim > 1 else v) for k, v in sp.items()}
+    lf.plan.load_state(_capi.NET_POS, sp2)
+    lf.plan.load_state(_capi.NET_TRJ, st)
+    lf.plan.finalize()
+    lf.plan.upload(lf.device)
+    new = [lf.join(p)[2].clone() for p in (lf.submit_uv(uvc, camc), lf.submit_uv(uvc, camc))]
+    fresh = Lifter(spec, sp2, st, precision="bf16x3").forward_uv(uvc, camc)[2]
+    assert torch.equal(new[0], fresh) and torch.equal(new[1], fresh) and not torch.equal(new[0], old[0])
+
+
 def test_first_forward_after_workspace_growth_is_already_right(golden_meta):
     """The workspace is (re)allocated and zero-filled when a larger batch arrives; the fill and the descriptor upload run
     on the legacy stream while the lanes use non-blocking streams, so they must be complete before the first launch: the
