@@ -8,16 +8,20 @@
 // as hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory (R3D_PREC_BF16X3, ~1e-5 normwise
 // end to end), or hi*hi only (R3D_PREC_BF16).
 //
-// Structure (one persistent CTA per SM, 256 threads, static round-robin tile schedule):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A / W planes of one 64-wide K block
-//               into a ring of 128B-swizzled smem stages, completion on "full" mbarriers
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16, bf16 -> fp32) for the
-//               1 or 3 products of every K step; tcgen05.commit releases the smem stage ("empty")
-//               and, after the last K block, publishes the accumulator ("tmem_full")
-//   warp 2      allocates / frees the 2 x BLOCK_N TMEM columns (double-buffered accumulators)
-//   warps 4..7  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias + LeakyReLU + residual in
-//               registers, re-split to bf16 hi/lo, 64-byte row-segment stores to up to 6 destinations
-// so the epilogue of tile i overlaps the main loop of tile i+1.
+// Structure (one persistent CTA per SM -- a CTA pair per tile in 2-SM mode --, 384 threads, static round-robin tile
+// schedule):
+//   warp 0       TMA producer: cp.async.bulk.tensor 2D loads of the A / W planes of one 64-wide K block into a ring of
+//                128B-swizzled smem stages, completion on "full" mbarriers; K blocks whose 16-column steps all carry
+//                zero weights (GemmProb::kmask) are never staged; L2 hints per operand class
+//   warp 1       MMA issuer: one thread issues tcgen05.mma (M=128 or 256 with cta_group::2, N=BLOCK_N, K=16, bf16 -> fp32)
+//                for the 1 or 3 products of every non-empty K step; tcgen05.commit releases the smem stage ("empty") and,
+//                after the last K block, publishes the accumulator ("tmem_full")
+//   warp 2       allocates / frees the TMEM columns (two accumulator stages; acc1/Y + acc2 in the fused conv pair)
+//   warps 2, 3   lane 0: store threads -- one TMA tensor store per destination for the 128-row staging tile that the four
+//                epilogue warps of a column group have filled (sready / sfree mbarriers)
+//   warps 4..11  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and chunk), bias + LeakyReLU + residual in registers,
+//                re-split to bf16 hi/lo, 64B-swizzled staging tiles in shared memory
+// so the epilogue of tile i overlaps the main loop of tile i+1.  FUSED: see gemm_tc_kernel below.
 #include <cuda.h>
 
 #include <cstdio>
