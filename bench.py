@@ -265,7 +265,7 @@ def main():
     value = total_B / ms_step * 1e3
 
     # -------- end to end through the host-buffer C-ABI calls (H2D + kernels + D2H of every step inside the timed region)
-    # (1) synchronous call: returns with the step's results in host memory, nothing overlaps;
+    # (1) synchronous call: returns with the step's results in host memory (chunks of the batch overlap inside the call);
     # (2) streaming submit/wait, depth 2: step i+1's H2D copy overlaps step i's kernels (what a loader thread does).
     outs = [torch.empty((B, 1, spec.num_joints, 3), dtype=torch.float32).pin_memory() for _ in range(3)]
     for i in range(3):
@@ -382,7 +382,8 @@ def main():
                                   "api": "Lifter.submit_uv_host / wait -> r3d_submit_uv_host / r3d_wait (pinned host buffers, 3 submissions in flight on the "
                                          "plan's two lanes: each step's H2D copy and tail launches overlap the neighbouring steps' kernels)",
                                   "sync_value": total_B / e2e_sync_ms * 1e3, "sync_ms_per_step": e2e_sync_ms,
-                                  "sync_api": "Lifter.forward_uv_host -> r3d_forward_uv_host (one blocking call per step, no overlap)"},
+                                  "sync_api": "Lifter.forward_uv_host -> r3d_forward_uv_host (one blocking call per step; inside it two 512-window chunks "
+                                              "alternate between the lanes, the second chunk's copy under the first chunk's kernels)"},
         "gpu_launches": lifter.plan.kernel_launches * args.steps, "launches_per_step": lifter.plan.kernel_launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_relerr_vs_oracle_f64": relerr,
         "flops_per_sequence": flops_per_sequence(spec), "achieved_tflops_step": flops_per_sequence(spec) * value / 1e12,
