@@ -84,6 +84,8 @@ struct PrologueDev {
   int32_t T, J, Cin, JC, tc, w0, L0;
   int32_t k_pad;         // row pitch of a0
   Mat a0;                // first-layer operand shared by all problems: [B*L0][k_pad], columns per a0_map
+  const int32_t* a0_row; // [k_pad] source of every operand column as an offset into [w0 frames | frame tc | zero word]
+                         // (the row-wise input stage's per-warp buffer)
   const int32_t* a0_off; // [k_pad] decoded source of every operand column (r3d_plan.cpp:build_a0_layout): offset into the
                          // window staged in shared memory, | 1 << 30 when relative to the row's first frame; padding
                          // columns point at a zero word

@@ -1110,7 +1110,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
   pd.T = p->T; pd.J = p->J; pd.Cin = p->Cin; pd.JC = p->JC; pd.tc = p->tc; pd.w0 = p->widths[0]; pd.L0 = p->lens[0];
   pd.a0 = mat(p->m_a0[0], 0);
   pd.k_pad = p->mats[p->m_a0[0]].ld;
-  pd.a0_off = nullptr;                           // patched below once the descriptor slab's address is known
+  pd.a0_off = pd.a0_row = nullptr;               // patched below once the descriptor slab's address is known
   for (int j = 0; j < 32; ++j) pd.flip_perm[j] = (int8_t)(j < (int)p->flip_in.size() ? p->flip_in[j] : j);
   pd.inc = mat(p->m_inc, 0);
   pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;
@@ -1143,8 +1143,10 @@ static int bind_workspace(r3d_plan* p, int cap) {
   p->off_asm = take(sizeof(AssembleDev));
   p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
   const size_t off_map = take(p->a0_src.size() * sizeof(int32_t));
+  const size_t off_map_row = take(p->a0_src.size() * sizeof(int32_t));
   CUDA_TRY(cudaMalloc(&p->d_desc, off));
   pd.a0_off = reinterpret_cast<const int32_t*>(p->d_desc + off_map);
+  pd.a0_row = reinterpret_cast<const int32_t*>(p->d_desc + off_map_row);
   std::vector<char> h(off, 0);
   {   // a0_src (index into [w0 frames | frame tc]) -> offset into the staged window, row-relative flag in bit 30
     const int k_frames = p->widths[0] * p->JC;
@@ -1152,6 +1154,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
       const int sidx = p->a0_src[k];
       reinterpret_cast<int32_t*>(h.data() + off_map)[k] =
           sidx < 0 ? p->T * p->JC : (sidx < k_frames ? (sidx | (1 << 30)) : sidx - k_frames + p->tc * p->JC);
+      reinterpret_cast<int32_t*>(h.data() + off_map_row)[k] = sidx < 0 ? k_frames + p->JC : sidx;
     }
   }
   for (size_t i = 0; i < nops; ++i) memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));

@@ -221,6 +221,174 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   }
 }
 
+// ---- input stage, row-wise form ---------------------------------------------------------------------------------
+// Same outputs as prologue_kernel, bit for bit, without staging the whole window: every warp builds operand rows on its
+// own.  A row (b, tq) needs the w0 frames [w0*tq, w0*tq + w0) and frame tc; the warp ray-encodes those w0*J keypoints
+// straight from global memory into a private [w0*JC | JC (frame tc) | 0] buffer and gathers its columns from there
+// (a0_row[k] = offset into that buffer).  ~7 KB of shared memory per CTA instead of 50 KB (no receptive-field limit, the
+// SM's L1 stays available for the embedder weights), no block-wide phase barrier, rows claimed dynamically so the warp
+// that also computes the camera embedding does not hold the CTA back.
+__global__ void __launch_bounds__(256) prologue_rows_kernel(const PrologueDev* __restrict__ dp, int precision,
+                                                            const float* __restrict__ src, int64_t src_batch_stride,
+                                                            int src_is_uv, const float* __restrict__ cam_or_param,
+                                                            int64_t param_stride, int batch, int flip_from) {
+  extern __shared__ double smem_d[];
+  const PrologueDev& d = *dp;
+  const int b = blockIdx.x;
+  const bool flip = b >= flip_from;                      // mirrored copy of window b - flip_from (trainer.py:299-302)
+  const int bs = flip ? b - flip_from : b;
+  const int J = d.J, JC = d.JC, Cin = d.Cin, w0 = d.w0, kf = w0 * JC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int WB = (kf + JC + 1 + 3) & ~3;                 // per-warp buffer: [w0 frames | frame tc | zero word], padded
+  double* cst = smem_d;                                  // fx, fy, cx, cy, 1/fx, 1/fy, sin(pitch), cos(pitch)
+  int* next_row = reinterpret_cast<int*>(smem_d + 8);
+  float* wbuf = reinterpret_cast<float*>(smem_d + 10) + warp * WB;
+  float* scratch = reinterpret_cast<float*>(smem_d + 10) + nwarp * WB;   // [2][emb_mid] embedder hidden layers
+
+  if (warp == 0) {
+    if (src_is_uv) {   // camera.py:438-439,471 in float64 (every lane computes, lane 0 publishes)
+      const float* cam = cam_or_param + (int64_t)bs * param_stride;
+      const double fx = cam[0], fy = cam[1];
+      double sp, cp;
+      sincos((double)cam[4], &sp, &cp);
+      if (lane == 0) {
+        cst[0] = fx; cst[1] = fy; cst[2] = cam[2]; cst[3] = cam[3];
+        cst[4] = __ddiv_rn(1.0, fx); cst[5] = __ddiv_rn(1.0, fy); cst[6] = sp; cst[7] = cp;
+      }
+    }
+    if (lane == 0) *next_row = 0;
+  }
+  __syncthreads();
+  const double fx = cst[0], fy = cst[1], cx = cst[2], cy = cst[3], rfx = cst[4], rfy = cst[5], sp = cst[6], cp = cst[7];
+  const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
+  const float* x = src + (int64_t)bs * src_batch_stride;
+
+  // keypoint `kp` (frame-major index inside the window) -> 3 ray components at dst (float64 math, rounded once)
+  auto encode = [&](float2 p, float* dst) {
+    const double xn = div_by(__dsub_rn((double)p.x, cx), fx, rfx);
+    const double yn = div_by(__dsub_rn((double)p.y, cy), fy, rfy);
+    dst[0] = flip ? -(float)xn : (float)xn;
+    dst[1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
+    dst[2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
+  };
+  // frames [f0, f0 + nf) of the window -> dst[nf * JC]
+  auto stage_frames = [&](int f0, int nf, float* dst) {
+    if (src_is_uv) {
+      const int nk = nf * J;
+      for (int k0 = lane; k0 < nk; k0 += 64) {            // two independent loads in flight per lane
+        const int k1 = k0 + 32;
+        const int j0 = k0 % J, j1 = k1 % J;
+        const float2 p0 = __ldg(uv + f0 * J + (flip ? k0 - j0 + d.flip_perm[j0] : k0));
+        float2 p1 = make_float2(0.f, 0.f);
+        if (k1 < nk) p1 = __ldg(uv + f0 * J + (flip ? k1 - j1 + d.flip_perm[j1] : k1));
+        encode(p0, dst + k0 * 3);
+        if (k1 < nk) encode(p1, dst + k1 * 3);
+      }
+    } else if (!flip) {
+      for (int i = lane; i < nf * JC; i += 32) dst[i] = __ldg(x + f0 * JC + i);
+    } else {
+      for (int i = lane; i < nf * JC; i += 32) {
+        const int c = i % Cin, jj = (i / Cin) % J;
+        const float v = __ldg(x + f0 * JC + i + (d.flip_perm[jj] - jj) * Cin);
+        dst[i] = c == 0 ? -v : v;
+      }
+    }
+  };
+
+  stage_frames(d.tc, 1, wbuf + kf);                      // frame tc: every warp keeps its own copy
+  if (lane == 0) wbuf[kf + JC] = 0.f;
+  __syncwarp();
+  if (warp == 0)                                          // in_current (rie.py:290-292), zero padded to the row pitch
+    for (int i = lane; i < d.inc.ld; i += 32) store_act(d.inc, precision, b, i, i < JC ? wbuf[kf + i] : 0.f);
+
+  // ---- camera embedding (embedding.py:15-19) by the last warp, before it joins the row loop -------------------------
+  if (warp == nwarp - 1 && d.n_embed > 0) {
+    const int mid = d.emb_mid, ne = d.n_embed;
+    float prm[8];
+    if (src_is_uv) {   // param = [height, pitch] (trainer.py:297)
+      const float* cam = cam_or_param + (int64_t)bs * param_stride;
+      prm[0] = cam[5];
+      prm[1] = cam[4];
+    } else {
+      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)bs * param_stride + i];
+    }
+    for (int t = lane; t < ne * mid; t += 32) {
+      const EmbedDev& em = d.embed[t / mid];
+      const int j = t % mid;
+      float acc = em.b1[j];
+      for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(em.w1[j * d.ext_dim + i], prm[i], acc);
+      scratch[t] = acc > 0.f ? acc : 0.01f * acc;
+    }
+    __syncwarp();
+    for (int t = lane; t < ne * d.emb_dim; t += 32) {
+      const int e = t / d.emb_dim, j = t % d.emb_dim;
+      const EmbedDev& em = d.embed[e];
+      const float* w = em.w2 + j * mid;
+      const float* h = scratch + e * mid;
+      float acc = em.b2[j];
+      int i = 0;
+      for (; i + 8 <= mid; i += 8) {
+        float wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + i + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(wv[u], h[i + u], acc);     // same summation order as prologue_kernel
+      }
+      for (; i < mid; ++i) acc = fmaf(w[i], h[i], acc);
+      acc = acc > 0.f ? acc : 0.01f * acc;
+      for (int q = 0; q < em.ndst; ++q) store_act(em.dst[q].m, precision, b, em.dst[q].col + j, acc);
+    }
+  }
+
+  // ---- operand rows ------------------------------------------------------------------------------------------------
+  const int kp = d.k_pad;
+  int off[16];
+  if (kp <= 512) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = lane * 2 + g * 64;
+      const int2 e = k < kp ? __ldg(reinterpret_cast<const int2*>(d.a0_row + k)) : make_int2(kf + JC, kf + JC);
+      off[2 * g] = e.x;
+      off[2 * g + 1] = e.y;
+    }
+  }
+  for (;;) {
+    int tq = 0;
+    if (lane == 0) tq = atomicAdd(next_row, 1);
+    tq = __shfl_sync(0xffffffffu, tq, 0);
+    if (tq >= d.L0) break;
+    stage_frames(w0 * tq, w0, wbuf);
+    __syncwarp();
+    const int64_t rb = ((int64_t)b * d.L0 + tq) * d.a0.ld + lane * 2;
+    if (kp <= 512) {
+      if (precision == R3D_PREC_FP32) {
+        float* o = reinterpret_cast<float*>(d.a0.p0) + rb;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (lane * 2 + g * 64 < kp) *reinterpret_cast<float2*>(o + g * 64) = make_float2(wbuf[off[2 * g]], wbuf[off[2 * g + 1]]);
+      } else {
+        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d.a0.p0) + rb;
+        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d.a0.p1) + rb;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (lane * 2 + g * 64 < kp) {
+            const float v0 = wbuf[off[2 * g]], v1 = wbuf[off[2 * g + 1]];
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+            *reinterpret_cast<__nv_bfloat162*>(oh + g * 64) = hi;
+            if (precision == R3D_PREC_BF16X3) {
+              const float2 hf = __bfloat1622float2(hi);
+              *reinterpret_cast<__nv_bfloat162*>(ol + g * 64) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+            }
+          }
+      }
+    } else {
+      for (int kk = lane * 2; kk < kp; kk += 64)
+        store_act2(d.a0, precision, (int64_t)b * d.L0 + tq, kk, wbuf[d.a0_row[kk]], wbuf[d.a0_row[kk + 1]]);
+    }
+    __syncwarp();                                         // the next row overwrites the buffer
+  }
+}
+
 static int g_prologue_smem_cap = 48 * 1024;
 
 cudaError_t prologue_configure(int max_smem_bytes) {
@@ -234,6 +402,23 @@ cudaError_t prologue_configure(int max_smem_bytes) {
 cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const void* src,
                             int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
                             int64_t param_stride, int batch, int flip_from, cudaStream_t s) {
+  // Measured at B=1024, T=243: 64 us against 58 us for the whole-window form (also with 5 or 6 CTAs per SM) -- the stage
+  // is bound by instruction issue, not by occupancy or the phase barrier -- so it is opt-in (R3D_PROLOGUE_ROWS=1).
+  static int rows_form = -1;
+  if (rows_form < 0) {
+    rows_form = 0;
+    if (const char* env = getenv("R3D_PROLOGUE_ROWS")) rows_form = atoi(env) != 0;
+  }
+  if (rows_form && h.Cin * h.J == h.JC && (!src_is_uv || h.Cin == 3)) {
+    const int threads = 256, nwarp = threads / 32;
+    const int wb = ((h.w0 + 1) * h.JC + 1 + 3) & ~3;
+    const size_t smem_rows = 10 * sizeof(double) + (size_t)(nwarp * wb + 2 * h.emb_mid + 8) * sizeof(float);
+    if (smem_rows <= 48 * 1024) {
+      prologue_rows_kernel<<<batch, threads, smem_rows, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
+                                                             src_is_uv, cam_or_param, param_stride, batch, flip_from);
+      return cudaGetLastError();
+    }
+  }
   const size_t smem = (size_t)(h.T * h.JC + 2 * h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
   static int threads = 0;
