@@ -13,6 +13,9 @@
  *   - "_dev" pointers are device pointers on the plan's device; "_host" pointers are host memory.
  *   - forward calls are asynchronous on `stream` (the caller's current stream) and do no host
  *     allocation; the *_host variants copy in/out themselves and synchronise before returning.
+ *   - a plan's activation workspace is single-buffered per lane: forwards that share a lane are ordered one after
+ *     the other ON THE DEVICE (an event recorded after each, waited for by the next), whatever streams they were
+ *     issued on -- mixing r3d_forward_* on several streams with r3d_submit_* is safe, it just does not overlap.
  *   - outputs are always freshly written caller-owned buffers (the reference's callers mutate
  *     the returned tensors in place, lib/train_val/trainer.py:215,340,353).
  */
@@ -31,7 +34,7 @@ extern "C" {
 #define R3D_API
 #endif
 
-#define R3D_ABI_VERSION 1
+#define R3D_ABI_VERSION 2
 #define R3D_MAX_WIDTHS 8
 
 typedef enum {
@@ -126,6 +129,68 @@ R3D_API int r3d_plan_set_profiling(r3d_plan* plan, int enable);
 R3D_API int r3d_plan_launch_times(r3d_plan* plan, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs);
 R3D_API const char* r3d_plan_launch_name(const r3d_plan* plan, int32_t index);
 
+/* --- what a forward reads ----------------------------------------------------------------------------
+ * One descriptor covers every input form the reference's eval loop produces:
+ *   src_kind  R3D_SRC_RAYS  windows of encoded input (B, T, J, Cin) float32 -- what nn.Module.forward receives
+ *                           (rie.py:284-304; T == receptive field)
+ *             R3D_SRC_UV    windows of pixel keypoints (B, T, J, 2) float32; CameraInfoPacket.get_cam_ray_given_uv
+ *                           (lib/camera/camera.py:423-441, 460-471) runs inside the input stage, in float64, rounded to
+ *                           float32 exactly like trainer.py:298.  in_features must be 3.
+ *   window_stride           floats between consecutive windows: T*J*C for materialised windows; J*C for the
+ *                           frames of ONE edge-padded video (F + RF - 1, J, C), whose F sliding windows are then
+ *                           indexed in place -- replaces Trainer.eval_data_prepare (trainer.py:47-58, 323-337)
+ *   cam_kind  R3D_CAM_PARAM (B, extrinsic_dim) float32 = the reference's `param` [height_m, pitch_rad]
+ *                           (trainer.py:297,324); only with R3D_SRC_RAYS; may be NULL when the embedding is off
+ *             R3D_CAM_F32   (B, 6) float32 [fx, fy, cx, cy, pitch_rad, height_m]; sin/cos evaluated on the device
+ *             R3D_CAM_F64   (B, R3D_CAM64_STRIDE) float64 [fx, fy, ppx, ppy, cos(pitch), sin(pitch), pitch, height,
+ *                           k1, k2, p1, p2, k3, undistort (0/1), K02, K12]: the reference's own float64 calibration
+ *                           (camera.py:438-439 divides by float64 K entries; Rc2n from libm cos/sin, :333-338), pp =
+ *                           CameraInfoPacket.pp_cam (camera.py:253-259: the undistorted principal point of a distorted
+ *                           lens), and the 5-coefficient lens model of cv2.undistortPoints around K's own principal
+ *                           point K02, K12 (camera.py:412-421, 435-436)
+ *   cam_stride              elements between camera rows; 0 = one row shared by every window (a video)
+ *   flags     R3D_IN_UNDISTORT  some row has its undistort flag set (selects the kernel variant with the lens model)
+ *             R3D_IN_FLIP_TTA   flip test-time augmentation (trainer.py:299-302, 338-353; needs r3d_plan_set_flip)
+ * Overlapping R3D_SRC_UV windows with a shared camera row are encoded ONCE per frame (not once per window). */
+#define R3D_SRC_RAYS 0
+#define R3D_SRC_UV 1
+#define R3D_CAM_PARAM 0
+#define R3D_CAM_F32 1
+#define R3D_CAM_F64 2
+#define R3D_CAM64_STRIDE 16
+#define R3D_IN_UNDISTORT 1
+#define R3D_IN_FLIP_TTA 2
+
+typedef struct {
+  const float* src;
+  int64_t window_stride;
+  int32_t src_kind;
+  int32_t cam_kind;
+  const void* cam;
+  int64_t cam_stride;
+  int32_t flags;
+  int32_t reserved;
+} r3d_input;
+
+/* Generic forms; every named entry point below is one of these with a fixed descriptor.
+ * r3d_forward       device pointers, asynchronous on `stream`.
+ * r3d_submit/r3d_join  device pointers, on one of the plan's two lanes (see r3d_submit_rays).
+ * r3d_forward_host  host pointers; H2D, kernels, D2H inside the call (see r3d_forward_rays_host).
+ * r3d_submit_host / r3d_wait  the streaming form of it (see r3d_submit_rays_host). */
+R3D_API int r3d_forward(r3d_plan* plan, const r3d_input* in_dev, float* pos_dev, float* trj_dev, float* sum_dev,
+                        int32_t n_windows, void* stream);
+R3D_API int r3d_submit(r3d_plan* plan, const r3d_input* in_dev, float* pos_dev, float* trj_dev, float* sum_dev,
+                       int32_t n_windows, void* stream, uint64_t* ticket);
+R3D_API int r3d_forward_host(r3d_plan* plan, const r3d_input* in_host, float* pos_host, float* trj_host,
+                             float* sum_host, int32_t n_windows);
+R3D_API int r3d_submit_host(r3d_plan* plan, const r3d_input* in_host, float* pos_host, float* trj_host, float* sum_host,
+                            int32_t n_windows, uint64_t* ticket);
+
+/* Result-neutral tuning: "graph_max_batch" (CUDA-graph replay for batches <= n, default 64, 0 off), "lanes" (1 or 2,
+ * default 2), "side_stream" (0/1, default 1), "host_chunk" (windows per staged chunk of a host-buffer call, 0 = auto),
+ * "bottom_fusion" (0/1, default 1: first layer + first tree level as one kernel). */
+R3D_API int r3d_plan_set_option(r3d_plan* plan, const char* name, int32_t value);
+
 /* --- forward: replaces nn.Module.forward(x, param) ------------------------------------------------
  * x_dev     (B, T, J, Cin) float32 contiguous, T == receptive field (rie.py:284-304; the reference
  *           only works for T == RF).
@@ -144,6 +209,10 @@ R3D_API int r3d_forward_rays(r3d_plan* plan, const float* x_dev, const float* pa
  * The encode runs in float64 and rounds to float32 exactly like trainer.py:298. in_features must be 3. */
 R3D_API int r3d_forward_uv(r3d_plan* plan, const float* uv_dev, const float* cam_dev, float* pos_dev,
                    float* trj_dev, float* sum_dev, int32_t batch, void* stream);
+/* Same with the reference's float64 calibration rows (R3D_CAM_F64, see r3d_input) and, when `undistort` != 0, the lens
+ * undistortion of CameraInfoPacket.encode_uv_with_intrinsic (camera.py:435-436) inside the input stage. */
+R3D_API int r3d_forward_uv_cam64(r3d_plan* plan, const float* uv_dev, const double* cam64_dev, int32_t undistort,
+                                 float* pos_dev, float* trj_dev, float* sum_dev, int32_t batch, void* stream);
 
 /* Host-buffer variants (the end-to-end call: H2D of inputs, forward, D2H of results, chunked and
  * double-buffered on internal streams; returns after the results are in host memory).
@@ -185,6 +254,16 @@ R3D_API int r3d_join(r3d_plan* plan, uint64_t ticket, void* stream);
  * param_dev (extrinsic_dim) float32 shared by all windows; outputs have F rows. */
 R3D_API int r3d_forward_video(r3d_plan* plan, const float* seq_dev, const float* param_dev, float* pos_dev,
                       float* trj_dev, float* sum_dev, int32_t frames_out, void* stream);
+/* The whole inner step of Trainer.evaluate_core for one video, from pixels (trainer.py:297-353): uv_seq
+ * (F + RF - 1, J, 2) float32 pixel keypoints of the edge-padded video, ONE R3D_CAM_F64 row; every frame is ray-encoded
+ * once, windows are indexed in place.  flags: R3D_IN_UNDISTORT | R3D_IN_FLIP_TTA.  The _host forms take host pointers
+ * (136 bytes per frame cross PCIe instead of RF x 136 per window) and return / complete with results in host memory. */
+R3D_API int r3d_forward_video_uv(r3d_plan* plan, const float* uv_seq_dev, const double* cam64_row_dev, int32_t flags,
+                                 float* pos_dev, float* trj_dev, float* sum_dev, int32_t frames_out, void* stream);
+R3D_API int r3d_forward_video_uv_host(r3d_plan* plan, const float* uv_seq_host, const double* cam64_row_host, int32_t flags,
+                                      float* pos_host, float* trj_host, float* sum_host, int32_t frames_out);
+R3D_API int r3d_submit_video_uv_host(r3d_plan* plan, const float* uv_seq_host, const double* cam64_row_host, int32_t flags,
+                                     float* pos_host, float* trj_host, float* sum_host, int32_t frames_out, uint64_t* ticket);
 
 /* --- test-time flip augmentation: Trainer.evaluate_core with flip_test=True (trainer.py:299-302, 338-353) ---------
  * r3d_plan_set_flip: in_perm[j] = source joint of input joint j in the mirrored copy (the kps_left/kps_right swap of
@@ -232,11 +311,6 @@ R3D_API int r3d_eval_metrics(const float* pred_dev, const float* target_dev, int
  * the FP32 FFMA GEMM on seeded data).  Returns max |tc - ffma| / max|ffma| in *rel_err. */
 R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
                       double* rel_err, double* ms_tc, double* ms_ffma);
-
-/* Diagnostics: out == NULL arms a per-tile SM-clock trace for the tensor-core GEMM launch `arm_after_launches` launches
- * from now; out != NULL synchronises the device and copies the last trace ([3 roles: TMA producer, MMA thread, first
- * epilogue warp][64 tiles][8 events] clock64 stamps of CTA 0).  Used by scripts/tile_trace.py only. */
-R3D_API int r3d_debug_tc_trace(int32_t arm_after_launches, int64_t* out, int32_t cap);
 
 #ifdef __cplusplus
 }

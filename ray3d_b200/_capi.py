@@ -71,8 +71,31 @@ EXPORTS = {
     "r3d_normalize_screen_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "r3d_eval_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_selftest_gemm": (C.c_int, [C.c_int32] * 6 + [C.POINTER(C.c_double)] * 3),
+    "r3d_forward": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p]),
+    "r3d_submit": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "r3d_forward_host": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 3 + [C.c_int32]),
+    "r3d_submit_host": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 3 + [C.c_int32, C.POINTER(C.c_uint64)]),
+    "r3d_plan_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "r3d_forward_uv_cam64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p]),
+    "r3d_forward_video_uv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p]),
+    "r3d_forward_video_uv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32]),
+    "r3d_submit_video_uv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.POINTER(C.c_uint64)]),
+}
+# only in trace builds (R3D_BUILD_TRACE=1): scripts/tile_trace.py
+OPTIONAL_EXPORTS = {
     "r3d_debug_tc_trace": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.c_int32]),
 }
+
+SRC_RAYS, SRC_UV = 0, 1
+CAM_PARAM, CAM_F32, CAM_F64 = 0, 1, 2
+CAM64_STRIDE = 16
+IN_UNDISTORT, IN_FLIP_TTA = 1, 2
+
+
+class R3DInput(C.Structure):
+    """Mirror of r3d_input (include/ray3d_b200.h)."""
+    _fields_ = [("src", C.c_void_p), ("window_stride", C.c_int64), ("src_kind", C.c_int32), ("cam_kind", C.c_int32),
+                ("cam", C.c_void_p), ("cam_stride", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class R3DError(RuntimeError):
@@ -101,7 +124,12 @@ def lib():
                 fn = getattr(handle, name)     # AttributeError if the .so does not export it
                 fn.restype = res
                 fn.argtypes = args
-            if handle.r3d_abi_version() != 1:
+            for name, (res, args) in OPTIONAL_EXPORTS.items():
+                fn = getattr(handle, name, None)
+                if fn is not None:
+                    fn.restype = res
+                    fn.argtypes = args
+            if handle.r3d_abi_version() != 2:
                 raise RuntimeError("libray3d_b200.so ABI version mismatch; rebuild it")
             _lib = handle
     return _lib
@@ -227,6 +255,43 @@ class Plan:
 
     def forward_uv(self, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> None:
         check(lib().r3d_forward_uv(self._h, uv_ptr, cam_ptr, pos_ptr, trj_ptr, sum_ptr, batch, stream))
+
+    def set_option(self, name: str, value: int) -> None:
+        check(lib().r3d_plan_set_option(self._h, name.encode(), int(value)))
+
+    @staticmethod
+    def make_input(src_ptr, window_stride: int, src_kind: int, cam_ptr, cam_kind: int, cam_stride: int, flags: int = 0) -> R3DInput:
+        return R3DInput(src_ptr, window_stride, src_kind, cam_kind, cam_ptr, cam_stride, flags, 0)
+
+    def forward(self, inp: R3DInput, pos_ptr, trj_ptr, sum_ptr, n_windows: int, stream: int) -> None:
+        check(lib().r3d_forward(self._h, C.byref(inp), pos_ptr, trj_ptr, sum_ptr, n_windows, stream))
+
+    def forward_host(self, inp: R3DInput, pos_ptr, trj_ptr, sum_ptr, n_windows: int) -> None:
+        check(lib().r3d_forward_host(self._h, C.byref(inp), pos_ptr, trj_ptr, sum_ptr, n_windows))
+
+    def submit_host(self, inp: R3DInput, pos_ptr, trj_ptr, sum_ptr, n_windows: int) -> int:
+        t = C.c_uint64()
+        check(lib().r3d_submit_host(self._h, C.byref(inp), pos_ptr, trj_ptr, sum_ptr, n_windows, C.byref(t)))
+        return int(t.value)
+
+    def submit(self, inp: R3DInput, pos_ptr, trj_ptr, sum_ptr, n_windows: int, stream: int) -> int:
+        t = C.c_uint64()
+        check(lib().r3d_submit(self._h, C.byref(inp), pos_ptr, trj_ptr, sum_ptr, n_windows, stream, C.byref(t)))
+        return int(t.value)
+
+    def forward_uv_cam64(self, uv_ptr, cam_ptr, undistort: bool, pos_ptr, trj_ptr, sum_ptr, batch: int, stream: int) -> None:
+        check(lib().r3d_forward_uv_cam64(self._h, uv_ptr, cam_ptr, int(bool(undistort)), pos_ptr, trj_ptr, sum_ptr, batch, stream))
+
+    def forward_video_uv(self, uv_ptr, cam_ptr, flags: int, pos_ptr, trj_ptr, sum_ptr, frames_out: int, stream: int) -> None:
+        check(lib().r3d_forward_video_uv(self._h, uv_ptr, cam_ptr, flags, pos_ptr, trj_ptr, sum_ptr, frames_out, stream))
+
+    def forward_video_uv_host(self, uv_ptr, cam_ptr, flags: int, pos_ptr, trj_ptr, sum_ptr, frames_out: int) -> None:
+        check(lib().r3d_forward_video_uv_host(self._h, uv_ptr, cam_ptr, flags, pos_ptr, trj_ptr, sum_ptr, frames_out))
+
+    def submit_video_uv_host(self, uv_ptr, cam_ptr, flags: int, pos_ptr, trj_ptr, sum_ptr, frames_out: int) -> int:
+        t = C.c_uint64()
+        check(lib().r3d_submit_video_uv_host(self._h, uv_ptr, cam_ptr, flags, pos_ptr, trj_ptr, sum_ptr, frames_out, C.byref(t)))
+        return int(t.value)
 
     def forward_video(self, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out: int, stream: int) -> None:
         check(lib().r3d_forward_video(self._h, seq_ptr, param_ptr, pos_ptr, trj_ptr, sum_ptr, frames_out, stream))

@@ -46,7 +46,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            trace = ["-DR3D_TC_TRACE"] if os.environ.get("R3D_BUILD_TRACE") == "1" else []   # per-tile clock stamps (scripts/tile_trace.py)
+            # experiment builds: R3D_BUILD_EXPERIMENTS=1 compiles the timing-experiment switches in (env R3D_TC_DEBUG etc.,
+            # some give wrong results by design); R3D_BUILD_TRACE=1 adds the per-tile clock stamps (scripts/tile_trace.py)
+            trace = ["-DR3D_TC_TRACE", "-DR3D_EXPERIMENTS"] if os.environ.get("R3D_BUILD_TRACE") == "1" else []
+            if os.environ.get("R3D_BUILD_EXPERIMENTS") == "1" and not trace:
+                trace = ["-DR3D_EXPERIMENTS"]
             cmd = [nvcc, *ARCH, *trace, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                    "-Xptxas", "-v" if verbose else "-warn-spills", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                    "-x", "cu", "-c", s, "-o", o]

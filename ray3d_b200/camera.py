@@ -94,11 +94,20 @@ class RayCamera:
         return np.array([self.height, self.cam_pitch_rad], dtype=np.float32)
 
     def table_row(self) -> np.ndarray:
-        """[fx, fy, cx, cy, pitch, height] row for Lifter.forward_uv (pinhole cameras: a distorted lens goes through
-        get_cam_ray_given_uv + forward_rays, the order the reference's dataset code uses)."""
+        """float32 [fx, fy, cx, cy, pitch, height] row for Lifter.forward_uv (pinhole cameras whose calibration is
+        float32-exact; real calibration doubles and distorted lenses go through table_row64)."""
         if self.undistort:
-            raise ValueError("forward_uv has no lens model: use get_cam_ray_given_uv() and Lifter.forward_rays for undistort=True")
+            raise ValueError("the float32 camera row has no lens model: use table_row64() for undistort=True")
         return np.array([self.K[0, 0], self.K[1, 1], self.K[0, 2], self.K[1, 2], self.cam_pitch_rad, self.height], dtype=np.float32)
+
+    def table_row64(self) -> np.ndarray:
+        """R3D_CAM_F64 row (include/ray3d_b200.h): the float64 intrinsics the reference divides by (camera.py:438-439),
+        pp_cam (camera.py:253-259), cos/sin of the pitch from libm exactly as Rc2n holds them (camera.py:333-338),
+        [pitch, height] for the embedding (trainer.py:297), the 5 distortion coefficients and K's own principal point."""
+        d = self.dist_coeff if (self.undistort and self.dist_coeff is not None) else np.zeros(5)
+        return np.array([self.K[0, 0], self.K[1, 1], self.pp_cam[0, 0], self.pp_cam[0, 1], math.cos(self.cam_pitch_rad),
+                         math.sin(self.cam_pitch_rad), self.cam_pitch_rad, self.height, d[0], d[1], d[2], d[3], d[4],
+                         1.0 if self.undistort else 0.0, self.K[0, 2], self.K[1, 2]], dtype=np.float64)
 
     def _undistort_host(self, u: float, v: float) -> np.ndarray:
         """One point through the same arithmetic as the device kernel (python floats are IEEE doubles, no FMA):

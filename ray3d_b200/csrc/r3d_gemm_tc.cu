@@ -22,245 +22,26 @@
 //   warps 4..11  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and chunk), bias + LeakyReLU + residual in registers,
 //                re-split to bf16 hi/lo, 64B-swizzled staging tiles in shared memory
 // so the epilogue of tile i overlaps the main loop of tile i+1.  FUSED: see gemm_tc_kernel below.
-#include <cuda.h>
-
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
-#include "r3d_internal.h"
+#include "r3d_tc_common.cuh"
 
 namespace r3d {
 
-constexpr int TBM = 128;            // UMMA M (one TMEM lane per output row)
-constexpr int TBK = 64;             // K block: 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 384;            // 4 control warps + 8 epilogue warps
 constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 256;   // keeps the staging tiles 1024-byte aligned
 // barriers, descriptor, per-warp hi/lo store staging tiles (double buffered in 2-SM mode, where the W half-tiles leave room)
-__host__ __device__ constexpr int tc_aux_bytes(int cl, int ew = 8) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + (cl == 2 ? ew * 512 : 0); }
-constexpr int SMEM_LIMIT = 227 * 1024;
+__host__ __device__ constexpr int tc_aux_bytes(int cl) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + (cl == 2 ? EPI_WARPS * 512 : 0); }
 
 // per-CTA bytes of one K block: A tile (128 rows) + this CTA's share of the W tile (all of it, or half in 2-SM mode)
 __host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit, int cl = 1) { return nsplit * (TBM + block_n / cl) * TBK * 2; }
-__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1, int ew = 8) {
-  int s = (SMEM_LIMIT - tc_aux_bytes(cl, ew)) / tc_stage_bytes(block_n, nsplit, cl);
+__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1) {
+  int s = (SMEM_LIMIT - tc_aux_bytes(cl)) / tc_stage_bytes(block_n, nsplit, cl);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
   int c = 2 * block_n;
   return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
-}
-
-// ---- PTX wrappers ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("r3d gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-// L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // activations: streamed once
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // weights: re-read by every tile of the problem
-constexpr uint64_t kEvictNormal = 0x1000000000000000ull;  // activations the epilogue reads again as the residual
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask,
-                                               uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], "
-      "[%2], %5, %6;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
-               : "memory");
-}
-// TMA store of one swizzled smem box; completion tracked per thread with bulk groups
-__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_3d_hint(const void* tmap, const void* smem_src, int c0, int c1, int c2, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
-                   reinterpret_cast<uint64_t>(tmap)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void tmap_prefetch(const void* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-// ---- 2-SM (cta_group::2) forms: one MMA spans the CTA pair (M = 256), issued by the leader CTA only ----------------
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-// A operand from tensor memory (TS mode): lane = row, two bf16 per 32-bit column, 8 columns per K=16 step
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// TMA load whose completion is signalled on the LEADER CTA's barrier (peer bit of the cluster address cleared)
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], "
-      "%5;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
-// Arrive on a barrier of CTA `rank` of the cluster.  These arrivals only hand tensor-memory columns back and forth
-// (the tcgen05.wait / tcgen05.fence pair around them orders those accesses), no shared/global data is published, so
-// the arrive is .relaxed: the .release.cluster form costs a MEMBAR.ALL.CTA + ERRBAR per arrival, which ncu showed as
-// 17% of all stall samples of the first-layer launch (22% of the epilogue warps' time).
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank, bool release = false) {
-  if (release)
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-        "r"(rank)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-        "r"(rank)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzled operand tile ([rows][64] bf16, 8-row groups 1024 bytes apart):
-// start address >> 4 | LBO (ignored for swizzled K-major; canonical value 1) | SBO = 1024 >> 4 |
-// descriptor version 1 (sm_100) | layout type 2 = SWIZZLE_128B        (cute/arch/mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t make_idesc(int n, int m = TBM) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct TileCoord {
@@ -339,8 +120,6 @@ __device__ __forceinline__ void residual_consume(uint4* stg, const ResidualRegs&
   }
 }
 
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_WARP0 = 4;
 
 // Diagnostics (R3D_TC_DEBUG bit 32 / r3d_debug_tc_trace): CTA 0 records SM clock stamps per tile for its producer (role 0),
 // MMA thread (role 1) and first epilogue warp (role 2): [role][tile index < 64][event < 8].
@@ -359,19 +138,16 @@ constexpr bool kTraceBuilt = false;
 // hi/lo IN PLACE in tensor memory (each 32-column fp32 chunk becomes 16 hi + 16 lo packed columns), acc2 = Y*W2^T with
 // the A operand read from tensor memory (TS-mode tcgen05.mma), then the usual epilogue on acc2.  TMEM: columns
 // [0,256) acc1/Y, [256,512) acc2.  Needs BLOCK_N == 256 == channels.
-// EW: epilogue warps, 8 or 16.  The 16-warp form (640 threads, <= 102 registers) is for launches whose tiles are short in K
-// and therefore bound by the epilogue (the first layer): four warps per TMEM lane quarter, each converting 64 of the 256
-// columns, twice the latency-hiding of the 8-warp form; it has no residual path and one staging set per column group.
-template <int BLOCK_N, int NSPLIT, int CL, bool FUSED, int EW = 8>
-__global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
+template <int BLOCK_N, int NSPLIT, int CL, bool FUSED>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
                                                                    int M, int total_tiles, int dbg) {
-  static_assert(EW == 8 || (EW == 16 && !FUSED && CL == 2 && BLOCK_N == 256), "16 epilogue warps: plain 2-SM 256-column tiles only");
-  constexpr int NTHREADS = 128 + 32 * EW;
+  constexpr int NTHREADS = TC_THREADS;
+  constexpr int EW = EPI_WARPS;
   // CL == 2: the CTA pair works as one 256-row tile with cta_group::2 MMAs; each CTA stages its own 128 A rows and
   // HALF of the W tile (the tensor cores read the other half from the peer's shared memory), which cuts the bytes
   // every SM has to receive per MMA by a third -- the measured limiter (~74 GB/s per SM from L2) -- and buys a third
   // pipeline stage.
-  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL, EW);
+  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL);
   constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = (BLOCK_N / CL) * TBK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT, CL);
   constexpr int TMEM_COLS = tc_tmem_cols(BLOCK_N);
@@ -415,7 +191,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
   constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA stages
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   const bool leader = crank == 0;
-  const bool trace = kTraceBuilt && (dbg & 32) && blockIdx.x == 0 && lane == 0;
+  const bool trace = kTraceBuilt && R3D_DBG(32) && blockIdx.x == 0 && lane == 0;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its own setup early
   {   // descriptor -> shared memory (read hundreds of times per tile by the epilogue)
@@ -464,31 +240,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // Optional L2 prefetch cursor (R3D_TC_DEBUG bit 8): runs PF_DIST K blocks ahead of the loads across tile
-      // boundaries.  Kept for experiments only: on B200 it raised DRAM reads by ~60% (evictions before use) and
-      // slowed the step by 6%, the 2-3 stage ring plus TMA's own latency tolerance is enough.
-      constexpr int PF_DIST = 6;
-      int pf_tile = unit0, pf_kb = 0, pf_nkb = 0, pf_m0 = 0, pf_p = 0, pf_ahead = 0;
-      if (pf_tile < total_tiles) {
-        const TileCoord t0 = decode_tile(op, pf_tile, per_m, BLOCK_N, CL, crank, total_tiles);
-        pf_p = t0.p; pf_m0 = t0.m0; pf_nkb = op.prob[t0.p].K / TBK;
-      }
-      auto prefetch_step = [&]() {
-        if (pf_tile >= total_tiles) return;
-        const CUtensorMap* tm = tmaps + pf_p * kTmapsPerProb;
-        tma_prefetch_2d(tm + 0, pf_kb * TBK, pf_m0);
-        if (NSPLIT == 2) tma_prefetch_2d(tm + 1, pf_kb * TBK, pf_m0);
-        if (++pf_kb == pf_nkb) {
-          pf_kb = 0;
-          pf_tile += unit_step;
-          if (pf_tile < total_tiles) {
-            const TileCoord t1 = decode_tile(op, pf_tile, per_m, BLOCK_N, CL, crank, total_tiles);
-            pf_p = t1.p; pf_m0 = t1.m0; pf_nkb = op.prob[t1.p].K / TBK;
-          }
-        }
-      };
       int ti = 0;
-      bool shared_a = op.nprob > 1 && !(dbg & 1024);
+      bool shared_a = op.nprob > 1 && !R3D_DBG(1024);
       for (int p = 1; p < op.nprob; ++p) shared_a = shared_a && op.prob[p].a.p0 == op.prob[0].a.p0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
@@ -498,14 +251,14 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
         // activations are streamed once (evict first) -- unless every problem of the launch reads the SAME operand (the
         // first layer): then it must survive in L2 from one problem's tile to the next while the output stream passes by
         // ... or the problem has several column tiles (the FC layers): each of them reads the operand again
-        const uint64_t a_hint = shared_a ? kEvictLast : ((op.prob[tc.p].n_pad > BLOCK_N && !(dbg & 8192)) ? kEvictNormal : kEvictFirst);
+        const uint64_t a_hint = shared_a ? kEvictLast : ((op.prob[tc.p].n_pad > BLOCK_N && !R3D_DBG(8192)) ? kEvictNormal : kEvictFirst);
         // the residual of a strided conv is the middle tap of its own operand (rie.py:94): those K blocks are read again
         // by the epilogue ~one tile later -> keep them out of the evict-first class so the second read hits L2
         const GemmProb& pp = op.prob[tc.p];
-        const bool res_in_a = pp.res.p0 != nullptr && pp.res.p0 == pp.a.p0 && !(dbg & 4096);
+        const bool res_in_a = pp.res.p0 != nullptr && pp.res.p0 == pp.a.p0 && !R3D_DBG(4096);
         const int res_k0 = pp.res_col, res_k1 = pp.res_col + pp.n_pad;
         R3D_TRACE(0, ti, 0);
-        if ((dbg & 256) && tile + unit_step < total_tiles) {     // experiment: next tile's load descriptors -> descriptor cache
+        if (R3D_DBG(256) && tile + unit_step < total_tiles) {     // experiment: next tile's load descriptors -> descriptor cache
           const TileCoord tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
           const CUtensorMap* nm = tmaps + tn.p * kTmapsPerProb;
           tmap_prefetch(nm + 0); tmap_prefetch(nm + 1);
@@ -513,10 +266,6 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
         }
         for (int kb = 0; kb < nkb; ++kb) {
           if (((kmask >> (kb * (TBK / UMMA_K))) & 0xFull) == 0) continue;      // K block without weights: never staged
-          if (dbg & 8) {   // measured on B200: the extra L2 prefetch stream costs more DRAM traffic than it hides -> off
-            while (pf_ahead < PF_DIST + 1) { prefetch_step(); ++pf_ahead; }
-            --pf_ahead;
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           const uint64_t a_hint_kb = (res_in_a && kb * TBK < res_k1 && (kb + 1) * TBK > res_k0) ? kEvictNormal : a_hint;
@@ -682,8 +431,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
     // plane moves all of it (4x fewer store instructions), and the epilogue warps convert the next chunk meanwhile.
     // Protocol per (column half, staging set): the four warps fill their slices, fence, arrive on sready (count 4);
     // this thread issues the stores, commits, and arrives on sfree once the store engine has read the set.
-    constexpr int EPI_BUFS = (CL == 2 && EW == 8) ? 2 : 1;
-    constexpr int GPS = COL_SPLIT > 2 ? COL_SPLIT / 2 : 1;      // column groups per store thread (2 with 16 epilogue warps)
+    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;
+    constexpr int GPS = COL_SPLIT > 2 ? COL_SPLIT / 2 : 1;      // column groups per store thread (1 with 8 epilogue warps)
     const int st = warp - 2;
     if (CH == 32 && lane == 0 && st >= 0 && st * GPS < COL_SPLIT) {
       uint32_t round = 0;                                       // staged chunks per group so far (the client warps count the same)
@@ -696,7 +445,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
         const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
         bool any_bf = false;
         for (int t = 0; t < pr.ndst; ++t) any_bf |= pr.dst[t].f32 == 0;
-        if (!any_bf || (dbg & 4)) continue;
+        if (!any_bf || R3D_DBG(4)) continue;
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
           const int b = EPI_BUFS == 2 ? (int)(round & 1) : 0;
           const uint32_t uses = EPI_BUFS == 2 ? round >> 1 : round;
@@ -704,7 +453,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
           for (int gi = 0; gi < GPS; ++gi) {
             const int grp = st * GPS + gi;
             const int n = tc.n0 + chunk_index(grp, cc) * CH;
-            if (n >= pr.N) continue;                            // (16-warp launches have N == BLOCK_N: never taken there)
+            if (n >= pr.N) continue;
             any = true;
             mbar_wait(&sready_bar[grp * 2 + b], uses & 1);
             if (strace3 && gi == 0 && cc < 4) R3D_TRACE(3, ti, 2 * cc);
@@ -712,14 +461,14 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
             // async proxy: ONE proxy fence here, on the causality path between the writes and the tensor stores, instead
             // of one per writing warp (the fence drains the SM's shared-memory pipe: 32 of them per tile serialised the
             // whole epilogue at ~250 cycles each)
-            if (!(dbg & 512)) fence_async_smem();
-            if (!(dbg & 1)) {
+            if (!R3D_DBG(512)) fence_async_smem();
+            if (!R3D_DBG(1)) {
               const uint4* tile_hi = stage_s + (grp * EPI_BUFS + b) * 1024;
-              const int srow = (dbg & 16) ? 0 : tc.m0;                     // experiment: keep every store in the same L2-resident rows
+              const int srow = R3D_DBG(16) ? 0 : tc.m0;                     // experiment: keep every store in the same L2-resident rows
               for (int t = 0; t < pr.ndst; ++t) {
                 const Dst& d = pr.dst[t];
                 if (d.f32) continue;
-                if (NSPLIT == 2 && (dbg & 2048)) tma_store_3d_hint(dmaps + 2 * t, tile_hi, d.col + n, srow, 0, 0x12F0000000000000ull);   // experiment: evict-first output stream
+                if (NSPLIT == 2 && R3D_DBG(2048)) tma_store_3d_hint(dmaps + 2 * t, tile_hi, d.col + n, srow, 0, 0x12F0000000000000ull);   // experiment: evict-first output stream
                 else if (NSPLIT == 2) tma_store_3d(dmaps + 2 * t, tile_hi, d.col + n, srow, 0);    // both planes, one store
                 else tma_store_2d(dmaps + 2 * t, tile_hi, d.col + n, srow);
               }
@@ -749,7 +498,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
     const int half = ew >> 2;                                 // column group (half of the columns with 8 epilogue warps)
     const bool active = half < COL_SPLIT;
-    constexpr int EPI_BUFS = (CL == 2 && EW == 8) ? 2 : 1;    // staging tile sets per column group (hi + lo each)
+    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;    // staging tile sets per column group (hi + lo each)
     // staging: [column group][set][plane] tiles of 128 rows x 64 B (64B-swizzled): the smem image of a (32 columns, 128 rows,
     // 2 planes) box, so ONE 3-D TMA store writes both planes; this warp owns rows [32 q, 32 q + 32)
     uint4* const stage_base = stage_s + half * EPI_BUFS * 1024;
@@ -780,7 +529,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
     uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
     for (int p = 0; p < op.nprob; ++p) {
       const GemmProb& g = op.prob[p];
-      uint32_t f = (g.res.p0 != nullptr && !(dbg & 2)) ? 8u : 0u;
+      uint32_t f = (g.res.p0 != nullptr && !R3D_DBG(2)) ? 8u : 0u;
       for (int t = 0; t < g.ndst; ++t) {
         f |= g.dst[t].f32 != 0 ? 1u : 2u;
         if (g.dst[t].f32 == 0 && g.dst[t].m.p1 != nullptr) f |= 4u;
@@ -801,14 +550,14 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
         tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
         if (BIAS_SMEM && active) prefetch_bias(tn);
       };
-      const bool ttrace = etrace && (dbg & 128);                 // stamps of the per-tile preamble
+      const bool ttrace = etrace && R3D_DBG(128);                 // stamps of the per-tile preamble
       if (ttrace) R3D_TRACE(2, ti, 1);
       const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
       const int m_base = tc.m0 + q * 32;
       const int row = m_base + lane;
       const bool row_ok = row < M;
       const uint32_t pf = pflags >> (4 * tc.p);
-      const bool any_f32 = pf & 1u, any_bf = pf & 2u, any_lo = pf & 4u, has_res = EW == 8 && (pf & 8u);
+      const bool any_f32 = pf & 1u, any_bf = pf & 2u, any_lo = pf & 4u, has_res = pf & 8u;
       if (ttrace) R3D_TRACE(2, ti, 2);
       const __nv_bfloat16* res_hi = reinterpret_cast<const __nv_bfloat16*>(pr.res.p0);
       const __nv_bfloat16* res_lo = reinterpret_cast<const __nv_bfloat16*>(pr.res.p1);
@@ -907,7 +656,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
             }
           }
           tmem_ld_wait();
-          const bool strace = etrace && (dbg & 64) && !(dbg & 128) && cc == 1;     // sub-step stamps of one steady-state chunk
+          const bool strace = etrace && R3D_DBG(64) && !R3D_DBG(128) && cc == 1;     // sub-step stamps of one steady-state chunk
           if (strace) R3D_TRACE(2, ti, 3);
           float v[32];
 #pragma unroll
@@ -919,7 +668,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
             if (CH == 32) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r); else tmem_ld16(taddr0 + chunk_index(half, cc + 1) * CH, r);
           }
           if (cc > 0) look_ahead();              // not in chunk 0: the store thread is waiting for that one
-          if (n < pr.N && !(dbg & 4)) {          // warp-uniform
+          if (n < pr.N && !R3D_DBG(4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
             const int sbuf = EPI_BUFS == 2 ? (int)(sround & 1) : 0;
@@ -969,7 +718,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
                 stage_write(stage_hi, hi, lane);
                 if (any_lo) stage_write(stage_lo, lo, lane);
                 if (strace) R3D_TRACE(2, ti, 5);
-                if (dbg & 512) fence_async_smem();     // experiment: per-writer fences (the previous scheme)
+                if (R3D_DBG(512)) fence_async_smem();     // experiment: per-writer fences (the previous scheme)
                 __syncwarp();
                 if (strace) R3D_TRACE(2, ti, 6);
                 if (lane == 0) mbar_arrive(&sready_bar[half * 2 + sbuf]);    // the store thread takes it from here
@@ -991,14 +740,14 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_tc_kernel(const GemmOpD
               }
             }
           }
-          if (etrace && !(dbg & (64 | 128)) && cc < 4) R3D_TRACE(2, ti, 3 + cc);
+          if (etrace && !R3D_DBG(64 | 128) && cc < 4) R3D_TRACE(2, ti, 3 + cc);
           if (ttrace && cc == 0) R3D_TRACE(2, ti, 6);
           if (strace) R3D_TRACE(2, ti, 7);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (etrace && !(dbg & 64)) R3D_TRACE(2, ti, 7);       // (dbg & 128: stamp 7 = tile done as well)
+      if (etrace && !R3D_DBG(64)) R3D_TRACE(2, ti, 7);       // (bit 128: stamp 7 = tile done as well)
       if (lane == 0) {
         if (CL == 1) mbar_arrive(&tempty_bar[fb]);
         else mbar_arrive_cluster(&tempty_bar[fb], 0, (op.flags & 2) != 0);         // the MMA thread lives in the leader CTA
@@ -1069,12 +818,14 @@ static int encode_planes_3d(CUtensorMap* out, const void* hi, const void* lo, ui
 }
 
 static int tc_block_n(const GemmOpDev& h) {
+#ifdef R3D_EXPERIMENTS
   if (const char* env = getenv("R3D_TC_NTILE")) {     // experiments: force a narrower tile when it divides every problem
     const int bn = atoi(env);
     bool ok = bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256;
     for (int p = 0; ok && p < h.nprob; ++p) ok = h.prob[p].n_pad % bn == 0;
     if (ok && bn <= h.n_tile) return bn;
   }
+#endif
   return h.n_tile;
 }
 
@@ -1134,8 +885,6 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
 
 template <int BN, int NS, int CL = 1>
 static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_stage_bytes(BN, NS, CL) + tc_aux_bytes(CL); }
-template <int NS>
-static constexpr int tc_smem_bytes_ew16() { return tc_num_stages(256, NS, 2, 16) * tc_stage_bytes(256, NS, 2) + tc_aux_bytes(2, 16); }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
@@ -1149,22 +898,14 @@ static cudaError_t configure_one() {
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 1>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<256, NS, 2, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes_ew16<NS>());
   }
   return e;
 }
 
 static int g_num_sms = 0;
-// R3D_TC_DEBUG bit mask (timing experiments only; results are wrong with bits 1/2/4/16): 1 skip the TMA stores, 2 skip the
-// residual, 4 skip the epilogue's staging and stores, 8 L2 prefetch cursor, 16 fold all stores onto the same rows,
-// 32 (set by r3d_debug_tc_trace) per-tile clock stamps, 64 / 128 stamp one chunk's sub-steps / the per-tile preamble
-// instead, 256 prefetch the next tile's tensor maps, 512 per-writer proxy fences, 1024 shared operand evict-first,
-// 2048 evict-first hint on the output stores, 4096 residual K blocks evict-first, 8192 FC operands evict-first
-static int g_dbg = 0;
-static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs (R3D_TC_PDL env)
-static int g_cluster_mode = 1;   // 0: never use 2-CTA clusters; 1: whenever the op has >= 2 m tiles (R3D_TC_CLUSTER env)
-static int g_epi16 = 0;          // 16-epilogue-warp form for short-K launches (R3D_TC_EPI16=1); measured: no gain, the store path limits them
+static int g_dbg = 0;            // R3D_EXPERIMENTS builds only (see R3D_DBG): bit mask of timing experiments, R3D_TC_DEBUG env
+static int g_pdl = 1;            // programmatic dependent launch between consecutive GEMMs
+static int g_cluster_mode = 1;   // 2-SM tiles (CTA pairs, cta_group::2) whenever the op has >= 2 m tiles
 static int g_trace_arm = -1;     // >= 0: the launch that many GEMM launches from now records the per-tile clock trace
 
 void tc_trace_arm(int launches_from_now) { g_trace_arm = launches_from_now; }
@@ -1183,15 +924,24 @@ cudaError_t tc_configure() {
   if ((e = configure_one<BN, 2>()) != cudaSuccess) return e;
   R3D_CFG(16) R3D_CFG(32) R3D_CFG(64) R3D_CFG(128) R3D_CFG(256)
 #undef R3D_CFG
+#ifdef R3D_EXPERIMENTS
+  // R3D_TC_DEBUG bit mask (results are wrong with bits 1/2/4/16): 1 skip the TMA stores, 2 skip the residual, 4 skip the
+  // epilogue's staging and stores, 16 fold all stores onto the same rows, 32 per-tile clock stamps, 64 / 128 stamp one
+  // chunk's sub-steps / the per-tile preamble instead, 256 prefetch the next tile's tensor maps, 512 per-writer proxy
+  // fences, 1024 shared operand evict-first, 2048 evict-first hint on the output stores, 4096 residual K blocks
+  // evict-first, 8192 FC operands evict-first
   if (const char* env = getenv("R3D_TC_CLUSTER")) g_cluster_mode = atoi(env);
   if (const char* env = getenv("R3D_TC_PDL")) g_pdl = atoi(env);
-  if (const char* env = getenv("R3D_TC_EPI16")) g_epi16 = atoi(env);
   if (const char* env = getenv("R3D_TC_DEBUG")) g_dbg = atoi(env);
+#endif
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   return cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
+int tc_num_sms() { return g_num_sms; }
+int tc_debug_mask() { return g_dbg; }
+int tc_use_pdl() { return g_pdl; }
 
 template <int BN, int NS>
 static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps, int M, const GemmOpDev& h, cudaStream_t s) {
@@ -1233,21 +983,6 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   cfg.attrs = attr;
   cfg.numAttrs = na;
   if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, dbg);
-  if (BN == 256 && g_epi16) {
-    // Epilogue-bound launch?  Few K steps per tile (the masked first layer: <= 16 of them) against a full 256-column
-    // epilogue, many tiles per CTA, no residual, whole 256-column outputs: run it with 16 epilogue warps.
-    bool wide = clusters == max_clusters && units >= 4 * clusters;
-    for (int p = 0; p < h.nprob && wide; ++p) {
-      const GemmProb& g = h.prob[p];
-      const int steps = g.kmask ? __builtin_popcountll(g.kmask) : g.K / UMMA_K;
-      wide = g.res.p0 == nullptr && g.N == 256 && g.n_pad == 256 && steps <= 16;
-    }
-    if (wide) {
-      cfg.blockDim = dim3(128 + 32 * 16);
-      cfg.dynamicSmemBytes = tc_smem_bytes_ew16<NS>();
-      return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, false, 16>, d_op, d_tmaps, M, units, dbg);
-    }
-  }
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2, false>, d_op, d_tmaps, M, units, dbg);
 }
 

@@ -84,8 +84,6 @@ struct PrologueDev {
   int32_t T, J, Cin, JC, tc, w0, L0;
   int32_t k_pad;         // row pitch of a0
   Mat a0;                // first-layer operand shared by all problems: [B*L0][k_pad], columns per a0_map
-  const int32_t* a0_row; // [k_pad] source of every operand column as an offset into [w0 frames | frame tc | zero word]
-                         // (the row-wise input stage's per-warp buffer)
   const int32_t* a0_off; // [k_pad] decoded source of every operand column (r3d_plan.cpp:build_a0_layout): offset into the
                          // window staged in shared memory, | 1 << 30 when relative to the row's first frame; padding
                          // columns point at a zero word
@@ -106,9 +104,25 @@ struct AssembleDev {
 };
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------------------
-cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h_desc, int precision, const void* src,
-                            int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
-                            int64_t param_stride, int batch, int flip_from, cudaStream_t s);
+// What one forward reads: windows of encoded rays or of pixel keypoints, plus one camera/param row per window (stride 0:
+// one row shared by all windows).  Pointers are device pointers by the time a kernel sees them.
+struct InputSpec {
+  const float* src;
+  int64_t src_stride;     // floats between consecutive windows: T*J*C for materialised windows, J*C for a video
+  int32_t src_kind;       // R3D_SRC_RAYS / R3D_SRC_UV
+  int32_t cam_kind;       // R3D_CAM_PARAM / R3D_CAM_F32 / R3D_CAM_F64
+  const void* cam;
+  int64_t cam_stride;     // elements (float or double) between rows
+  int32_t undistort;      // host-side knowledge: some R3D_CAM_F64 row has its undistort flag set
+  int32_t _pad;
+};
+inline int64_t cam_row_elems(int cam_kind, int ext_dim) { return cam_kind == R3D_CAM_F64 ? R3D_CAM64_STRIDE : cam_kind == R3D_CAM_F32 ? 6 : ext_dim; }
+inline int64_t cam_elem_bytes(int cam_kind) { return cam_kind == R3D_CAM_F64 ? 8 : 4; }
+
+cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h_desc, int precision, const InputSpec& in, int batch,
+                            int flip_from, cudaStream_t s);
+cudaError_t launch_video_encode(const float* uv, float* rays, float* param, int64_t n_points, const void* cam, int cam_kind,
+                                int undistort, cudaStream_t s);
 cudaError_t launch_assemble(const AssembleDev* d_desc, const AssembleDev& h_desc, float* pos, float* trj, float* sum,
                             int batch, int flip, cudaStream_t s);
 cudaError_t launch_gemm_ffma(const GemmOpDev* d_op, const GemmOpDev& h_op, int M, cudaStream_t s);

@@ -41,6 +41,36 @@ static int fail(int code, const char* fmt, ...) {
                                        __FILE__, __LINE__);                                         \
   } while (0)
 
+// Experiment switches are read from the environment only in builds made with -DR3D_EXPERIMENTS; the shipped library
+// takes its (few, result-neutral) tuning options through r3d_plan_set_option.
+static const char* exp_env(const char* name) {
+#ifdef R3D_EXPERIMENTS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
+// Selects the plan's device for the duration of a call and restores the caller's on every exit path.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 extern "C" R3D_API const char* r3d_last_error(void) { return g_err.c_str(); }
 extern "C" R3D_API int r3d_abi_version(void) { return R3D_ABI_VERSION; }
 
@@ -180,10 +210,14 @@ struct r3d_plan {
   uint64_t slot_seq = 0;                     // staging-slot uses so far (alternates the two slots across calls)
   char* d_stage = nullptr;
   size_t stage_bytes = 0;
+  int host_chunk = 0;                        // windows per chunk of a host-buffer call (0: 512 blocking / 1024 streamed)
+  char* d_vid = nullptr;                     // per lane: [param row | ray-encoded frames] of the video being evaluated
+  size_t vid_bytes = 0;
+  cudaEvent_t ev_ws = nullptr;               // per lane: recorded after the last forward that used this lane's buffers
   // small batches are launch-latency bound (~20 launches, 2 streams): their launch sequence is captured once into a
   // CUDA graph per (batch, input kind, output set) and replayed with one cudaGraphLaunch
   struct GraphEntry {
-    int batch = 0, is_uv = 0, mask = 0;
+    int batch = 0, mask = 0;
     int64_t src_stride = 0, prm_stride = 0;
     cudaGraphExec_t exec = nullptr;
     char* buf = nullptr;                         // static input/output buffers the captured kernels point at
@@ -545,11 +579,11 @@ static void build_graph(r3d_plan* p) {
   // tensor-core precisions with 256 channels: the k=w conv and the 1x1 conv of a level run as ONE launch whose
   // intermediate stays in tensor memory (gemm_tc_kernel FUSED); otherwise two launches through the Y scratch.
   bool fuse_pairs = p->cfg.precision != R3D_PREC_FP32 && C == 256;
-  if (const char* env = getenv("R3D_TC_FUSE")) fuse_pairs = fuse_pairs && atoi(env) != 0;
+  if (const char* env = exp_env("R3D_TC_FUSE")) fuse_pairs = fuse_pairs && atoi(env) != 0;
   // Levels with few rows per window (the top of the tree) are one-wave launches: a fused tile there serialises
   // GEMM -> convert -> GEMM -> store on a fraction of the SMs, while two narrow-tile launches spread over all of them.
   int fuse_min_rows = 3;
-  if (const char* env = getenv("R3D_TC_FUSE_MIN_ROWS")) fuse_min_rows = atoi(env);
+  if (const char* env = exp_env("R3D_TC_FUSE_MIN_ROWS")) fuse_min_rows = atoi(env);
   std::vector<char> lvl_fused(nl, 0);
   int y_len = 0;
   for (int i = 1; i < nl; ++i) {
@@ -881,6 +915,10 @@ static void free_device(r3d_plan* p) {
   if (p->d_ws) cudaFree(p->d_ws);
   if (p->d_desc) cudaFree(p->d_desc);
   if (p->d_stage) cudaFree(p->d_stage);
+  if (p->d_vid) cudaFree(p->d_vid);
+  p->d_vid = nullptr; p->vid_bytes = 0;
+  if (p->ev_ws) cudaEventDestroy(p->ev_ws);
+  p->ev_ws = nullptr;
   for (int i = 0; i < r3d_plan::kSlots; ++i) {
     if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
     if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
@@ -916,7 +954,7 @@ extern "C" R3D_API void r3d_plan_destroy(r3d_plan* p) {
 
 static int create_side_stream(r3d_plan* p) {
   int prio = 0;
-  if (const char* env = getenv("R3D_SIDE_PRIO")) prio = atoi(env);
+  if (const char* env = exp_env("R3D_SIDE_PRIO")) prio = atoi(env);
   int lo = 0, hi = 0;
   CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least urgent (numerically largest)
   CUDA_TRY(cudaStreamCreateWithPriority(&p->s_side, cudaStreamNonBlocking, prio > 0 ? lo : prio < 0 ? hi : 0));
@@ -937,7 +975,8 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   std::lock_guard<std::mutex> lk(*p->mu);
   free_device(p);
   p->device = device;
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard dg(device);                  // the caller's current device is restored on every exit path
+  CUDA_TRY(dg.err);
   CUDA_TRY(cudaMalloc(&p->d_weights, p->weight_bytes));
   std::vector<char> slab(p->weight_bytes, 0);
   const int prec = p->cfg.precision;
@@ -962,8 +1001,8 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
   {   // experiment knobs: R3D_SIDE_STREAM=0 serialises the GlobalInfo chain; R3D_SIDE_PRIO=-1/0/1 sets its stream priority
-    if (const char* env = getenv("R3D_SIDE_STREAM")) p->use_side_stream = atoi(env) != 0;
-    if (const char* env = getenv("R3D_GRAPH_MAX_BATCH")) p->graph_max_batch = std::max(0, atoi(env));
+    if (const char* env = exp_env("R3D_SIDE_STREAM")) p->use_side_stream = atoi(env) != 0;
+    if (const char* env = exp_env("R3D_GRAPH_MAX_BATCH")) p->graph_max_batch = std::max(0, atoi(env));
     const int rc = create_side_stream(p);
     if (rc) return rc;
   }
@@ -976,7 +1015,8 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   for (int i = 0; i < r3d_plan::kTicketRing; ++i)
     for (int l = 0; l < 2; ++l) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_ticket[i][l], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&p->ev_sub, cudaEventDisableTiming));
-  if (const char* env = getenv("R3D_LANES")) p->use_lanes = atoi(env) >= 2;
+  CUDA_TRY(cudaEventCreateWithFlags(&p->ev_ws, cudaEventDisableTiming));
+  if (const char* env = exp_env("R3D_LANES")) p->use_lanes = atoi(env) >= 2;
   p->uploaded = true;
   return R3D_OK;
 }
@@ -997,7 +1037,8 @@ static int get_lane(r3d_plan* p, int lane, r3d_plan** out) {
     t->graphs.clear(); t->graph_max_batch = 0; t->graph_launches = 0;
     t->prof_ev.clear(); t->prof_runs = 0; t->profiling = false;
     t->s_copy = t->s_comp = t->s_side = nullptr;
-    t->ev_fork = t->ev_join = t->ev_sub = nullptr;
+    t->ev_fork = t->ev_join = t->ev_sub = t->ev_ws = nullptr;
+    t->d_vid = nullptr; t->vid_bytes = 0;
     for (int i = 0; i < r3d_plan::kSlots; ++i) t->ev_in[i] = t->ev_done[i] = nullptr;
     for (int i = 0; i < r3d_plan::kTicketRing; ++i) t->ev_ticket[i][0] = t->ev_ticket[i][1] = nullptr;
     CUDA_TRY(cudaStreamCreateWithFlags(&t->s_comp, cudaStreamNonBlocking));
@@ -1005,6 +1046,7 @@ static int get_lane(r3d_plan* p, int lane, r3d_plan** out) {
     if (rc) return rc;
     CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&t->ev_ws, cudaEventDisableTiming));
     p->twin = t.release();
   }
   *out = p->twin;
@@ -1062,7 +1104,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
       g.res_col = b.res_col;
       g.K = l.k_pad; g.N = l.n; g.n_pad = l.n_pad;
       g.kmask = l.kmask;                           // K steps whose weights are all zero are never loaded or multiplied
-      if (const char* env = getenv("R3D_TC_KMASK")) if (atoi(env) == 0) g.kmask = 0;
+      if (const char* env = exp_env("R3D_TC_KMASK")) if (atoi(env) == 0) g.kmask = 0;
       g.ndst = dsts(b.dst, b.dst_f32, g.dst);
       ntile = std::min(ntile, pick_n_tile(l.n_pad));
       if (!b.layer2.empty()) {
@@ -1078,7 +1120,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
     // (upper tree levels, FC chains) then occupy a fraction of the 148 SMs.  Minimise waves x (tile cost) with a
     // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
     bool tile_heuristic = true;
-    if (const char* env = getenv("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
+    if (const char* env = exp_env("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
     if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
       const int64_t m_tiles = ((int64_t)cap * op.dev.rows_per_seq + 127) / 128;
       auto cost = [&](int bn) {
@@ -1100,9 +1142,9 @@ static int bind_workspace(r3d_plan* p, int cap) {
       op.dev.reverse = (i % 2 == 0) ? 1 : 0;
       ++i;
     }
-    if (const char* env = getenv("R3D_TC_YSPLIT")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.flags |= 1;
-    if (const char* env = getenv("R3D_TC_RELEASE_ARRIVE")) if (atoi(env) != 0) for (auto& op : p->ops) op.dev.flags |= 2;
-    if (const char* env = getenv("R3D_TC_REVERSE")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.reverse = 0;
+    if (const char* env = exp_env("R3D_TC_YSPLIT")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.flags |= 1;
+    if (const char* env = exp_env("R3D_TC_RELEASE_ARRIVE")) if (atoi(env) != 0) for (auto& op : p->ops) op.dev.flags |= 2;
+    if (const char* env = exp_env("R3D_TC_REVERSE")) if (atoi(env) == 0) for (auto& op : p->ops) op.dev.reverse = 0;
   }
   // prologue
   PrologueDev& pd = p->pro;
@@ -1110,7 +1152,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
   pd.T = p->T; pd.J = p->J; pd.Cin = p->Cin; pd.JC = p->JC; pd.tc = p->tc; pd.w0 = p->widths[0]; pd.L0 = p->lens[0];
   pd.a0 = mat(p->m_a0[0], 0);
   pd.k_pad = p->mats[p->m_a0[0]].ld;
-  pd.a0_off = pd.a0_row = nullptr;               // patched below once the descriptor slab's address is known
+  pd.a0_off = nullptr;                           // patched below once the descriptor slab's address is known
   for (int j = 0; j < 32; ++j) pd.flip_perm[j] = (int8_t)(j < (int)p->flip_in.size() ? p->flip_in[j] : j);
   pd.inc = mat(p->m_inc, 0);
   pd.n_embed = (int)p->emb_binds.size(); pd.ext_dim = p->ext; pd.emb_mid = p->embed ? kEmbedMid : 0; pd.emb_dim = p->E;
@@ -1143,10 +1185,8 @@ static int bind_workspace(r3d_plan* p, int cap) {
   p->off_asm = take(sizeof(AssembleDev));
   p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
   const size_t off_map = take(p->a0_src.size() * sizeof(int32_t));
-  const size_t off_map_row = take(p->a0_src.size() * sizeof(int32_t));
   CUDA_TRY(cudaMalloc(&p->d_desc, off));
   pd.a0_off = reinterpret_cast<const int32_t*>(p->d_desc + off_map);
-  pd.a0_row = reinterpret_cast<const int32_t*>(p->d_desc + off_map_row);
   std::vector<char> h(off, 0);
   {   // a0_src (index into [w0 frames | frame tc]) -> offset into the staged window, row-relative flag in bit 30
     const int k_frames = p->widths[0] * p->JC;
@@ -1154,7 +1194,6 @@ static int bind_workspace(r3d_plan* p, int cap) {
       const int sidx = p->a0_src[k];
       reinterpret_cast<int32_t*>(h.data() + off_map)[k] =
           sidx < 0 ? p->T * p->JC : (sidx < k_frames ? (sidx | (1 << 30)) : sidx - k_frames + p->tc * p->JC);
-      reinterpret_cast<int32_t*>(h.data() + off_map_row)[k] = sidx < 0 ? k_frames + p->JC : sidx;
     }
   }
   for (size_t i = 0; i < nops; ++i) memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
@@ -1182,9 +1221,23 @@ static int ensure_capacity(r3d_plan* p, int batch) {
 static constexpr int kMaxChunk = 8192;
 static constexpr int kProfRing = 64;
 
+static int64_t window_floats(const r3d_plan* p, int src_kind) {
+  return src_kind == R3D_SRC_UV ? (int64_t)p->T * p->J * 2 : (int64_t)p->T * p->JC;
+}
+// floats / camera-row elements spanned by `n` consecutive windows (windows of a video overlap: stride < window length)
+static int64_t src_span(const r3d_plan* p, const InputSpec& in, int64_t n) { return n <= 0 ? 0 : (n - 1) * in.src_stride + window_floats(p, in.src_kind); }
+static int64_t cam_span(const r3d_plan* p, const InputSpec& in, int64_t n) {
+  return (n <= 0 || in.cam == nullptr) ? 0 : (n - 1) * in.cam_stride + cam_row_elems(in.cam_kind, p->ext);
+}
+static InputSpec advance(const InputSpec& in, int64_t b0) {
+  InputSpec o = in;
+  o.src = in.src + b0 * in.src_stride;
+  if (in.cam) o.cam = reinterpret_cast<const char*>(in.cam) + b0 * in.cam_stride * cam_elem_bytes(in.cam_kind);
+  return o;
+}
+
 // `batch` windows are read; with tta the launch graph runs on 2*batch windows (direct + mirrored copies)
-static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                     float* pos, float* trj, float* sum, int batch_in, cudaStream_t s, bool tta = false) {
+static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, float* sum, int batch_in, cudaStream_t s, bool tta = false) {
   const int batch = tta ? 2 * batch_in : batch_in;
   const int prec = p->cfg.precision;
   const int nl = (int)p->ops.size() + 2, nev = 2 * nl;      // start/end event per launch
@@ -1198,8 +1251,7 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
     ++p->prof_runs;
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
-  CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, src, src_stride,
-                           is_uv, prm, prm_stride, batch, tta ? batch_in : batch, s));
+  CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, in, batch, tta ? batch_in : batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
   // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
   // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.
@@ -1245,45 +1297,92 @@ static int run_chunk(r3d_plan* p, const float* src, int64_t src_stride, int is_u
   return R3D_OK;
 }
 
-static int check_forward(r3d_plan* p, const void* src, float* pos, float* trj, float* sum, int batch) {
+// r3d_input -> InputSpec, with the argument checks every entry point shares (mirrors the asserts at rie.py:285-287)
+static int make_input(r3d_plan* p, const r3d_input* in, float* pos, float* trj, float* sum, int batch, InputSpec* out, bool* tta) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "forward: null plan");
-  if (!src && batch != 0) return fail(R3D_ERR_BAD_ARG, "forward: null input");
+  if (!in) return fail(R3D_ERR_BAD_ARG, "forward: null input descriptor");
   if (!p->uploaded) return fail(R3D_ERR_STATE, "forward before r3d_plan_upload");
   if (batch < 0) return fail(R3D_ERR_BAD_ARG, "batch=%d", batch);
+  if (!in->src && batch != 0) return fail(R3D_ERR_BAD_ARG, "forward: null input");
   if ((pos || sum) && !p->has_pos) return fail(R3D_ERR_BAD_ARG, "plan has no pose net but pos/sum output requested");
   if (trj && !p->has_trj) return fail(R3D_ERR_BAD_ARG, "plan has no trajectory net but trj output requested");
   if (sum && !p->has_trj) return fail(R3D_ERR_BAD_ARG, "sum output needs both nets");
+  if (in->window_stride <= 0) return fail(R3D_ERR_BAD_ARG, "window_stride=%lld must be positive", (long long)in->window_stride);
+  if (in->cam_stride < 0) return fail(R3D_ERR_BAD_ARG, "cam_stride=%lld", (long long)in->cam_stride);
+  if (in->flags & ~(R3D_IN_UNDISTORT | R3D_IN_FLIP_TTA)) return fail(R3D_ERR_BAD_ARG, "unknown input flags 0x%x", in->flags);
+  InputSpec s{};
+  s.src = in->src; s.src_stride = in->window_stride; s.src_kind = in->src_kind;
+  s.cam = in->cam; s.cam_stride = in->cam_stride; s.cam_kind = in->cam_kind;
+  s.undistort = (in->flags & R3D_IN_UNDISTORT) ? 1 : 0;
+  if (in->src_kind == R3D_SRC_UV) {
+    if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "pixel-keypoint input needs in_features == 3 (ray encoding, utils.py:91-96)");
+    if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "pixel-keypoint input derives param=[height,pitch]: extrinsic_dim must be 2");
+    if (in->cam_kind != R3D_CAM_F32 && in->cam_kind != R3D_CAM_F64) return fail(R3D_ERR_BAD_ARG, "pixel-keypoint input needs R3D_CAM_F32 or R3D_CAM_F64 camera rows");
+    if (!in->cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
+    if (s.undistort && in->cam_kind != R3D_CAM_F64) return fail(R3D_ERR_BAD_ARG, "R3D_IN_UNDISTORT needs R3D_CAM_F64 rows (they carry the distortion coefficients)");
+  } else if (in->src_kind == R3D_SRC_RAYS) {
+    if (in->cam_kind != R3D_CAM_PARAM) return fail(R3D_ERR_BAD_ARG, "encoded input takes R3D_CAM_PARAM rows");
+    if (s.undistort) return fail(R3D_ERR_BAD_ARG, "R3D_IN_UNDISTORT applies to pixel-keypoint input only");
+    if (p->embed && !in->cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
+    if (!p->embed) s.cam = nullptr;
+  } else {
+    return fail(R3D_ERR_BAD_ARG, "src_kind=%d", in->src_kind);
+  }
+  *tta = (in->flags & R3D_IN_FLIP_TTA) != 0;
+  if (*tta && p->flip_in.empty()) return fail(R3D_ERR_STATE, "flip augmentation requested before r3d_plan_set_flip");
+  *out = s;
+  return R3D_OK;
+}
+
+// Overlapping pixel-keypoint windows that share one camera row are the frames of ONE video (trainer.py:47-58, :323-324):
+// every frame is ray-encoded once into the lane's scratch and the windows are indexed there by the input stage, instead
+// of each window re-encoding its RF frames.  Rewrites `in` to the encoded form.  Caller holds the lane's mutex / device.
+static int encode_video_once(r3d_plan* p, InputSpec& in, int batch, cudaStream_t s) {
+  const int64_t frame = (int64_t)p->J * 2;
+  if (in.src_kind != R3D_SRC_UV || in.cam_stride != 0 || batch < 2 || in.src_stride >= window_floats(p, R3D_SRC_UV) || in.src_stride % frame) return R3D_OK;
+  const int64_t step = in.src_stride / frame, frames = (int64_t)(batch - 1) * step + p->T;
+  const size_t need = 256 + (size_t)frames * p->JC * 4;
+  if (p->vid_bytes < need) {
+    if (p->d_vid) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(p->d_vid)); p->d_vid = nullptr; p->vid_bytes = 0; }
+    const size_t cap = need + need / 4;
+    CUDA_TRY(cudaMalloc(&p->d_vid, cap));
+    p->vid_bytes = cap;
+  }
+  float* prm = reinterpret_cast<float*>(p->d_vid);
+  float* rays = reinterpret_cast<float*>(p->d_vid + 256);
+  CUDA_TRY(launch_video_encode(in.src, rays, prm, frames * p->J, in.cam, in.cam_kind, in.undistort, s));
+  in.src = rays; in.src_stride = step * p->JC; in.src_kind = R3D_SRC_RAYS;
+  in.cam = p->embed ? prm : nullptr; in.cam_kind = R3D_CAM_PARAM; in.cam_stride = 0; in.undistort = 0;
   return R3D_OK;
 }
 
 // Small-batch path: replay the captured launch sequence.  Returns 1 when the graph route is not available (the caller
 // then launches directly), R3D_OK / an error code otherwise.  Caller holds p->mu and has selected the device.
-static int forward_graph(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                         float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
-  const int mask = (prm ? 1 : 0) | (pos ? 2 : 0) | (trj ? 4 : 0) | (sum ? 8 : 0);
+static int forward_graph(r3d_plan* p, const InputSpec& in, float* pos, float* trj, float* sum, int batch, cudaStream_t s) {
+  const int mask = (in.cam ? 1 : 0) | (pos ? 2 : 0) | (trj ? 4 : 0) | (sum ? 8 : 0) | (in.src_kind << 4) | (in.cam_kind << 6) | (in.undistort << 8);
   int rc = ensure_capacity(p, batch);           // may rebind the workspace and drop every captured graph
   if (rc) return rc;
   r3d_plan::GraphEntry* g = nullptr;
   for (auto& e : p->graphs)
-    if (e.batch == batch && e.is_uv == is_uv && e.mask == mask && e.src_stride == src_stride && e.prm_stride == prm_stride) g = &e;
+    if (e.batch == batch && e.mask == mask && e.src_stride == in.src_stride && e.prm_stride == in.cam_stride) g = &e;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   // windows may overlap (video: batch stride of one frame) and the parameter row may be shared (stride 0)
-  const int64_t win_len = is_uv ? (int64_t)p->T * p->J * 2 : (int64_t)p->T * p->JC, prm_len = is_uv ? 6 : p->ext;
-  const size_t in_b = (size_t)((batch - 1) * src_stride + win_len) * 4, prm_b = (size_t)((batch - 1) * prm_stride + prm_len) * 4;
+  const size_t in_b = (size_t)src_span(p, in, batch) * 4, prm_b = (size_t)cam_span(p, in, batch) * cam_elem_bytes(in.cam_kind);
   const size_t out_b = (size_t)batch * p->J * 3 * 4, trj_b = (size_t)batch * 3 * 4;
   if (g == nullptr) {
     if (p->graphs.size() >= 16) clear_graphs(p);
     r3d_plan::GraphEntry e;
-    e.batch = batch; e.is_uv = is_uv; e.mask = mask; e.src_stride = src_stride; e.prm_stride = prm_stride;
+    e.batch = batch; e.mask = mask; e.src_stride = in.src_stride; e.prm_stride = in.cam_stride;
     e.off_prm = al(in_b); e.off_pos = e.off_prm + al(prm_b); e.off_sum = e.off_pos + al(out_b); e.off_trj = e.off_sum + al(out_b);
     CUDA_TRY(cudaMalloc(&e.buf, e.off_trj + al(trj_b)));
+    InputSpec gi = in;
+    gi.src = reinterpret_cast<float*>(e.buf);
+    gi.cam = in.cam ? e.buf + e.off_prm : nullptr;
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamBeginCapture(p->s_comp, cudaStreamCaptureModeThreadLocal);
     if (ce == cudaSuccess) {
-      rc = run_chunk(p, reinterpret_cast<float*>(e.buf), src_stride, is_uv, prm ? reinterpret_cast<float*>(e.buf + e.off_prm) : nullptr,
-                     prm_stride, pos ? reinterpret_cast<float*>(e.buf + e.off_pos) : nullptr,
-                     trj ? reinterpret_cast<float*>(e.buf + e.off_trj) : nullptr, sum ? reinterpret_cast<float*>(e.buf + e.off_sum) : nullptr,
-                     batch, p->s_comp);
+      rc = run_chunk(p, gi, pos ? reinterpret_cast<float*>(e.buf + e.off_pos) : nullptr, trj ? reinterpret_cast<float*>(e.buf + e.off_trj) : nullptr,
+                     sum ? reinterpret_cast<float*>(e.buf + e.off_sum) : nullptr, batch, p->s_comp);
       ce = cudaStreamEndCapture(p->s_comp, &graph);          // always ends the capture, also after a failed launch
       if (rc == R3D_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&e.exec, graph, 0);
       if (graph) cudaGraphDestroy(graph);
@@ -1297,8 +1396,8 @@ static int forward_graph(r3d_plan* p, const float* src, int64_t src_stride, int 
     p->graphs.push_back(e);
     g = &p->graphs.back();
   }
-  CUDA_TRY(cudaMemcpyAsync(g->buf, src, in_b, cudaMemcpyDeviceToDevice, s));
-  if (prm) CUDA_TRY(cudaMemcpyAsync(g->buf + g->off_prm, prm, prm_b, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(g->buf, in.src, in_b, cudaMemcpyDeviceToDevice, s));
+  if (in.cam) CUDA_TRY(cudaMemcpyAsync(g->buf + g->off_prm, in.cam, prm_b, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaGraphLaunch(g->exec, s));
   ++p->graph_launches;
   if (pos) CUDA_TRY(cudaMemcpyAsync(pos, g->buf + g->off_pos, out_b, cudaMemcpyDeviceToDevice, s));
@@ -1324,164 +1423,84 @@ static int ticket_issue(r3d_plan* p, int lanes, uint64_t* ticket) {
   return R3D_OK;
 }
 
-static int forward_dev_core(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                            float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta);
+// One forward on the lane `p` (workspace, descriptors, side stream, captured graphs and the video scratch are the
+// lane's), enqueued on stream `s`.  A lane's resources are single-buffered, so whatever stream used them last -- another
+// caller stream, the lane's own compute stream (r3d_submit_*, r3d_*_host) -- is waited for on the device first
+// (ev_ws = "lane last used"); the host never blocks.  Caller holds the lane owner's mutex and has selected the device.
+static int forward_on_lane(r3d_plan* p, InputSpec in, float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta) {
+  int rc = R3D_OK;
+  CUDA_TRY(cudaStreamWaitEvent(s, p->ev_ws, 0));
+  rc = encode_video_once(p, in, batch, s);
+  bool done = false;
+  if (rc == R3D_OK && !tta && !p->profiling && batch <= p->graph_max_batch) {
+    rc = forward_graph(p, in, pos, trj, sum, batch, s);
+    if (rc != 1) done = true; else rc = R3D_OK;
+  }
+  if (!done && rc == R3D_OK) {
+    const int max_in = tta ? kMaxChunk / 2 : kMaxChunk;     // the mirrored copies double the rows in flight
+    rc = ensure_capacity(p, std::min(batch, max_in) * (tta ? 2 : 1));
+    for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += max_in) {
+      const int nb = std::min(max_in, batch - b0);
+      rc = run_chunk(p, advance(in, b0), pos ? pos + (int64_t)b0 * p->J * 3 : nullptr, trj ? trj + (int64_t)b0 * 3 : nullptr,
+                     sum ? sum + (int64_t)b0 * p->J * 3 : nullptr, nb, s, tta);
+    }
+  }
+  CUDA_TRY(cudaEventRecord(p->ev_ws, s));        // (also after a failed enqueue: whatever was launched still uses the lane)
+  return rc;
+}
 
-static int forward_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                       float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta = false) {
-  int rc = check_forward(p, src, pos, trj, sum, batch);
-  if (rc) return rc;
-  if (tta && p->flip_in.empty()) return fail(R3D_ERR_STATE, "flip augmentation requested before r3d_plan_set_flip");
-  if (batch == 0) return R3D_OK;
-  if (p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
+extern "C" R3D_API int r3d_forward(r3d_plan* p, const r3d_input* in, float* pos, float* trj, float* sum, int32_t batch, void* stream) {
+  InputSpec is;
+  bool tta = false;
+  int rc = make_input(p, in, pos, trj, sum, batch, &is, &tta);
+  if (rc || batch == 0) return rc;
   std::lock_guard<std::mutex> lk(*p->mu);
-  return forward_dev_core(p, src, src_stride, is_uv, prm, prm_stride, pos, trj, sum, batch, s, tta);
+  DeviceGuard dg(p->device);
+  CUDA_TRY(dg.err);
+  return forward_on_lane(p, is, pos, trj, sum, batch, (cudaStream_t)stream, tta);
 }
 
 // Asynchronous device-buffer submission: ordered after the work already enqueued on `stream`, executed on one of the
 // plan's two lanes (alternating), completion observed through r3d_join / r3d_wait.  Inputs and outputs must stay valid
 // until then.  Two submissions in flight keep the GPU busy across the under-filled tail launches of each batch.
-static int submit_dev(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                      float* pos, float* trj, float* sum, int batch, cudaStream_t stream, uint64_t* ticket) {
-  int rc = check_forward(p, src, pos, trj, sum, batch);
+extern "C" R3D_API int r3d_submit(r3d_plan* p, const r3d_input* in, float* pos, float* trj, float* sum, int32_t batch, void* stream,
+                                  uint64_t* ticket) {
+  if (!ticket) return fail(R3D_ERR_BAD_ARG, "null ticket");
+  InputSpec is;
+  bool tta = false;
+  int rc = make_input(p, in, pos, trj, sum, batch, &is, &tta);
   if (rc) return rc;
-  if (batch != 0 && p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   std::lock_guard<std::mutex> lk(*p->mu);
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  DeviceGuard dg(p->device);
+  CUDA_TRY(dg.err);
   rc = ticket_slot_reuse(p);
   r3d_plan* lp = p;
   if (rc == R3D_OK) rc = get_lane(p, p->use_lanes ? (int)(p->slot_seq++ & 1) : 0, &lp);
   if (rc == R3D_OK) {
-    CUDA_TRY(cudaEventRecord(p->ev_sub, stream));
+    CUDA_TRY(cudaEventRecord(p->ev_sub, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamWaitEvent(lp->s_comp, p->ev_sub, 0));
-    if (batch > 0) rc = forward_dev_core(lp, src, src_stride, is_uv, prm, prm_stride, pos, trj, sum, batch, lp->s_comp, false);
+    if (batch > 0) rc = forward_on_lane(lp, is, pos, trj, sum, batch, lp->s_comp, tta);
   }
   if (rc == R3D_OK) rc = ticket_issue(p, lp == p ? 1 : 2, ticket);
-  if (dev != p->device) cudaSetDevice(dev);
   return rc;
 }
 
-// caller holds the lane owner's mutex
-static int forward_dev_core(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                            float* pos, float* trj, float* sum, int batch, cudaStream_t s, bool tta) {
-  int rc = R3D_OK;
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
-  if (!tta && !p->profiling && batch <= p->graph_max_batch) {
-    rc = forward_graph(p, src, src_stride, is_uv, prm, prm_stride, pos, trj, sum, batch, s);
-    if (rc != 1) {
-      if (dev != p->device) cudaSetDevice(dev);
-      return rc;
-    }
-  }
-  const int max_in = tta ? kMaxChunk / 2 : kMaxChunk;     // the mirrored copies double the rows in flight
-  rc = ensure_capacity(p, std::min(batch, max_in) * (tta ? 2 : 1));
-  for (int b0 = 0; rc == R3D_OK && b0 < batch; b0 += max_in) {
-    const int nb = std::min(max_in, batch - b0);
-    rc = run_chunk(p, src + (int64_t)b0 * src_stride, src_stride, is_uv, prm ? prm + (int64_t)b0 * prm_stride : nullptr, prm_stride,
-                   pos ? pos + (int64_t)b0 * p->J * 3 : nullptr, trj ? trj + (int64_t)b0 * 3 : nullptr,
-                   sum ? sum + (int64_t)b0 * p->J * 3 : nullptr, nb, s, tta);
-  }
-  if (dev != p->device) cudaSetDevice(dev);
-  return rc;
-}
-
-extern "C" R3D_API int r3d_forward_rays(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
-                                int32_t batch, void* stream) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  return forward_dev(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, (cudaStream_t)stream);
-}
-
-extern "C" R3D_API int r3d_forward_uv(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum,
-                              int32_t batch, void* stream) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv needs in_features == 3 (ray encoding, utils.py:91-96)");
-  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv derives param=[height,pitch]: extrinsic_dim must be 2");
-  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
-  return forward_dev(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, (cudaStream_t)stream);
-}
-
-extern "C" R3D_API int r3d_submit_rays(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
-                                       int32_t batch, void* stream, uint64_t* ticket) {
-  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
-  return submit_dev(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, (cudaStream_t)stream, ticket);
-}
-
-extern "C" R3D_API int r3d_submit_uv(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum,
-                                     int32_t batch, void* stream, uint64_t* ticket) {
-  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
-  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_submit_uv needs in_features == 3 (ray encoding, utils.py:91-96)");
-  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "r3d_submit_uv derives param=[height,pitch]: extrinsic_dim must be 2");
-  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
-  return submit_dev(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, (cudaStream_t)stream, ticket);
-}
-
-extern "C" R3D_API int r3d_forward_video(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
-                                 int32_t frames_out, void* stream) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  // window f = frames [f, f+RF) of the padded video: batch stride of one frame, shared param row
-  return forward_dev(p, seq, (int64_t)p->JC, 0, param, 0, pos, trj, sum, frames_out, (cudaStream_t)stream);
-}
-
-extern "C" R3D_API int r3d_plan_set_flip(r3d_plan* p, const int32_t* in_perm, const int32_t* out_perm) {
-  if (!p || !in_perm || !out_perm) return fail(R3D_ERR_BAD_ARG, "r3d_plan_set_flip: null argument");
-  std::vector<int> a(in_perm, in_perm + p->J), b(out_perm, out_perm + p->J);
-  for (int j = 0; j < p->J; ++j)
-    if (a[j] < 0 || a[j] >= p->J || b[j] < 0 || b[j] >= p->J) return fail(R3D_ERR_BAD_ARG, "flip permutation entry out of range at joint %d", j);
-  std::lock_guard<std::mutex> lk(*p->mu);
-  p->flip_in = a;
-  p->flip_out = b;
-  if (p->twin) {               // the second lane is re-cloned (with the new tables) on its next use
-    cudaDeviceSynchronize();
-    free_device(p->twin);
-    delete p->twin;
-    p->twin = nullptr;
-  }
-  if (p->cap > 0) {            // descriptors already on the device: rebuild them with the new tables
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
-    const int rc = bind_workspace(p, p->cap);
-    if (dev != p->device) cudaSetDevice(dev);
-    return rc;
-  }
-  return R3D_OK;
-}
-
-extern "C" R3D_API int r3d_forward_rays_tta(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
-                                    int32_t batch, void* stream) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  return forward_dev(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, (cudaStream_t)stream, true);
-}
-
-extern "C" R3D_API int r3d_forward_video_tta(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
-                                     int32_t frames_out, void* stream) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  return forward_dev(p, seq, (int64_t)p->JC, 0, param, 0, pos, trj, sum, frames_out, (cudaStream_t)stream, true);
-}
-
-// Host-buffer forward: chunks of the batch flow H2D (copy stream) -> compute stream -> D2H (copy stream)
-// with two staging slots so the PCIe transfer of chunk i+1 overlaps the kernels of chunk i.
+// Host-buffer forward: chunks of the batch flow H2D (copy stream) -> a lane's compute stream -> D2H, through four device
+// staging slots so the PCIe transfer of one chunk overlaps the kernels of the others.
 // ticket == nullptr: synchronous (results are in host memory on return).  Otherwise the copies and launches are only
-// enqueued (two staging slots: the H2D copy of one submission overlaps the kernels of the previous one) and *ticket
-// identifies the submission for r3d_wait.
-static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int is_uv, const float* prm, int64_t prm_stride,
-                        float* pos, float* trj, float* sum, int batch, uint64_t* ticket = nullptr) {
-  int rc = check_forward(p, src, pos, trj, sum, batch);
+// enqueued and *ticket identifies the submission for r3d_wait.
+static int forward_host(r3d_plan* p, const r3d_input* in, float* pos, float* trj, float* sum, int batch, uint64_t* ticket) {
+  InputSpec hs;
+  bool tta = false;
+  int rc = make_input(p, in, pos, trj, sum, batch, &hs, &tta);
   if (rc) return rc;
   if (batch == 0 && ticket == nullptr) return R3D_OK;
-  if (batch != 0 && p->embed && !prm) return fail(R3D_ERR_BAD_ARG, "camera embedding enabled but param/cam pointer is null");
   std::lock_guard<std::mutex> lk(*p->mu);
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev != p->device) CUDA_TRY(cudaSetDevice(p->device));
+  DeviceGuard dg(p->device);
+  CUDA_TRY(dg.err);
   if (batch == 0) {   // empty submission: a ticket that completes with everything enqueued before it (on both lanes)
     rc = ticket_slot_reuse(p);
     if (rc == R3D_OK) rc = ticket_issue(p, p->twin ? 3 : 1, ticket);
-    if (dev != p->device) cudaSetDevice(dev);
     return rc;
   }
   // chunking trades PCIe/compute overlap against per-launch efficiency (small batches under-fill the GPU)
@@ -1489,10 +1508,14 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
   // under-filled launches than they gain in copy/compute overlap (H2D of 1024 windows is 0.6 ms at 55 GB/s)
   // ... for streamed submissions.  A blocking call has nothing else to overlap with, so it splits into 512-window chunks
   // that alternate between the two lanes: the second chunk's copy runs under the first chunk's kernels (+16 %).
-  int parts = std::max(1, batch / (ticket != nullptr ? 1024 : 512));
-  if (const char* env = getenv("R3D_HOST_CHUNKS")) parts = std::max(1, atoi(env));
-  const int chunk = std::min(batch, std::max(64, std::min(kMaxChunk, (batch + parts - 1) / parts)));
-  const size_t in_b = (size_t)chunk * src_stride * 4, prm_b = (size_t)chunk * std::max<int64_t>(prm_stride, 1) * 4;
+  // A video (overlapping windows) ships 136 B per frame: no copy to hide, whole launches win.
+  const bool video = hs.src_stride < window_floats(p, hs.src_kind);
+  int per = p->host_chunk > 0 ? p->host_chunk : ((ticket != nullptr || video) ? 1024 : 512);
+  const int max_in = tta ? kMaxChunk / 2 : kMaxChunk;
+  const int parts = std::max(1, batch / per);
+  const int chunk = std::min(batch, std::max(64, std::min(max_in, (batch + parts - 1) / parts)));
+  const size_t cam_eb = cam_elem_bytes(hs.cam_kind);
+  const size_t in_b = (size_t)src_span(p, hs, chunk) * 4, prm_b = std::max<size_t>((size_t)cam_span(p, hs, chunk) * cam_eb, 8);
   const size_t out_b = (size_t)chunk * p->J * 3 * 4, trj_b = (size_t)chunk * 3 * 4;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t slot = al(in_b) + al(prm_b) + 2 * al(out_b) + al(trj_b);
@@ -1510,23 +1533,28 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
     const int nb = std::min(chunk, batch - b0), sl = (int)(p->slot_seq++ % r3d_plan::kSlots);
     r3d_plan* lp = p;
     rc = get_lane(p, p->use_lanes ? (sl & 1) : 0, &lp);
-    if (rc == R3D_OK) rc = ensure_capacity(lp, chunk);
     if (rc) break;
     lanes_used |= lp == p ? 1 : 2;
     char* base = p->d_stage + (size_t)sl * (p->stage_bytes / r3d_plan::kSlots);   // fixed stride: submissions of other sizes may be in flight
     float* d_in = reinterpret_cast<float*>(base);
-    float* d_prm = reinterpret_cast<float*>(base + al(in_b));
+    char* d_prm = base + al(in_b);
     float* d_pos = reinterpret_cast<float*>(base + al(in_b) + al(prm_b));
     float* d_sum = reinterpret_cast<float*>(base + al(in_b) + al(prm_b) + al(out_b));
     float* d_trj = reinterpret_cast<float*>(base + al(in_b) + al(prm_b) + 2 * al(out_b));
+    const InputSpec hc = advance(hs, b0);
     CUDA_TRY(cudaStreamWaitEvent(p->s_copy, p->ev_done[sl], 0));   // slot's previous results have left (no-op on first use)
-    CUDA_TRY(cudaMemcpyAsync(d_in, src + (int64_t)b0 * src_stride, (size_t)nb * src_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
-    if (prm) CUDA_TRY(cudaMemcpyAsync(d_prm, prm + (int64_t)b0 * prm_stride, (size_t)nb * prm_stride * 4, cudaMemcpyHostToDevice, p->s_copy));
+    CUDA_TRY(cudaMemcpyAsync(d_in, hc.src, (size_t)src_span(p, hc, nb) * 4, cudaMemcpyHostToDevice, p->s_copy));
+    if (hc.cam) CUDA_TRY(cudaMemcpyAsync(d_prm, hc.cam, (size_t)cam_span(p, hc, nb) * cam_eb, cudaMemcpyHostToDevice, p->s_copy));
     CUDA_TRY(cudaEventRecord(p->ev_in[sl], p->s_copy));
     cudaStream_t sc = lp->s_comp;
     CUDA_TRY(cudaStreamWaitEvent(sc, p->ev_in[sl], 0));
-    rc = run_chunk(lp, d_in, src_stride, is_uv, prm ? d_prm : nullptr, prm_stride, pos ? d_pos : nullptr, trj ? d_trj : nullptr,
-                   sum ? d_sum : nullptr, nb, sc);
+    InputSpec dc = hc;
+    dc.src = d_in;
+    dc.cam = hc.cam ? d_prm : nullptr;
+    const int graph_cap = lp->graph_max_batch;       // staged chunks are launched directly (their buffers are static already)
+    lp->graph_max_batch = 0;
+    rc = forward_on_lane(lp, dc, pos ? d_pos : nullptr, trj ? d_trj : nullptr, sum ? d_sum : nullptr, nb, sc, tta);
+    lp->graph_max_batch = graph_cap;
     if (rc) break;
     if (pos) CUDA_TRY(cudaMemcpyAsync(pos + (int64_t)b0 * p->J * 3, d_pos, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, sc));
     if (sum) CUDA_TRY(cudaMemcpyAsync(sum + (int64_t)b0 * p->J * 3, d_sum, (size_t)nb * p->J * 12, cudaMemcpyDeviceToHost, sc));
@@ -1540,23 +1568,148 @@ static int forward_host(r3d_plan* p, const float* src, int64_t src_stride, int i
     if (p->twin) CUDA_TRY(cudaStreamSynchronize(p->twin->s_comp));
     CUDA_TRY(cudaStreamSynchronize(p->s_copy));
   }
-  if (dev != p->device) cudaSetDevice(dev);
   return rc;
+}
+
+extern "C" R3D_API int r3d_forward_host(r3d_plan* p, const r3d_input* in, float* pos, float* trj, float* sum, int32_t batch) {
+  return forward_host(p, in, pos, trj, sum, batch, nullptr);
+}
+extern "C" R3D_API int r3d_submit_host(r3d_plan* p, const r3d_input* in, float* pos, float* trj, float* sum, int32_t batch, uint64_t* ticket) {
+  if (!ticket) return fail(R3D_ERR_BAD_ARG, "null ticket");
+  return forward_host(p, in, pos, trj, sum, batch, ticket);
+}
+
+// ---- named forms of the generic calls (the reference interface each stands in for: include/ray3d_b200.h) -------------
+static r3d_input in_rays(const r3d_plan* p, const float* x, const float* param, int64_t stride, int32_t flags = 0) {
+  r3d_input in{};
+  in.src = x; in.window_stride = stride; in.src_kind = R3D_SRC_RAYS;
+  in.cam = param; in.cam_kind = R3D_CAM_PARAM; in.cam_stride = stride == (int64_t)p->T * p->JC ? p->ext : 0; in.flags = flags;
+  return in;
+}
+static r3d_input in_uv(const r3d_plan* p, const float* uv, const void* cam, int cam_kind, int64_t stride, int32_t flags = 0) {
+  r3d_input in{};
+  in.src = uv; in.window_stride = stride; in.src_kind = R3D_SRC_UV;
+  in.cam = cam; in.cam_kind = cam_kind;
+  in.cam_stride = stride == (int64_t)p->T * p->J * 2 ? (cam_kind == R3D_CAM_F64 ? R3D_CAM64_STRIDE : 6) : 0; in.flags = flags;
+  return in;
+}
+#define R3D_NEED_PLAN(p) do { if (!(p)) return fail(R3D_ERR_BAD_ARG, "null plan"); } while (0)
+
+extern "C" R3D_API int r3d_forward_rays(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
+                                int32_t batch, void* stream) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_rays(p, x, param, (int64_t)p->T * p->JC);
+  return r3d_forward(p, &in, pos, trj, sum, batch, stream);
+}
+extern "C" R3D_API int r3d_forward_uv(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum,
+                              int32_t batch, void* stream) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_uv(p, uv, cam, R3D_CAM_F32, (int64_t)p->T * p->J * 2);
+  return r3d_forward(p, &in, pos, trj, sum, batch, stream);
+}
+extern "C" R3D_API int r3d_forward_uv_cam64(r3d_plan* p, const float* uv, const double* cam64, int32_t undistort, float* pos, float* trj,
+                                            float* sum, int32_t batch, void* stream) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_uv(p, uv, cam64, R3D_CAM_F64, (int64_t)p->T * p->J * 2, undistort ? R3D_IN_UNDISTORT : 0);
+  return r3d_forward(p, &in, pos, trj, sum, batch, stream);
+}
+extern "C" R3D_API int r3d_submit_rays(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
+                                       int32_t batch, void* stream, uint64_t* ticket) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_rays(p, x, param, (int64_t)p->T * p->JC);
+  return r3d_submit(p, &in, pos, trj, sum, batch, stream, ticket);
+}
+extern "C" R3D_API int r3d_submit_uv(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum,
+                                     int32_t batch, void* stream, uint64_t* ticket) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_uv(p, uv, cam, R3D_CAM_F32, (int64_t)p->T * p->J * 2);
+  return r3d_submit(p, &in, pos, trj, sum, batch, stream, ticket);
+}
+extern "C" R3D_API int r3d_forward_video(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
+                                 int32_t frames_out, void* stream) {
+  R3D_NEED_PLAN(p);
+  // window f = frames [f, f+RF) of the padded video: batch stride of one frame, shared param row
+  const r3d_input in = in_rays(p, seq, param, (int64_t)p->JC);
+  return r3d_forward(p, &in, pos, trj, sum, frames_out, stream);
+}
+extern "C" R3D_API int r3d_forward_video_uv(r3d_plan* p, const float* uv_seq, const double* cam64_row, int32_t flags, float* pos, float* trj,
+                                            float* sum, int32_t frames_out, void* stream) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_uv(p, uv_seq, cam64_row, R3D_CAM_F64, (int64_t)p->J * 2, flags);
+  return r3d_forward(p, &in, pos, trj, sum, frames_out, stream);
+}
+extern "C" R3D_API int r3d_forward_video_uv_host(r3d_plan* p, const float* uv_seq, const double* cam64_row, int32_t flags, float* pos, float* trj,
+                                                 float* sum, int32_t frames_out) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_uv(p, uv_seq, cam64_row, R3D_CAM_F64, (int64_t)p->J * 2, flags);
+  return forward_host(p, &in, pos, trj, sum, frames_out, nullptr);
+}
+extern "C" R3D_API int r3d_submit_video_uv_host(r3d_plan* p, const float* uv_seq, const double* cam64_row, int32_t flags, float* pos, float* trj,
+                                                float* sum, int32_t frames_out, uint64_t* ticket) {
+  R3D_NEED_PLAN(p);
+  if (!ticket) return fail(R3D_ERR_BAD_ARG, "null ticket");
+  const r3d_input in = in_uv(p, uv_seq, cam64_row, R3D_CAM_F64, (int64_t)p->J * 2, flags);
+  return forward_host(p, &in, pos, trj, sum, frames_out, ticket);
+}
+
+extern "C" R3D_API int r3d_plan_set_flip(r3d_plan* p, const int32_t* in_perm, const int32_t* out_perm) {
+  if (!p || !in_perm || !out_perm) return fail(R3D_ERR_BAD_ARG, "r3d_plan_set_flip: null argument");
+  std::vector<int> a(in_perm, in_perm + p->J), b(out_perm, out_perm + p->J);
+  for (int j = 0; j < p->J; ++j)
+    if (a[j] < 0 || a[j] >= p->J || b[j] < 0 || b[j] >= p->J) return fail(R3D_ERR_BAD_ARG, "flip permutation entry out of range at joint %d", j);
+  std::lock_guard<std::mutex> lk(*p->mu);
+  p->flip_in = a;
+  p->flip_out = b;
+  if (p->cap > 0 || p->twin) {            // descriptors already on the device: rebuild them with the new tables
+    DeviceGuard dg(p->device);
+    CUDA_TRY(dg.err);
+    if (p->twin) {               // the second lane is re-cloned (with the new tables) on its next use
+      cudaDeviceSynchronize();
+      free_device(p->twin);
+      delete p->twin;
+      p->twin = nullptr;
+    }
+    if (p->cap > 0) return bind_workspace(p, p->cap);
+  }
+  return R3D_OK;
+}
+
+extern "C" R3D_API int r3d_forward_rays_tta(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum,
+                                    int32_t batch, void* stream) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_rays(p, x, param, (int64_t)p->T * p->JC, R3D_IN_FLIP_TTA);
+  return r3d_forward(p, &in, pos, trj, sum, batch, stream);
+}
+extern "C" R3D_API int r3d_forward_video_tta(r3d_plan* p, const float* seq, const float* param, float* pos, float* trj, float* sum,
+                                     int32_t frames_out, void* stream) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_rays(p, seq, param, (int64_t)p->JC, R3D_IN_FLIP_TTA);
+  return r3d_forward(p, &in, pos, trj, sum, frames_out, stream);
 }
 
 extern "C" R3D_API int r3d_submit_rays_host(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum, int32_t batch,
                                             uint64_t* ticket) {
-  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
-  return forward_host(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch, ticket);
+  R3D_NEED_PLAN(p);
+  if (!ticket) return fail(R3D_ERR_BAD_ARG, "null ticket");
+  const r3d_input in = in_rays(p, x, param, (int64_t)p->T * p->JC);
+  return forward_host(p, &in, pos, trj, sum, batch, ticket);
 }
-
 extern "C" R3D_API int r3d_submit_uv_host(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum, int32_t batch,
                                           uint64_t* ticket) {
-  if (!p || !ticket) return fail(R3D_ERR_BAD_ARG, "null plan or ticket");
-  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_submit_uv_host needs in_features == 3");
-  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim must be 2");
-  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
-  return forward_host(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch, ticket);
+  R3D_NEED_PLAN(p);
+  if (!ticket) return fail(R3D_ERR_BAD_ARG, "null ticket");
+  const r3d_input in = in_uv(p, uv, cam, R3D_CAM_F32, (int64_t)p->T * p->J * 2);
+  return forward_host(p, &in, pos, trj, sum, batch, ticket);
+}
+extern "C" R3D_API int r3d_forward_rays_host(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum, int32_t batch) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_rays(p, x, param, (int64_t)p->T * p->JC);
+  return forward_host(p, &in, pos, trj, sum, batch, nullptr);
+}
+extern "C" R3D_API int r3d_forward_uv_host(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum, int32_t batch) {
+  R3D_NEED_PLAN(p);
+  const r3d_input in = in_uv(p, uv, cam, R3D_CAM_F32, (int64_t)p->T * p->J * 2);
+  return forward_host(p, &in, pos, trj, sum, batch, nullptr);
 }
 
 extern "C" R3D_API int r3d_wait(r3d_plan* p, uint64_t ticket) {
@@ -1587,17 +1740,18 @@ extern "C" R3D_API int r3d_join(r3d_plan* p, uint64_t ticket, void* stream) {
   return R3D_OK;
 }
 
-extern "C" R3D_API int r3d_forward_rays_host(r3d_plan* p, const float* x, const float* param, float* pos, float* trj, float* sum, int32_t batch) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  return forward_host(p, x, (int64_t)p->T * p->JC, 0, param, p->ext, pos, trj, sum, batch);
-}
-
-extern "C" R3D_API int r3d_forward_uv_host(r3d_plan* p, const float* uv, const float* cam, float* pos, float* trj, float* sum, int32_t batch) {
-  if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
-  if (p->Cin != 3) return fail(R3D_ERR_UNSUPPORTED, "r3d_forward_uv_host needs in_features == 3");
-  if (p->embed && p->ext != 2) return fail(R3D_ERR_UNSUPPORTED, "extrinsic_dim must be 2");
-  if (!cam && batch != 0) return fail(R3D_ERR_BAD_ARG, "cam is null");
-  return forward_host(p, uv, (int64_t)p->T * p->J * 2, 1, cam, 6, pos, trj, sum, batch);
+// Result-neutral tuning options (everything else is fixed at build time; experiment switches need -DR3D_EXPERIMENTS).
+extern "C" R3D_API int r3d_plan_set_option(r3d_plan* p, const char* name, int32_t value) {
+  if (!p || !name) return fail(R3D_ERR_BAD_ARG, "r3d_plan_set_option: null argument");
+  std::lock_guard<std::mutex> lk(*p->mu);
+  const std::string k(name);
+  auto both = [&](auto&& f) { f(p); if (p->twin) f(p->twin); };
+  if (k == "graph_max_batch") p->graph_max_batch = std::max(0, (int)value);          // lane 0 only: submissions launch directly
+  else if (k == "lanes") p->use_lanes = value >= 2;
+  else if (k == "side_stream") both([&](r3d_plan* q) { q->use_side_stream = value != 0; });
+  else if (k == "host_chunk") p->host_chunk = std::max(0, (int)value);
+  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk)", name);
+  return R3D_OK;
 }
 
 extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
@@ -1667,6 +1821,10 @@ extern "C" R3D_API int r3d_eval_metrics(const float* pred, const float* target, 
 }
 
 // ---- on-device self test: tensor-core GEMM vs FP32 FFMA GEMM -----------------------------------------
+#ifdef R3D_TC_TRACE
+// Diagnostics of trace builds only (R3D_BUILD_TRACE=1 python -m ray3d_b200.build --force; scripts/tile_trace.py): out == NULL
+// arms a per-tile SM-clock trace for the tensor-core GEMM launch `arm_after_launches` launches from now; out != NULL
+// synchronises the device and copies the last trace ([4 roles][64 tiles][8 events] clock64 stamps of CTA 0).
 extern "C" R3D_API int r3d_debug_tc_trace(int32_t arm_after_launches, int64_t* out, int32_t cap) {
   if (out == nullptr) { tc_trace_arm(arm_after_launches); return R3D_OK; }
   static_assert(sizeof(long long) == sizeof(int64_t), "trace word");
@@ -1674,6 +1832,7 @@ extern "C" R3D_API int r3d_debug_tc_trace(int32_t arm_after_launches, int64_t* o
   CUDA_TRY(tc_trace_read(reinterpret_cast<long long*>(out), cap));
   return R3D_OK;
 }
+#endif
 
 extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_t nprob, int32_t precision, int32_t device,
                                  double* rel_err, double* ms_tc, double* ms_ffma) {

@@ -53,11 +53,84 @@ __device__ __forceinline__ double div_by(double a, double b, double rb) {
   return __fma_rn(r, rb, q);
 }
 
+// ---- camera row of one window ---------------------------------------------------------------------------------------
+// R3D_CAM_F32: 6 floats [fx, fy, cx, cy, pitch, height]; sin/cos of the pitch are evaluated on the device.
+// R3D_CAM_F64: 16 doubles [fx, fy, ppx, ppy, cos(pitch), sin(pitch), pitch, height, k1, k2, p1, p2, k3, undistort, K02, K12]
+//   (pp = the principal point the encode subtracts, camera.py:253-259: the UNDISTORTED one for a distorted lens; K02/K12 =
+//   the raw principal point the lens model itself uses):
+//   the reference's own float64 intrinsics (camera.py:438-439 divides by float64 K entries), cos/sin as the host's libm
+//   produced them for Rc2n (camera.py:333-338), and the lens model of cv2.undistortPoints (camera.py:412-421, :435-436).
+struct CamRow {
+  double fx, fy, cx, cy, rfx, rfy, cp, sp;     // cx, cy: principal point of the encode (pp_cam)
+  double k1, k2, p1, p2, k3, kcx, kcy;        // lens model; kcx, kcy: K's own principal point
+  float height, pitch;
+  bool undistort;
+};
+
+__device__ __forceinline__ CamRow load_cam(const void* cam, int64_t stride, int kind, int64_t row) {
+  CamRow c;
+  c.k1 = c.k2 = c.p1 = c.p2 = c.k3 = c.kcx = c.kcy = 0.0;
+  c.undistort = false;
+  if (kind == R3D_CAM_F64) {
+    const double* r = reinterpret_cast<const double*>(cam) + row * stride;
+    c.fx = r[0]; c.fy = r[1]; c.cx = r[2]; c.cy = r[3]; c.cp = r[4]; c.sp = r[5];
+    c.pitch = (float)r[6]; c.height = (float)r[7];
+    c.k1 = r[8]; c.k2 = r[9]; c.p1 = r[10]; c.p2 = r[11]; c.k3 = r[12];
+    c.undistort = r[13] != 0.0;
+    c.kcx = r[14]; c.kcy = r[15];
+  } else {
+    const float* r = reinterpret_cast<const float*>(cam) + row * stride;
+    c.fx = r[0]; c.fy = r[1]; c.cx = r[2]; c.cy = r[3];
+    sincos((double)r[4], &c.sp, &c.cp);
+    c.pitch = r[4]; c.height = r[5];
+  }
+  c.rfx = __ddiv_rn(1.0, c.fx);
+  c.rfy = __ddiv_rn(1.0, c.fy);
+  return c;
+}
+
+// cv2.undistortPoints(pts, K, dist, P=K) with the 5-coefficient model (k1, k2, p1, p2, k3), pixels in -> pixels out.
+// OpenCV's default termination for this overload is exactly 5 fixed-point iterations; the arithmetic follows
+// cvUndistortPointsInternal operation by operation with round-to-nearest multiplies/adds (no FMA contraction), which
+// reproduces opencv-python 4.13 bit for bit (tests/golden/camera_undistort.npz).
+__device__ __forceinline__ void undistort_px(double& u, double& v, const CamRow& c) {
+  double x = __dmul_rn(__dsub_rn(u, c.kcx), c.rfx), y = __dmul_rn(__dsub_rn(v, c.kcy), c.rfy);
+  const double x0 = x, y0 = y;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    // numerator 1 + ((k6 r2 + k5) r2 + k4) r2 with k4..k6 = 0 evaluates to exactly 1
+    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c.k3, r2), c.k2), r2), c.k1), r2));
+    const double icdist = __ddiv_rn(1.0, den);
+    const double two_xx = __dmul_rn(__dmul_rn(2.0, x), x), two_yy = __dmul_rn(__dmul_rn(2.0, y), y);
+    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, c.p1), x), y), __dmul_rn(c.p2, __dadd_rn(r2, two_xx)));
+    const double dy = __dadd_rn(__dmul_rn(c.p1, __dadd_rn(r2, two_yy)), __dmul_rn(__dmul_rn(__dmul_rn(2.0, c.p2), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+  }
+  // P = K:  xx = fx*x + 0*y + cx,  ww = 1/(0*x + 0*y + 1) = 1
+  u = __dadd_rn(__dmul_rn(c.fx, x), c.kcx);
+  v = __dadd_rn(__dmul_rn(c.fy, y), c.kcy);
+}
+
+// One keypoint: camera.py:435-439 (optional undistortion, (uv - pp) / f) and :471 ([xn, yn, 1] @ Rx(pitch)^T) in float64,
+// then .astype(float32) (trainer.py:298).
+template <bool UNDIST>
+__device__ __forceinline__ float3 encode_keypoint(float2 p, const CamRow& c) {
+  double u = (double)p.x, v = (double)p.y;
+  if (UNDIST && c.undistort) undistort_px(u, v, c);
+  const double xn = div_by(__dsub_rn(u, c.cx), c.fx, c.rfx);
+  const double yn = div_by(__dsub_rn(v, c.cy), c.fy, c.rfy);
+  return make_float3((float)xn, (float)__dadd_rn(__dmul_rn(c.cp, yn), c.sp), (float)__dadd_rn(__dmul_rn(-c.sp, yn), c.cp));
+}
+
 // One CTA per sequence (window).  Dynamic smem: T*J*Cin floats (+ embed scratch).
+// src_kind R3D_SRC_UV: pixel keypoints, camera rows per cam_kind; R3D_SRC_RAYS: encoded input, `cam` = param rows (float).
+template <bool UNDIST>
 __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
                                                        const float* __restrict__ src, int64_t src_batch_stride,
-                                                       int src_is_uv, const float* __restrict__ cam_or_param,
-                                                       int64_t param_stride, int batch, int flip_from) {
+                                                       int src_is_uv, const void* __restrict__ cam, int64_t cam_stride,
+                                                       int cam_kind, int batch, int flip_from) {
   extern __shared__ float smem[];
   const PrologueDev& d = *dp;
   const int b = blockIdx.x;
@@ -69,15 +142,14 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   float* xs = smem;                    // [T][JC]
   float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
   if (threadIdx.x == 0) xs[T * JC] = 0.f;   // zero word read for the padding columns of the first-layer operand
+  float prm[8];                        // the embedder's input row (trainer.py:297: [height, pitch])
 
   // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
   if (src_is_uv) {
     // camera.py:438-439,471 in float64, then .astype(float32) (trainer.py:298)
-    const float* cam = cam_or_param + (int64_t)bs * param_stride;
-    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
-    const double rfx = __ddiv_rn(1.0, fx), rfy = __ddiv_rn(1.0, fy);
-    double sp, cp;
-    sincos((double)cam[4], &sp, &cp);
+    const CamRow c = load_cam(cam, cam_stride, cam_kind, bs);
+    prm[0] = c.height;
+    prm[1] = c.pitch;
     const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
     // keypoints are fetched in batches of 8 independent loads per thread before any float64 math touches them
     // (one HBM round trip per batch instead of one per keypoint)
@@ -95,11 +167,10 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * blockDim.x;
         if (i < T * J) {
-          const double xn = div_by(__dsub_rn((double)pv[u].x, cx), fx, rfx);
-          const double yn = div_by(__dsub_rn((double)pv[u].y, cy), fy, rfy);
-          xs[i * 3 + 0] = flip ? -(float)xn : (float)xn;
-          xs[i * 3 + 1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
-          xs[i * 3 + 2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
+          const float3 r = encode_keypoint<UNDIST>(pv[u], c);
+          xs[i * 3 + 0] = flip ? -r.x : r.x;
+          xs[i * 3 + 1] = r.y;
+          xs[i * 3 + 2] = r.z;
         }
       }
     }
@@ -184,14 +255,8 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   // ---- 4. camera embedding (embedding.py:15-19), BN folded, fp32 FFMA; both nets' embedders side by side ----------
   if (d.n_embed > 0) {
     const int mid = d.emb_mid, ne = d.n_embed;
-    float prm[8];
-    if (src_is_uv) {   // param = [height, pitch] (trainer.py:297)
-      const float* cam = cam_or_param + (int64_t)bs * param_stride;
-      prm[0] = cam[5];
-      prm[1] = cam[4];
-    } else {
-      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)bs * param_stride + i];
-    }
+    if (!src_is_uv)
+      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = reinterpret_cast<const float*>(cam)[(int64_t)bs * cam_stride + i];
     for (int t = threadIdx.x; t < ne * mid; t += blockDim.x) {           // hidden layer
       const EmbedDev& em = d.embed[t / mid];
       const int j = t % mid;
@@ -221,214 +286,57 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   }
 }
 
-// ---- input stage, row-wise form ---------------------------------------------------------------------------------
-// Same outputs as prologue_kernel, bit for bit, without staging the whole window: every warp builds operand rows on its
-// own.  A row (b, tq) needs the w0 frames [w0*tq, w0*tq + w0) and frame tc; the warp ray-encodes those w0*J keypoints
-// straight from global memory into a private [w0*JC | JC (frame tc) | 0] buffer and gathers its columns from there
-// (a0_row[k] = offset into that buffer).  ~7 KB of shared memory per CTA instead of 50 KB (no receptive-field limit, the
-// SM's L1 stays available for the embedder weights), no block-wide phase barrier, rows claimed dynamically so the warp
-// that also computes the camera embedding does not hold the CTA back.
-__global__ void __launch_bounds__(256) prologue_rows_kernel(const PrologueDev* __restrict__ dp, int precision,
-                                                            const float* __restrict__ src, int64_t src_batch_stride,
-                                                            int src_is_uv, const float* __restrict__ cam_or_param,
-                                                            int64_t param_stride, int batch, int flip_from) {
-  extern __shared__ double smem_d[];
-  const PrologueDev& d = *dp;
-  const int b = blockIdx.x;
-  const bool flip = b >= flip_from;                      // mirrored copy of window b - flip_from (trainer.py:299-302)
-  const int bs = flip ? b - flip_from : b;
-  const int J = d.J, JC = d.JC, Cin = d.Cin, w0 = d.w0, kf = w0 * JC;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int WB = (kf + JC + 1 + 3) & ~3;                 // per-warp buffer: [w0 frames | frame tc | zero word], padded
-  double* cst = smem_d;                                  // fx, fy, cx, cy, 1/fx, 1/fy, sin(pitch), cos(pitch)
-  int* next_row = reinterpret_cast<int*>(smem_d + 8);
-  float* wbuf = reinterpret_cast<float*>(smem_d + 10) + warp * WB;
-  float* scratch = reinterpret_cast<float*>(smem_d + 10) + nwarp * WB;   // [2][emb_mid] embedder hidden layers
-
-  if (warp == 0) {
-    if (src_is_uv) {   // camera.py:438-439,471 in float64 (every lane computes, lane 0 publishes)
-      const float* cam = cam_or_param + (int64_t)bs * param_stride;
-      const double fx = cam[0], fy = cam[1];
-      double sp, cp;
-      sincos((double)cam[4], &sp, &cp);
-      if (lane == 0) {
-        cst[0] = fx; cst[1] = fy; cst[2] = cam[2]; cst[3] = cam[3];
-        cst[4] = __ddiv_rn(1.0, fx); cst[5] = __ddiv_rn(1.0, fy); cst[6] = sp; cst[7] = cp;
-      }
-    }
-    if (lane == 0) *next_row = 0;
-  }
-  __syncthreads();
-  const double fx = cst[0], fy = cst[1], cx = cst[2], cy = cst[3], rfx = cst[4], rfy = cst[5], sp = cst[6], cp = cst[7];
-  const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
-  const float* x = src + (int64_t)bs * src_batch_stride;
-
-  // keypoint `kp` (frame-major index inside the window) -> 3 ray components at dst (float64 math, rounded once)
-  auto encode = [&](float2 p, float* dst) {
-    const double xn = div_by(__dsub_rn((double)p.x, cx), fx, rfx);
-    const double yn = div_by(__dsub_rn((double)p.y, cy), fy, rfy);
-    dst[0] = flip ? -(float)xn : (float)xn;
-    dst[1] = (float)__dadd_rn(__dmul_rn(cp, yn), sp);
-    dst[2] = (float)__dadd_rn(__dmul_rn(-sp, yn), cp);
-  };
-  // frames [f0, f0 + nf) of the window -> dst[nf * JC]
-  auto stage_frames = [&](int f0, int nf, float* dst) {
-    if (src_is_uv) {
-      const int nk = nf * J;
-      for (int k0 = lane; k0 < nk; k0 += 64) {            // two independent loads in flight per lane
-        const int k1 = k0 + 32;
-        const int j0 = k0 % J, j1 = k1 % J;
-        const float2 p0 = __ldg(uv + f0 * J + (flip ? k0 - j0 + d.flip_perm[j0] : k0));
-        float2 p1 = make_float2(0.f, 0.f);
-        if (k1 < nk) p1 = __ldg(uv + f0 * J + (flip ? k1 - j1 + d.flip_perm[j1] : k1));
-        encode(p0, dst + k0 * 3);
-        if (k1 < nk) encode(p1, dst + k1 * 3);
-      }
-    } else if (!flip) {
-      for (int i = lane; i < nf * JC; i += 32) dst[i] = __ldg(x + f0 * JC + i);
-    } else {
-      for (int i = lane; i < nf * JC; i += 32) {
-        const int c = i % Cin, jj = (i / Cin) % J;
-        const float v = __ldg(x + f0 * JC + i + (d.flip_perm[jj] - jj) * Cin);
-        dst[i] = c == 0 ? -v : v;
-      }
-    }
-  };
-
-  stage_frames(d.tc, 1, wbuf + kf);                      // frame tc: every warp keeps its own copy
-  if (lane == 0) wbuf[kf + JC] = 0.f;
-  __syncwarp();
-  if (warp == 0)                                          // in_current (rie.py:290-292), zero padded to the row pitch
-    for (int i = lane; i < d.inc.ld; i += 32) store_act(d.inc, precision, b, i, i < JC ? wbuf[kf + i] : 0.f);
-
-  // ---- camera embedding (embedding.py:15-19) by the last warp, before it joins the row loop -------------------------
-  if (warp == nwarp - 1 && d.n_embed > 0) {
-    const int mid = d.emb_mid, ne = d.n_embed;
-    float prm[8];
-    if (src_is_uv) {   // param = [height, pitch] (trainer.py:297)
-      const float* cam = cam_or_param + (int64_t)bs * param_stride;
-      prm[0] = cam[5];
-      prm[1] = cam[4];
-    } else {
-      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = cam_or_param[(int64_t)bs * param_stride + i];
-    }
-    for (int t = lane; t < ne * mid; t += 32) {
-      const EmbedDev& em = d.embed[t / mid];
-      const int j = t % mid;
-      float acc = em.b1[j];
-      for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(em.w1[j * d.ext_dim + i], prm[i], acc);
-      scratch[t] = acc > 0.f ? acc : 0.01f * acc;
-    }
-    __syncwarp();
-    for (int t = lane; t < ne * d.emb_dim; t += 32) {
-      const int e = t / d.emb_dim, j = t % d.emb_dim;
-      const EmbedDev& em = d.embed[e];
-      const float* w = em.w2 + j * mid;
-      const float* h = scratch + e * mid;
-      float acc = em.b2[j];
-      int i = 0;
-      for (; i + 8 <= mid; i += 8) {
-        float wv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + i + u);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(wv[u], h[i + u], acc);     // same summation order as prologue_kernel
-      }
-      for (; i < mid; ++i) acc = fmaf(w[i], h[i], acc);
-      acc = acc > 0.f ? acc : 0.01f * acc;
-      for (int q = 0; q < em.ndst; ++q) store_act(em.dst[q].m, precision, b, em.dst[q].col + j, acc);
-    }
-  }
-
-  // ---- operand rows ------------------------------------------------------------------------------------------------
-  const int kp = d.k_pad;
-  int off[16];
-  if (kp <= 512) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int k = lane * 2 + g * 64;
-      const int2 e = k < kp ? __ldg(reinterpret_cast<const int2*>(d.a0_row + k)) : make_int2(kf + JC, kf + JC);
-      off[2 * g] = e.x;
-      off[2 * g + 1] = e.y;
-    }
-  }
-  for (;;) {
-    int tq = 0;
-    if (lane == 0) tq = atomicAdd(next_row, 1);
-    tq = __shfl_sync(0xffffffffu, tq, 0);
-    if (tq >= d.L0) break;
-    stage_frames(w0 * tq, w0, wbuf);
-    __syncwarp();
-    const int64_t rb = ((int64_t)b * d.L0 + tq) * d.a0.ld + lane * 2;
-    if (kp <= 512) {
-      if (precision == R3D_PREC_FP32) {
-        float* o = reinterpret_cast<float*>(d.a0.p0) + rb;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          if (lane * 2 + g * 64 < kp) *reinterpret_cast<float2*>(o + g * 64) = make_float2(wbuf[off[2 * g]], wbuf[off[2 * g + 1]]);
-      } else {
-        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d.a0.p0) + rb;
-        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d.a0.p1) + rb;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          if (lane * 2 + g * 64 < kp) {
-            const float v0 = wbuf[off[2 * g]], v1 = wbuf[off[2 * g + 1]];
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
-            *reinterpret_cast<__nv_bfloat162*>(oh + g * 64) = hi;
-            if (precision == R3D_PREC_BF16X3) {
-              const float2 hf = __bfloat1622float2(hi);
-              *reinterpret_cast<__nv_bfloat162*>(ol + g * 64) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
-            }
-          }
-      }
-    } else {
-      for (int kk = lane * 2; kk < kp; kk += 64)
-        store_act2(d.a0, precision, (int64_t)b * d.L0 + tq, kk, wbuf[d.a0_row[kk]], wbuf[d.a0_row[kk + 1]]);
-    }
-    __syncwarp();                                         // the next row overwrites the buffer
-  }
-}
-
 static int g_prologue_smem_cap = 48 * 1024;
 
 cudaError_t prologue_configure(int max_smem_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  if (e == cudaSuccess)   // several windows per SM: ask for the largest shared-memory carve-out
-    e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess) g_prologue_smem_cap = max_smem_bytes;
-  return e;
+  for (int u = 0; u < 2; ++u) {
+    const void* fn = u ? (const void*)prologue_kernel<true> : (const void*)prologue_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+    if (e == cudaSuccess)   // several windows per SM: ask for the largest shared-memory carve-out
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
+  g_prologue_smem_cap = max_smem_bytes;
+  return cudaSuccess;
 }
 
-cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const void* src,
-                            int64_t src_batch_stride, int src_is_uv, const float* cam_or_param,
-                            int64_t param_stride, int batch, int flip_from, cudaStream_t s) {
-  // Measured at B=1024, T=243: 64 us against 58 us for the whole-window form (also with 5 or 6 CTAs per SM) -- the stage
-  // is bound by instruction issue, not by occupancy or the phase barrier -- so it is opt-in (R3D_PROLOGUE_ROWS=1).
-  static int rows_form = -1;
-  if (rows_form < 0) {
-    rows_form = 0;
-    if (const char* env = getenv("R3D_PROLOGUE_ROWS")) rows_form = atoi(env) != 0;
-  }
-  if (rows_form && h.Cin * h.J == h.JC && (!src_is_uv || h.Cin == 3)) {
-    const int threads = 256, nwarp = threads / 32;
-    const int wb = ((h.w0 + 1) * h.JC + 1 + 3) & ~3;
-    const size_t smem_rows = 10 * sizeof(double) + (size_t)(nwarp * wb + 2 * h.emb_mid + 8) * sizeof(float);
-    if (smem_rows <= 48 * 1024) {
-      prologue_rows_kernel<<<batch, threads, smem_rows, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
-                                                             src_is_uv, cam_or_param, param_stride, batch, flip_from);
-      return cudaGetLastError();
-    }
-  }
+cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int precision, const InputSpec& in, int batch,
+                            int flip_from, cudaStream_t s) {
   const size_t smem = (size_t)(h.T * h.JC + 2 * h.emb_mid + 16) * sizeof(float);
   if ((int)smem > g_prologue_smem_cap) return cudaErrorInvalidValue;
-  static int threads = 0;
-  if (threads == 0) {
-    threads = 256;      // measured: 4 CTAs x 256 threads per SM (register-limited) beat 3 x 320 (57 vs 64 us at B=1024, T=243)
-    if (const char* env = getenv("R3D_PROLOGUE_THREADS")) threads = atoi(env);
-    if (threads < 64 || threads > 320 || threads % 32) threads = 256;
-  }
-  prologue_kernel<<<batch, threads, smem, s>>>(d_desc, precision, reinterpret_cast<const float*>(src), src_batch_stride,
-                                           src_is_uv, cam_or_param, param_stride, batch, flip_from);
+  const int threads = 256;   // measured: 4 CTAs x 256 threads per SM (register-limited) beat 3 x 320 (57 vs 64 us at B=1024, T=243)
+  const int is_uv = in.src_kind == R3D_SRC_UV;
+  if (is_uv && in.undistort)   // lens undistortion inside the encode: a separate instantiation keeps the common path's registers
+    prologue_kernel<true><<<batch, threads, smem, s>>>(d_desc, precision, in.src, in.src_stride, is_uv, in.cam, in.cam_stride, in.cam_kind,
+                                                     batch, flip_from);
+  else
+    prologue_kernel<false><<<batch, threads, smem, s>>>(d_desc, precision, in.src, in.src_stride, is_uv, in.cam, in.cam_stride, in.cam_kind,
+                                                      batch, flip_from);
+  return cudaGetLastError();
+}
+
+// ---- per-frame ray encode of a whole video (r3d_forward_video_uv): every frame is encoded ONCE -- the windows that
+// contain it are indexed in the input stage afterwards (trainer.py:47-58 copies each frame RF times instead).  One camera
+// row for the whole video; also writes the embedder's param row [height, pitch] (trainer.py:297, :324).
+template <bool UNDIST>
+__global__ void video_encode_kernel(const float2* __restrict__ uv, float* __restrict__ rays, float* __restrict__ param, int64_t n,
+                                    const void* __restrict__ cam, int cam_kind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const CamRow c = load_cam(cam, 0, cam_kind, 0);
+  const float3 r = encode_keypoint<UNDIST>(__ldg(uv + i), c);
+  rays[i * 3 + 0] = r.x;
+  rays[i * 3 + 1] = r.y;
+  rays[i * 3 + 2] = r.z;
+  if (i == 0 && param != nullptr) { param[0] = c.height; param[1] = c.pitch; }
+}
+
+cudaError_t launch_video_encode(const float* uv, float* rays, float* param, int64_t n_points, const void* cam, int cam_kind,
+                                int undistort, cudaStream_t s) {
+  if (n_points <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n_points + 255) / 256);
+  if (undistort) video_encode_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(uv), rays, param, n_points, cam, cam_kind);
+  else video_encode_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(uv), rays, param, n_points, cam, cam_kind);
   return cudaGetLastError();
 }
 
@@ -489,32 +397,18 @@ cudaError_t launch_ray_encode_f64(const double* uv, double* ray, int64_t n, doub
   return cudaGetLastError();
 }
 
-// ---- lens undistortion: CameraInfoPacket.undistort_point (camera.py:412-421) == cv2.undistortPoints(pts, K, dist, P=K)
-// with the 5-coefficient model (k1, k2, p1, p2, k3).  OpenCV's default termination for this overload is exactly 5
-// fixed-point iterations; the arithmetic below follows cvUndistortPointsInternal operation by operation with
-// round-to-nearest multiplies/adds (no FMA contraction), which reproduces opencv-python 4.13 bit for bit.
+// ---- lens undistortion: CameraInfoPacket.undistort_point (camera.py:412-421), float64 pixels in -> float64 pixels out
 __global__ void undistort_points_f64_kernel(const double2* __restrict__ uv, double2* __restrict__ out, int64_t n, double fx, double fy,
                                             double cx, double cy, double k1, double k2, double p1, double p2, double k3) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double ifx = __ddiv_rn(1.0, fx), ify = __ddiv_rn(1.0, fy);
-  const double2 p = uv[i];
-  double x = __dmul_rn(__dsub_rn(p.x, cx), ifx), y = __dmul_rn(__dsub_rn(p.y, cy), ify);
-  const double x0 = x, y0 = y;
-#pragma unroll 1
-  for (int it = 0; it < 5; ++it) {
-    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
-    // numerator 1 + ((k6 r2 + k5) r2 + k4) r2 with k4..k6 = 0 evaluates to exactly 1
-    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
-    const double icdist = __ddiv_rn(1.0, den);
-    const double two_xx = __dmul_rn(__dmul_rn(2.0, x), x), two_yy = __dmul_rn(__dmul_rn(2.0, y), y);
-    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y), __dmul_rn(p2, __dadd_rn(r2, two_xx)));
-    const double dy = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, two_yy)), __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
-    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
-    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
-  }
-  // P = K:  xx = fx*x + 0*y + cx,  ww = 1/(0*x + 0*y + 1) = 1
-  out[i] = make_double2(__dadd_rn(__dmul_rn(fx, x), cx), __dadd_rn(__dmul_rn(fy, y), cy));
+  CamRow c;
+  c.fx = fx; c.fy = fy; c.kcx = cx; c.kcy = cy;
+  c.rfx = __ddiv_rn(1.0, fx); c.rfy = __ddiv_rn(1.0, fy);
+  c.k1 = k1; c.k2 = k2; c.p1 = p1; c.p2 = p2; c.k3 = k3;
+  double2 p = uv[i];
+  undistort_px(p.x, p.y, c);
+  out[i] = p;
 }
 
 cudaError_t launch_undistort_points_f64(const double* uv, double* out, int64_t n, double fx, double fy, double cx, double cy,

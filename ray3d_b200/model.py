@@ -127,21 +127,33 @@ class _PlanCache:
     def __init__(self, owner: nn.Module):
         self.owner = weakref.ref(owner)
         self.lock = threading.Lock()
-        self.plans: Dict[Tuple[int, str], Tuple[int, Lifter]] = {}
+        self.plans: Dict[Tuple, Tuple[object, Lifter]] = {}
+        self.tensors = None                     # flat list of the owner's parameters + buffers (rebuilt on invalidate)
+        self.sibling = None                     # weakref to the other network of the same Model (pose <-> trajectory)
+        self.spec_out: Dict[int, tuple] = {}    # id(x) -> speculative result for the sibling's next call
 
     def invalidate(self):
         with self.lock:
             self.plans.clear()
+            self.tensors = None
+            self.spec_out.clear()
 
 
 class _NativeNet(nn.Module):
-    """Shared machinery: weight-version tracking and plan lookup."""
+    """Shared machinery: weight-version tracking and plan lookup.
+
+    The packed native copy of the weights is rebuilt when ``load_state_dict`` runs (also through a wrapper such as
+    nn.DataParallel or the reference's ``load_weight``, lib/utils/utils.py:208-218: a post-hook fires inside the
+    recursion), when the module is moved/cast, put in training mode, or when any parameter/buffer was replaced or
+    modified in place through autograd-visible ops (per-tensor ``(data_ptr, _version)`` fingerprint).  Writes through
+    ``tensor.data`` bypass the version counter: call ``refresh_plan()`` after those."""
 
     _net_kind = "pos"
 
     def _init_native(self, spec: NetSpec):
         self._spec = spec
         object.__setattr__(self, "_cache", _PlanCache(self))
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._cache.invalidate())
 
     # invalidation hooks ---------------------------------------------------------------------------
     def load_state_dict(self, *a, **k):
@@ -160,34 +172,53 @@ class _NativeNet(nn.Module):
         return super().train(mode)
 
     def refresh_plan(self):
-        """Force the packed native weights to be rebuilt on the next forward."""
+        """Force the packed native weights to be rebuilt on the next forward (needed after ``p.data`` edits)."""
         self._cache.invalidate()
 
     @staticmethod
-    def _fingerprint(mod: nn.Module) -> int:
-        v = 0
-        for t in mod.parameters():
-            v += t._version
-        for t in mod.buffers():
-            v += t._version
-        return v
+    def _fingerprint(mod: "_NativeNet"):
+        cache = mod._cache
+        ts = cache.tensors
+        if ts is None:
+            ts = cache.tensors = list(mod.parameters()) + list(mod.buffers())
+        return hash(tuple([(t.data_ptr(), t._version) for t in ts]))
 
-    def _lifter(self, device: torch.device) -> Lifter:
+    def _owner(self) -> "_NativeNet":
+        return self._cache.owner() or self          # replicas read the master's weights
+
+    def _lifter(self, device: torch.device, joint_with: Optional["_NativeNet"] = None) -> Lifter:
+        """The plan of this network alone, or -- ``joint_with`` = the sibling network -- ONE plan that evaluates both
+        (grouped launches over the 5 joint groups + the trajectory net, one input stage)."""
         cache: _PlanCache = self._cache
-        owner = cache.owner() or self          # replicas read the master's weights
-        key = (device.index if device.index is not None else torch.cuda.current_device(), _precision())
-        fp = self._fingerprint(owner) if os.environ.get("RAY3D_B200_CHECK_WEIGHTS", "1") != "0" else 0
+        owner = self._owner()
+        check = os.environ.get("RAY3D_B200_CHECK_WEIGHTS", "1") != "0"
+        fp = self._fingerprint(owner) if check else 0
+        if joint_with is not None:
+            fp = (fp, self._fingerprint(joint_with) if check else 0)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), _precision(), joint_with is not None)
         with cache.lock:
             hit = cache.plans.get(key)
             if hit is not None and hit[0] == fp:
                 return hit[1]
             sd = owner.state_dict()
-            if self._net_kind == "pos":
+            if joint_with is not None:
+                sd2 = joint_with.state_dict()
+                pos_sd, trj_sd = (sd, sd2) if self._net_kind == "pos" else (sd2, sd)
+                spec = owner._spec if self._net_kind == "pos" else joint_with._spec     # the pose net's spec carries `stage`
+                lf = Lifter(spec, pos_sd, trj_sd, precision=key[1], device=key[0])
+            elif self._net_kind == "pos":
                 lf = Lifter(self._spec, sd, None, precision=key[1], device=key[0])
             else:
                 lf = Lifter(self._spec, None, sd, precision=key[1], device=key[0])
             cache.plans[key] = (fp, lf)
             return lf
+
+    def _sibling(self) -> Optional["_NativeNet"]:
+        ref = self._owner()._cache.sibling
+        sib = ref() if ref is not None else None
+        if sib is None or sib.training or os.environ.get("RAY3D_B200_JOINT", "1") == "0":
+            return None
+        return sib
 
     def _native_forward(self, x: torch.Tensor, param: Optional[torch.Tensor]) -> torch.Tensor:
         assert len(x.shape) == 4                                   # rie.py:285-287
@@ -198,9 +229,40 @@ class _NativeNet(nn.Module):
                                "no dropout); call .eval() -- training is out of scope of this drop-in")
         if not x.is_cuda:
             raise RuntimeError("ray3d_b200 has no CPU path: move the input to a CUDA device")
-        lf = self._lifter(x.device)
+        sib = self._sibling()
+        if sib is None:
+            pos, trj, _ = self._lifter(x.device).forward_rays(x, param, want_sum=False)
+            return pos if self._net_kind == "pos" else trj
+        # The reference's callers evaluate BOTH networks on the same tensors back to back (trainer.py:337-348:
+        # pos_model(x, param) ... trj_model(x, param)).  The first of the two calls runs one joint plan and parks the
+        # sibling's output; the sibling's call on the very same tensor objects (same storage, same version counters,
+        # same stream, unchanged weights) takes it instead of launching the whole tree again.  Anything else misses
+        # and computes normally; a parked result is handed out once (callers mutate outputs in place).
+        owner, stream = self._owner(), torch.cuda.current_stream(x.device).cuda_stream
+        pv = None if param is None else (id(param), param.data_ptr(), param._version)
+        ident = (id(x), x.data_ptr(), x._version, tuple(x.shape), pv, stream, _precision())
+        with owner._cache.lock:
+            parked = owner._cache.spec_out.pop(id(x), None)
+        if parked is not None and parked[0] == ident and parked[1]() is x and parked[2] == self._fingerprint(owner):
+            return parked[3]
+        lf = self._lifter(x.device, joint_with=sib._owner())
         pos, trj, _ = lf.forward_rays(x, param, want_sum=False)
-        return pos if self._net_kind == "pos" else trj
+        mine, theirs = (pos, trj) if self._net_kind == "pos" else (trj, pos)
+        sc = sib._owner()._cache
+        with sc.lock:
+            if len(sc.spec_out) >= 4:
+                sc.spec_out.clear()
+            sc.spec_out[id(x)] = (ident, weakref.ref(x), self._fingerprint(sib._owner()), theirs)
+        return mine
+
+
+def link_models(pos_model: nn.Module, trj_model: nn.Module) -> None:
+    """Declare the two networks of one Model siblings: their eval forwards then share one native plan (one input
+    stage, grouped launches), see _NativeNet._native_forward."""
+    p, t = getattr(pos_model, "module", pos_model), getattr(trj_model, "module", trj_model)
+    if p._spec.replace_stage(1) != t._spec.replace_stage(1):
+        return                                      # different architectures: nothing to share
+    p._cache.sibling, t._cache.sibling = weakref.ref(t), weakref.ref(p)
 
 
 def _spec_from_ctor(num_joints_in, in_features, filter_widths, latten_features, channels, stage, extrinsic_dim, embedd_dim):
@@ -342,6 +404,8 @@ class Model(object):
             pos_model = nn.DataParallel(pos_model, device_ids=dev).cuda()
             trj_model = nn.DataParallel(trj_model, device_ids=dev).cuda() if trj_model is not None else None
         self.pos_model, self.trj_model = pos_model, trj_model
+        if trj_model is not None:
+            link_models(pos_model, trj_model)
 
     def get_pos_model(self):
         return self.pos_model

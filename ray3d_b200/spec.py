@@ -14,6 +14,7 @@ Reference behaviour it encodes (all paths relative to the reference checkout):
 """
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence, Tuple
 
@@ -64,6 +65,10 @@ class NetSpec:
             raise ValueError("in_features must be 2 (pixel/intrinsic encoding) or 3 (ray encoding)")
         if not self.filter_widths or any(w < 1 or w % 2 == 0 for w in self.filter_widths):
             raise ValueError("filter widths must be odd and positive")
+
+    def replace_stage(self, stage: int) -> "NetSpec":
+        """Same architecture with another ``stage`` (the trajectory net ignores it, rie.py:491-494)."""
+        return dataclasses.replace(self, stage=stage)
 
     # -- derived ---------------------------------------------------------------------------
     @property

@@ -181,13 +181,12 @@ def test_first_forward_after_workspace_growth_is_already_right(golden_meta):
 
 
 @pytest.mark.parametrize("name", ["h36m_s1_t27", "h36m_s3_t9"])
-def test_small_batches_replay_a_cuda_graph(golden_meta, name, monkeypatch):
+def test_small_batches_replay_a_cuda_graph(golden_meta, name):
     """Batches <= 64 go through a captured CUDA graph (one launch): bit-identical to the direct launch sequence, for the
     uv, ray and sliding-window entry points, across repeated calls and changing batch sizes."""
     spec, lf, sp, st = lifter_for(golden_meta, name, "bf16x3")
-    monkeypatch.setenv("R3D_GRAPH_MAX_BATCH", "0")
     direct = Lifter(spec, sp, st, precision="bf16x3")
-    monkeypatch.delenv("R3D_GRAPH_MAX_BATCH")
+    direct.plan.set_option("graph_max_batch", 0)
     g0 = lf.plan.graph_launches
     for rep in range(2):
         for B in (1, 3, 64, 65, 2):

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = _capi.lib()                      # loads the .so and resolves every EXPORTS entry
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.r3d_abi_version() == 1
+    assert lib.r3d_abi_version() == 2
 
 
 def make_plan(spec, nets=3, precision="fp32"):
