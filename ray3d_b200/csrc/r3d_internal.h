@@ -66,6 +66,7 @@ struct GemmOpDev {
   int32_t flags;         // experiments: bit 0 fused pair waits for the whole intermediate before the second GEMM;
                          // bit 1 release (instead of relaxed) remote barrier arrivals
   int32_t _pad;
+  uint32_t* sched;       // work-unit counter of this launch (zeroed before every forward): CTAs claim units with atomicAdd
   GemmProb prob[kMaxProb];
 };
 

@@ -185,7 +185,8 @@ struct r3d_plan {
   PrologueDev pro{};
   AssembleDev asmb{};
   char* d_desc = nullptr;                             // ops + prologue + assemble + tmaps
-  size_t off_ops = 0, off_pro = 0, off_asm = 0, off_tmaps = 0;
+  size_t off_ops = 0, off_pro = 0, off_asm = 0, off_tmaps = 0, off_sched = 0;
+  static constexpr size_t kSchedStride = 128;
   // symbolic ids used while building
   int m_inc = -1, m_heads[kMaxProb] = {-1, -1, -1, -1, -1, -1};
   struct EmbBind { int net; std::vector<std::pair<int, int>> dst; };
@@ -1184,6 +1185,7 @@ static int bind_workspace(r3d_plan* p, int cap) {
   p->off_pro = take(sizeof(PrologueDev));
   p->off_asm = take(sizeof(AssembleDev));
   p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
+  p->off_sched = take(nops * r3d_plan::kSchedStride);                    // one work-unit counter per GEMM launch, 128 bytes apart
   const size_t off_map = take(p->a0_src.size() * sizeof(int32_t));
   CUDA_TRY(cudaMalloc(&p->d_desc, off));
   pd.a0_off = reinterpret_cast<const int32_t*>(p->d_desc + off_map);
@@ -1196,7 +1198,10 @@ static int bind_workspace(r3d_plan* p, int cap) {
           sidx < 0 ? p->T * p->JC : (sidx < k_frames ? (sidx | (1 << 30)) : sidx - k_frames + p->tc * p->JC);
     }
   }
-  for (size_t i = 0; i < nops; ++i) memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
+  for (size_t i = 0; i < nops; ++i) {
+    p->ops[i].dev.sched = reinterpret_cast<uint32_t*>(p->d_desc + p->off_sched + i * r3d_plan::kSchedStride);
+    memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
+  }
   memcpy(h.data() + p->off_pro, &pd, sizeof(pd));
   memcpy(h.data() + p->off_asm, &ad, sizeof(ad));
   if (prec != R3D_PREC_FP32) {
@@ -1251,6 +1256,8 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
     ++p->prof_runs;
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
+  if (prec != R3D_PREC_FP32)   // work-unit counters of the launches below (claimed by their CTAs with atomicAdd)
+    CUDA_TRY(cudaMemsetAsync(p->d_desc + p->off_sched, 0, p->ops.size() * r3d_plan::kSchedStride, s));
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, in, batch, tta ? batch_in : batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
   // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
@@ -1903,6 +1910,9 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
     if (bf_dst) b.dst[0] = Dst{Mat{dOh + q * nc, precision == R3D_PREC_BF16X3 ? dOl + q * nc : nullptr, n, 0}, 0, 0};
   }
   GemmOpDev *dF, *dT;
+  uint32_t* dSched;
+  CUDA_TRY(cudaMalloc(&dSched, 128));
+  t.sched = dSched;
   void* dMaps;
   std::vector<char> maps((size_t)kMaxProb * kTmapsPerProb * kTmapBytes, 0);
   if (tc_build_tmaps(t, precision, m, maps.data()) != 0) return fail(R3D_ERR_CUDA, "selftest: tensor map encode failed");
@@ -1921,6 +1931,7 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   }
   if (ms_ffma) *ms_ffma = ms;
   for (int rep = 0; rep < 2; ++rep) {
+    CUDA_TRY(cudaMemsetAsync(dSched, 0, 128, 0));
     CUDA_TRY(cudaEventRecord(e0, 0));
     CUDA_TRY(launch_gemm_tc(dT, t, dMaps, m, precision, 0));
     CUDA_TRY(cudaEventRecord(e1, 0));
@@ -1945,7 +1956,7 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   }
   if (rel_err) *rel_err = md / std::max(mx, 1e-30);
   for (void* q : {(void*)dA, (void*)dW, (void*)dB, (void*)dR, (void*)dC0, (void*)dC1, (void*)dAh, (void*)dAl, (void*)dWh, (void*)dWl,
-                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps, (void*)dOh})
+                  (void*)dRh, (void*)dRl, (void*)dF, (void*)dT, dMaps, (void*)dOh, (void*)dSched})
     cudaFree(q);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return R3D_OK;

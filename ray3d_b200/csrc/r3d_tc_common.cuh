@@ -60,6 +60,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Same with cluster-scope acquire: the waiter reads data another CTA of the cluster wrote before its (release.cluster)
+// arrival -- the tile ids the leader CTA's scheduler stores into the peer's queue.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("r3d gemm_tc: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+// 32-bit store into the shared memory of CTA `rank` of the cluster (same offset as `p` in this CTA)
+__device__ __forceinline__ void st_shared_cluster_u32(const volatile void* p, uint32_t rank, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(smem_u32(const_cast<const void*>(p))),
+      "r"(rank), "r"(v)
+      : "memory");
+}
 // L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // activations: streamed once
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // weights: re-read by every tile of the problem

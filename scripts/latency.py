@@ -1,5 +1,5 @@
 """Small-batch latency of the lifting path (BASELINE.json config 0: one clip, T=27, batch 1), with the launch sequence
-replayed from a CUDA graph (default) and launched kernel by kernel (R3D_GRAPH_MAX_BATCH=0).  Per case: blocking
+replayed from a CUDA graph (default) and launched kernel by kernel (option graph_max_batch=0).  Per case: blocking
 latency (call + synchronize, median of 300) and back-to-back rate (300 calls, one synchronize).  Run under gpurun."""
 import json
 import os
@@ -18,11 +18,9 @@ def main():
         spec = NetSpec(filter_widths=widths, stage=1)
         sp, st = synth.make_state_dicts(spec)
         for graphs in (1, 0):
-            if graphs:
-                os.environ.pop("R3D_GRAPH_MAX_BATCH", None)
-            else:
-                os.environ["R3D_GRAPH_MAX_BATCH"] = "0"
             lf = Lifter(spec, sp, st, precision="bf16x3")
+            if not graphs:
+                lf.plan.set_option("graph_max_batch", 0)
             for B in (1, 16, 64):
                 uv, cam = synth.make_inputs(spec, B, seed=3)
                 uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
@@ -44,7 +42,6 @@ def main():
                                       latency_us_p10=round(sorted(lat)[30], 1), back_to_back_us=round(rate_us, 1),
                                       graph_launches=lf.plan.graph_launches)), flush=True)
             del lf
-    os.environ.pop("R3D_GRAPH_MAX_BATCH", None)
 
 
 if __name__ == "__main__":
