@@ -285,8 +285,10 @@ def gemm_roofline(run: Run, ms_step: float, timed_seconds: float, peaks, profile
     launch_times, runs = lf.plan.launch_times()
     lf.plan.set_profiling(False)
     graph = lf.plan.describe()
-    flops = [0.0] + [sum(2.0 * B * o["rows_per_seq"] * (q["n"] * q.get("alg_k", q["k"]) + q.get("n2", 0) * q.get("k2", 0)) +
-                         2.0 * B * o["rows_per_seq"] * q.get("flops0_per_row", 0) for q in o["prob"]) for o in graph["ops"]] + [0.0]
+    op_flops = [sum(2.0 * B * o["rows_per_seq"] * (q["n"] * q.get("alg_k", q["k"]) + q.get("n2", 0) * q.get("k2", 0)) for q in o["prob"]) for o in graph["ops"]]
+    # one entry per kernel launch: the chained tail launch covers many ops (graph["launches"][k]["ops"])
+    flops = [0.0] + [sum(op_flops[i] for i in L["ops"]) for L in graph["launches"]] + [0.0]
+    assert len(flops) == len(launch_times), (len(flops), len(launch_times))
     per = [dict(name=nm, ms=ms, gflop=f / 1e9) for (nm, ms), f in zip(launch_times, flops)]
     gemms = [p for p in per if p["gflop"] > 0]
     top = max(gemms, key=lambda p: p["ms"])

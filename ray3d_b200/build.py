@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libray3d_b200.so")
-SOURCES = ["r3d_plan.cpp", "r3d_stage_kernels.cu", "r3d_gemm_ffma.cu", "r3d_gemm_tc.cu"]
+SOURCES = ["r3d_plan.cpp", "r3d_stage_kernels.cu", "r3d_gemm_ffma.cu", "r3d_gemm_tc.cu", "r3d_tail_tc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

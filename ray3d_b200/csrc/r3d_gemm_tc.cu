@@ -65,62 +65,6 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, 
   return TileCoord{p, (mg * cl + rank) * TBM, rem * block_n};
 }
 
-// ---- epilogue helpers -------------------------------------------------------------------------------
-// Per-warp staging tile in shared memory: 32 rows x 64 bytes (one 32-column bf16 chunk), 16-byte units
-// XOR-swizzled so that both the row-per-thread access and the 4-lanes-per-row access are conflict free.
-__device__ __forceinline__ int stg_index(int row, int unit) { return row * 4 + (unit ^ ((row >> 1) & 3)); }
-
-// registers (thread = row, 32 bf16 packed in w[16]) -> staging tile in the 64B-swizzle layout the TMA store expects
-__device__ __forceinline__ void stage_write(uint4* stg, const uint32_t (&w)[16], int lane) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) stg[stg_index(lane, u)] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
-}
-
-// Residual tile of one 32x32 chunk.  Loads are coalesced (4 lanes x 16 B per row) and *issued one chunk ahead*
-// (software pipelining in registers), so their HBM/L2 latency overlaps the previous chunk's math and stores.
-struct ResidualRegs {
-  uint4 h[4], l[4];
-};
-__device__ __forceinline__ void residual_issue(ResidualRegs& rr, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int col, int lane,
-                                               int m_base, int M) {
-  const int u = lane & 3;
-#pragma unroll
-  for (int pass = 0; pass < 4; ++pass) {
-    const int row = m_base + pass * 8 + (lane >> 2);
-    rr.h[pass] = make_uint4(0, 0, 0, 0);
-    rr.l[pass] = make_uint4(0, 0, 0, 0);
-    if (row < M) {
-      const int64_t o = (int64_t)row * ld + col + u * 8;
-      rr.h[pass] = __ldg(reinterpret_cast<const uint4*>(hi + o));
-      if (lo != nullptr) rr.l[pass] = __ldg(reinterpret_cast<const uint4*>(lo + o));
-    }
-  }
-}
-// registers (4 lanes per row) -> swizzled staging tile -> registers (thread = row), accumulated into v[32]
-__device__ __forceinline__ void residual_consume(uint4* stg, const ResidualRegs& rr, bool has_lo, int lane, float (&v)[32]) {
-  const int u = lane & 3;
-#pragma unroll
-  for (int plane = 0; plane < 2; ++plane) {
-    if (plane == 1 && !has_lo) break;
-#pragma unroll
-    for (int pass = 0; pass < 4; ++pass) stg[stg_index(pass * 8 + (lane >> 2), u)] = plane ? rr.l[pass] : rr.h[pass];
-    __syncwarp();
-#pragma unroll
-    for (int uu = 0; uu < 4; ++uu) {
-      const uint4 val = stg[stg_index(lane, uu)];
-      const uint32_t w[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-        v[uu * 8 + 2 * j] += f.x;
-        v[uu * 8 + 2 * j + 1] += f.y;
-      }
-    }
-    __syncwarp();
-  }
-}
-
-
 // Diagnostics (R3D_TC_DEBUG bit 32 / r3d_debug_tc_trace): CTA 0 records SM clock stamps per tile for its producer (role 0),
 // MMA thread (role 1) and first epilogue warp (role 2): [role][tile index < 64][event < 8].
 constexpr int kTraceTiles = 64, kTraceEvents = 8;

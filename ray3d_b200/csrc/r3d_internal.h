@@ -70,6 +70,27 @@ struct GemmOpDev {
   GemmProb prob[kMaxProb];
 };
 
+// ---- chained tail launch (r3d_tail_tc.cu) -----------------------------------------------------------------
+// Every GEMM with ONE row per window -- the top of the temporal tree, shrink, GlobalInfo, FuseBlocks, Integration
+// (rie.py:99-105, 159-169, 362-414) -- runs in a single persistent kernel: its work units (128-column tiles of every op,
+// in dependency order) are claimed dynamically, and a unit starts as soon as the units that produce its input rows
+// have landed (per (op, problem, row group) completion counters), instead of one under-filled launch per layer.
+constexpr int kMaxTailOps = 24;
+constexpr int kMaxDeps = 4;
+constexpr int kTailN = 128;      // tile width of every unit
+struct MultiOpDev {
+  int32_t nops, m_groups_cap;
+  uint32_t* done;                                  // [nops * kMaxProb][m_groups_cap] arrivals, zeroed before every forward
+  uint32_t* sched;                                 // the launch's work-unit counter (zeroed with it)
+  int32_t unit0[kMaxTailOps + 1];                  // units PER ROW GROUP of the ops before op i; op i's first unit = unit0[i] * row groups
+  int32_t op_index[kMaxTailOps];                   // index into the plan's op / tensor-map arrays
+  uint8_t nprob[kMaxTailOps];
+  uint8_t ntiles[kMaxTailOps][kMaxProb];           // column tiles per problem
+  uint8_t ndep[kMaxTailOps][kMaxProb];
+  int16_t dep[kMaxTailOps][kMaxProb][kMaxDeps];    // counter rows (local op * kMaxProb + problem) a unit of (op, problem) waits for;
+                                                   // a row is complete at ntiles x 2 store threads x CTAs-per-tile arrivals
+};
+
 // ---- input stage --------------------------------------------------------------------------------
 struct EmbedDev {
   const float* w1;   // [mid][ext]  BN folded
@@ -141,6 +162,13 @@ cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h_op, const v
                            cudaStream_t s);
 int tc_build_tmaps(const GemmOpDev& h_op, int precision, int64_t cap_rows, void* h_tmaps_out /* kMaxProb*4 maps */);
 cudaError_t tc_configure();
+cudaError_t tail_configure();
+int tc_num_sms();
+// one launch for every op listed in `mo` (device copy d_mo); ops / tensor maps are the plan's arrays
+cudaError_t launch_tail_tc(const GemmOpDev* d_ops, const void* d_tmaps, const MultiOpDev* d_mo, const MultiOpDev& h_mo, int M, int precision,
+                           cudaStream_t s);
+inline bool tail_uses_pairs(int M) { return (M + 127) / 128 >= 2; }           // 2-SM (256-row) units whenever there are >= 2 row tiles
+inline int tail_row_groups(int M) { const int t = (M + 127) / 128; return tail_uses_pairs(M) ? (t + 1) / 2 : t; }
 void tc_trace_arm(int launches_from_now);              // diagnostics: per-tile clock trace of one GEMM launch
 cudaError_t tc_trace_read(long long* out, int cap);     // 3 roles x 64 tiles x 8 events
 constexpr int kTmapsPerProb = 6 + 2 * kMaxDst + 4;   // A hi/lo, W hi/lo, W hi/lo (half tile), {hi, lo} store maps per destination, W2 hi/lo full + half

@@ -195,6 +195,13 @@ struct r3d_plan {
   // optional per-launch timing (r3d_plan_set_profiling): ring of event sets, one per forward chunk
   bool profiling = false;
   bool use_side_stream = true;
+  // chained tail launch (r3d_tail_tc.cu): the ops with one row per window run as ONE kernel
+  bool tail_fusion = true;                            // option "tail_fusion"
+  std::vector<int> tail_ops;                          // plan op indices in unit order (empty: every op is its own launch)
+  MultiOpDev tail{};                                  // host copy; the device copy lives in the descriptor slab
+  size_t off_tail = 0, off_done = 0, zero_bytes = 0;
+  struct Launch { std::string name; std::vector<int> ops; bool tail; };
+  std::vector<Launch> launches;                       // GEMM launches of one forward, in main-stream order (side-stream ops included)
   std::vector<int> flip_in, flip_out;                 // joint permutations of the flip augmentation (empty: not set)
   std::vector<cudaEvent_t> prof_ev;                   // [kProfRing][nops + 3]
   int prof_runs = 0;
@@ -436,7 +443,7 @@ struct Folder {
   // conv weight (n, cin, w) [+ BN]  ->  [n_pad][k_pad] with column = tap*cin + c
   PackedLayer conv(const std::string& wkey, int n, int cin, int w, const std::string& bnpre, const std::string& biaskey) const {
     PackedLayer pl;
-    pl.n = n; pl.k = cin * w; pl.n_pad = round_up(n, 16); pl.k_pad = round_up(pl.k, kKAlign);
+    pl.n = n; pl.k = cin * w; pl.n_pad = n < kTailN ? kTailN : round_up(n, 16); pl.k_pad = round_up(pl.k, kKAlign);   // narrow heads: one 128-column unit
     pl.w.assign((size_t)pl.n_pad * pl.k_pad, 0.f); pl.b.assign(pl.n_pad, 0.f);
     std::vector<double> sc(n, 1.0), sh(n, 0.0);
     if (!bnpre.empty()) bn(bnpre, n, sc, sh);
@@ -741,6 +748,92 @@ static void build_graph(r3d_plan* p) {
   }
 }
 
+// Which ops form the chained tail launch (r3d_tail_tc.cu), in which order their units are claimed, and which earlier
+// (op, problem) pairs each (op, problem) reads from.  Host only; pointers are resolved in bind_workspace.
+static void plan_tail(r3d_plan* p) {
+  p->tail_ops.clear();
+  p->launches.clear();
+  memset(&p->tail, 0, sizeof(p->tail));
+  const int nops = (int)p->ops.size();
+  bool ok = p->tail_fusion && p->cfg.precision != R3D_PREC_FP32;
+  std::vector<int> order;
+  if (ok) {
+    // main chain: the maximal suffix of one-row ops (a fused conv pair keeps its own launch); side chain: all of it
+    int first = nops;
+    for (int i = nops - 1; i >= 0; --i) {
+      if (p->ops[i].side) continue;
+      if (p->ops[i].dev.rows_per_seq != 1 || p->ops[i].dev.fused2) break;
+      first = i;
+    }
+    std::vector<int> mains, sides;
+    for (int i = 0; i < nops; ++i) {
+      if (p->ops[i].side) { ok = ok && p->ops[i].dev.rows_per_seq == 1; sides.push_back(i); }
+      else if (i >= first) mains.push_back(i);
+    }
+    // the independent GlobalInfo chain is interleaved with the dependent top of the tree; all of it precedes the op that joins
+    size_t a = 0, b = 0;
+    while (a < mains.size() && !p->ops[mains[a]].join_before) {
+      order.push_back(mains[a++]);
+      if (b < sides.size()) order.push_back(sides[b++]);
+    }
+    while (b < sides.size()) order.push_back(sides[b++]);
+    while (a < mains.size()) order.push_back(mains[a++]);
+    ok = ok && order.size() >= 2 && order.size() <= (size_t)kMaxTailOps && !mains.empty();
+    for (size_t li = 0; ok && li < order.size(); ++li) {
+      const OpHost& op = p->ops[order[li]];
+      for (int q = 0; q < op.dev.nprob; ++q) {
+        const PackedLayer& l = p->layers.at(op.bind[q].layer);
+        ok = ok && l.n_pad % kTailN == 0 && l.n_pad / kTailN <= 255 && l.k_pad % kKAlign == 0;
+      }
+    }
+  }
+  MultiOpDev& mo = p->tail;
+  if (ok) {
+    mo.nops = (int)order.size();
+    for (int li = 0; ok && li < mo.nops; ++li) {
+      const OpHost& op = p->ops[order[li]];
+      mo.op_index[li] = order[li];
+      mo.nprob[li] = (uint8_t)op.dev.nprob;
+      int per_m = 0;
+      for (int q = 0; q < op.dev.nprob; ++q) {
+        mo.ntiles[li][q] = (uint8_t)(p->layers.at(op.bind[q].layer).n_pad / kTailN);
+        per_m += mo.ntiles[li][q];
+        // producers: for every matrix this problem reads (operand, residual) and every column offset written into it, the
+        // LAST earlier (op, problem) of the launch that writes there (activation buffers are recycled along a chain)
+        std::map<std::pair<int, int>, int> writer;                   // (matrix, column) -> counter row
+        for (int lj = 0; lj < li; ++lj) {
+          const OpHost& pj = p->ops[order[lj]];
+          for (int r = 0; r < pj.dev.nprob; ++r)
+            for (auto& d : pj.bind[r].dst)
+              if (d.first == op.bind[q].a || (op.bind[q].res >= 0 && d.first == op.bind[q].res)) writer[{d.first, d.second}] = lj * kMaxProb + r;
+        }
+        std::vector<int> rows;
+        for (auto& kv : writer)
+          if (std::find(rows.begin(), rows.end(), kv.second) == rows.end()) rows.push_back(kv.second);
+        int nd = 0;
+        for (int row : rows) {
+          if (nd == kMaxDeps) { ok = false; break; }
+          mo.dep[li][q][nd++] = (int16_t)row;
+        }
+        mo.ndep[li][q] = (uint8_t)nd;
+      }
+      mo.unit0[li + 1] = mo.unit0[li] + per_m;
+    }
+  }
+  if (ok) p->tail_ops = order;
+  else memset(&mo, 0, sizeof(mo));
+  // the GEMM launches of one forward
+  std::vector<char> in_tail(nops, 0);
+  for (int i : p->tail_ops) in_tail[i] = 1;
+  bool tail_listed = false;
+  for (int i = 0; i < nops; ++i) {
+    if (!in_tail[i]) { p->launches.push_back({p->ops[i].name, {i}, false}); continue; }
+    if (tail_listed || p->ops[i].side) continue;
+    tail_listed = true;
+    p->launches.push_back({"tail[" + p->ops[p->tail_ops.front()].name + " .. " + p->ops[p->tail_ops.back()].name + "]", p->tail_ops, true});
+  }
+}
+
 static int pick_n_tile(int n_pad) {
   for (int t : {256, 128, 64, 32, 16})
     if (n_pad % t == 0) return t;
@@ -775,6 +868,7 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
     pack_fcblock(p, 1, "Integration", p->feat_trj, 3, 1);
   }
   build_graph(p);
+  plan_tail(p);
   // weight slab layout
   const int prec = p->cfg.precision;
   size_t off = 0;
@@ -844,7 +938,26 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
       j += std::string(d ? "," : "") + "[" + std::to_string(p->emb_binds[e].dst[d].first) + "," + std::to_string(p->emb_binds[e].dst[d].second) + "]";
     j += "]}";
   }
-  j += "],\"ops\":[";
+  j += "],\"launches\":[";
+  for (size_t k = 0; k < p->launches.size(); ++k) {
+    j += std::string(k ? "," : "") + "{\"name\":\"" + p->launches[k].name + "\",\"tail\":" + (p->launches[k].tail ? "1" : "0") + ",\"ops\":[";
+    for (size_t q = 0; q < p->launches[k].ops.size(); ++q) j += std::string(q ? "," : "") + std::to_string(p->launches[k].ops[q]);
+    j += "]}";
+  }
+  j += "],\"tail\":{\"unit0\":[";
+  for (int i = 0; i <= p->tail.nops && p->tail.nops > 0; ++i) j += std::string(i ? "," : "") + std::to_string(p->tail.unit0[i]);
+  j += "],\"deps\":[";                               // per tail op, per problem: [local producer op, producer problem] pairs
+  for (int i = 0; i < p->tail.nops; ++i) {
+    j += std::string(i ? "," : "") + "[";
+    for (int q = 0; q < p->tail.nprob[i]; ++q) {
+      j += std::string(q ? "," : "") + "[";
+      for (int d = 0; d < p->tail.ndep[i][q]; ++d)
+        j += std::string(d ? "," : "") + "[" + std::to_string(p->tail.dep[i][q][d] / kMaxProb) + "," + std::to_string(p->tail.dep[i][q][d] % kMaxProb) + "]";
+      j += "]";
+    }
+    j += "]";
+  }
+  j += "]},\"ops\":[";
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const OpHost& op = p->ops[i];
     char sl[32];
@@ -880,7 +993,7 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
 extern "C" R3D_API int64_t r3d_plan_weight_bytes(const r3d_plan* p) { return p ? (int64_t)p->weight_bytes : 0; }
 extern "C" R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* p) { return p ? (int64_t)p->ws_bytes : 0; }
 extern "C" R3D_API int r3d_plan_receptive_field(const r3d_plan* p) { return p ? p->T : 0; }
-extern "C" R3D_API int r3d_plan_kernel_launches(const r3d_plan* p) { return p ? (int)p->ops.size() + 2 : 0; }
+extern "C" R3D_API int r3d_plan_kernel_launches(const r3d_plan* p) { return p ? (int)p->launches.size() + 2 : 0; }
 extern "C" R3D_API int64_t r3d_plan_graph_launches(const r3d_plan* p) { return p ? (int64_t)p->graph_launches : 0; }
 
 // ---- device upload -------------------------------------------------------------------------------
@@ -998,7 +1111,10 @@ extern "C" R3D_API int r3d_plan_upload(r3d_plan* p, int device) {
   CUDA_TRY(cudaMemcpy(p->d_weights, slab.data(), p->weight_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaDeviceSynchronize());   // (same: the weights must have landed before any non-blocking stream reads them)
   CUDA_TRY(prologue_configure(200 * 1024 + 1024));
-  if (prec != R3D_PREC_FP32) CUDA_TRY(tc_configure());
+  if (prec != R3D_PREC_FP32) {
+    CUDA_TRY(tc_configure());
+    CUDA_TRY(tail_configure());
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
   {   // experiment knobs: R3D_SIDE_STREAM=0 serialises the GlobalInfo chain; R3D_SIDE_PRIO=-1/0/1 sets its stream priority
@@ -1122,7 +1238,9 @@ static int bind_workspace(r3d_plan* p, int cap) {
     // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
     bool tile_heuristic = true;
     if (const char* env = exp_env("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
-    if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
+    const bool in_tail = std::find(p->tail_ops.begin(), p->tail_ops.end(), (int)(&op - p->ops.data())) != p->tail_ops.end();
+    if (in_tail) ntile = kTailN;                 // the chained tail launch works in 128-column units
+    else if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
       const int64_t m_tiles = ((int64_t)cap * op.dev.rows_per_seq + 127) / 128;
       auto cost = [&](int bn) {
         int64_t tiles = 0;
@@ -1186,6 +1304,10 @@ static int bind_workspace(r3d_plan* p, int cap) {
   p->off_asm = take(sizeof(AssembleDev));
   p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
   p->off_sched = take(nops * r3d_plan::kSchedStride);                    // one work-unit counter per GEMM launch, 128 bytes apart
+  const int m_groups_cap = (cap + 127) / 128;
+  p->off_done = take((size_t)std::max(1, p->tail.nops) * kMaxProb * m_groups_cap * sizeof(uint32_t));   // (contiguous with the counters: one memset)
+  p->zero_bytes = off - p->off_sched;
+  p->off_tail = take(sizeof(MultiOpDev));
   const size_t off_map = take(p->a0_src.size() * sizeof(int32_t));
   CUDA_TRY(cudaMalloc(&p->d_desc, off));
   pd.a0_off = reinterpret_cast<const int32_t*>(p->d_desc + off_map);
@@ -1201,6 +1323,12 @@ static int bind_workspace(r3d_plan* p, int cap) {
   for (size_t i = 0; i < nops; ++i) {
     p->ops[i].dev.sched = reinterpret_cast<uint32_t*>(p->d_desc + p->off_sched + i * r3d_plan::kSchedStride);
     memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
+  }
+  if (p->tail.nops > 0) {
+    p->tail.m_groups_cap = m_groups_cap;
+    p->tail.done = reinterpret_cast<uint32_t*>(p->d_desc + p->off_done);
+    p->tail.sched = reinterpret_cast<uint32_t*>(p->d_desc + p->off_sched + (size_t)p->tail_ops.front() * r3d_plan::kSchedStride);
+    memcpy(h.data() + p->off_tail, &p->tail, sizeof(MultiOpDev));
   }
   memcpy(h.data() + p->off_pro, &pd, sizeof(pd));
   memcpy(h.data() + p->off_asm, &ad, sizeof(ad));
@@ -1245,7 +1373,7 @@ static InputSpec advance(const InputSpec& in, int64_t b0) {
 static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, float* sum, int batch_in, cudaStream_t s, bool tta = false) {
   const int batch = tta ? 2 * batch_in : batch_in;
   const int prec = p->cfg.precision;
-  const int nl = (int)p->ops.size() + 2, nev = 2 * nl;      // start/end event per launch
+  const int nl = (int)p->launches.size() + 2, nev = 2 * nl;      // start/end event per launch
   cudaEvent_t* ev = nullptr;
   if (p->profiling) {
     if (p->prof_ev.empty()) {
@@ -1256,43 +1384,49 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
     ++p->prof_runs;
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
-  if (prec != R3D_PREC_FP32)   // work-unit counters of the launches below (claimed by their CTAs with atomicAdd)
-    CUDA_TRY(cudaMemsetAsync(p->d_desc + p->off_sched, 0, p->ops.size() * r3d_plan::kSchedStride, s));
+  if (prec != R3D_PREC_FP32)   // work-unit counters of the launches below (claimed by their CTAs with atomicAdd) + the tail's completion counters
+    CUDA_TRY(cudaMemsetAsync(p->d_desc + p->off_sched, 0, p->zero_bytes, s));
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, in, batch, tta ? batch_in : batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
   // fork: the GlobalInfo chain only depends on the input stage and runs on the side stream, filling the SMs the
-  // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.
+  // (small-M) upper levels of the temporal tree leave idle; it joins before the first Integration GEMM.  (With the
+  // chained tail launch that chain is part of the tail kernel's unit sequence instead: no side stream.)
   // per-launch timing serialises the launches on one stream: a side-stream launch's start/end events would also span the
   // time it spends waiting for SMs held by the main stream's kernels
   const bool use_side = p->use_side_stream && !p->profiling;
   bool forked = false, fork_recorded = false;
   if (use_side) {
-    for (const OpHost& oh : p->ops) fork_recorded |= oh.side;
+    for (const auto& L : p->launches) fork_recorded |= !L.tail && p->ops[L.ops[0]].side;
     if (fork_recorded) CUDA_TRY(cudaEventRecord(p->ev_fork, s));   // right after the input stage, before any GEMM is enqueued
   }
-  for (size_t i = 0; i < p->ops.size(); ++i) {
+  const GemmOpDev* d_ops = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops);
+  for (size_t k = 0; k < p->launches.size(); ++k) {
+    const auto& L = p->launches[k];
+    const size_t i = (size_t)L.ops[0];
     const OpHost& oh = p->ops[i];
-    const GemmOpDev* d_op = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops) + i;
-    const int M = batch * oh.dev.rows_per_seq;
     cudaStream_t st = s;
-    if (use_side && oh.side) {
+    if (!L.tail && use_side && oh.side) {
       if (!forked) {
         CUDA_TRY(cudaStreamWaitEvent(p->s_side, p->ev_fork, 0));
         forked = true;
       }
       st = p->s_side;
     }
-    if (use_side && oh.join_before && forked) {
+    bool joins = false;
+    for (int j : L.ops) joins |= p->ops[j].join_before;
+    if (use_side && joins && forked) {
       CUDA_TRY(cudaEventRecord(p->ev_join, p->s_side));
       CUDA_TRY(cudaStreamWaitEvent(s, p->ev_join, 0));
       forked = false;
     }
-    if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (i + 1)], st));
-    if (prec == R3D_PREC_FP32)
-      CUDA_TRY(launch_gemm_ffma(d_op, oh.dev, M, st));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (k + 1)], st));
+    if (L.tail)
+      CUDA_TRY(launch_tail_tc(d_ops, p->d_desc + p->off_tmaps, reinterpret_cast<const MultiOpDev*>(p->d_desc + p->off_tail), p->tail, batch, prec, st));
+    else if (prec == R3D_PREC_FP32)
+      CUDA_TRY(launch_gemm_ffma(d_ops + i, oh.dev, batch * oh.dev.rows_per_seq, st));
     else
-      CUDA_TRY(launch_gemm_tc(d_op, oh.dev, p->d_desc + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes, M, prec, st));
-    if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (i + 1) + 1], st));
+      CUDA_TRY(launch_gemm_tc(d_ops + i, oh.dev, p->d_desc + p->off_tmaps + i * kMaxProb * kTmapsPerProb * kTmapBytes, batch * oh.dev.rows_per_seq, prec, st));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (k + 1) + 1], st));
   }
   if (forked) {
     CUDA_TRY(cudaEventRecord(p->ev_join, p->s_side));
@@ -1757,7 +1891,11 @@ extern "C" R3D_API int r3d_plan_set_option(r3d_plan* p, const char* name, int32_
   else if (k == "lanes") p->use_lanes = value >= 2;
   else if (k == "side_stream") both([&](r3d_plan* q) { q->use_side_stream = value != 0; });
   else if (k == "host_chunk") p->host_chunk = std::max(0, (int)value);
-  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk)", name);
+  else if (k == "tail_fusion") {
+    if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "tail_fusion must be set before r3d_plan_finalize");
+    p->tail_fusion = value != 0;
+  }
+  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion)", name);
   return R3D_OK;
 }
 
@@ -1772,7 +1910,7 @@ extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
 extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   std::lock_guard<std::mutex> lk(*p->mu);
-  const int nl = (int)p->ops.size() + 2, nev = 2 * nl;
+  const int nl = (int)p->launches.size() + 2, nev = 2 * nl;
   if (n_launches) *n_launches = nl;
   const int runs = std::min(p->prof_runs, kProfRing);
   if (n_runs) *n_runs = runs;
@@ -1793,10 +1931,10 @@ extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t
 
 extern "C" R3D_API const char* r3d_plan_launch_name(const r3d_plan* p, int32_t i) {
   if (!p) return "";
-  const int nl = (int)p->ops.size() + 2;
+  const int nl = (int)p->launches.size() + 2;
   if (i == 0) return "input_stage";
   if (i == nl - 1) return "output_stage";
-  if (i > 0 && i < nl - 1) return p->ops[i - 1].name.c_str();
+  if (i > 0 && i < nl - 1) return p->launches[i - 1].name.c_str();
   return "";
 }
 

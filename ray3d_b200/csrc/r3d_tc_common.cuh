@@ -60,6 +60,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Tagged form (the chained tail kernel): the message names the barrier kind and the waiter's progress.
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag, int info) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("r3d tail_tc: mbarrier timeout tag %d info %d (block %d thread %d)\n", tag, info, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // Same with cluster-scope acquire: the waiter reads data another CTA of the cluster wrote before its (release.cluster)
 // arrival -- the tile ids the leader CTA's scheduler stores into the peer's queue.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -92,6 +103,16 @@ __device__ __forceinline__ void st_shared_cluster_u32(const volatile void* p, ui
       "r"(rank), "r"(v)
       : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders the generic proxy (ld/st/atomics of this thread, observed writes) with the async proxy (TMA loads/stores), all spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // activations: streamed once
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // weights: re-read by every tile of the problem
@@ -268,5 +289,64 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int n, int m = TBM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// ---- epilogue helpers -------------------------------------------------------------------------------
+// Per-warp staging tile in shared memory: 32 rows x 64 bytes (one 32-column bf16 chunk), 16-byte units
+// XOR-swizzled so that both the row-per-thread access and the 4-lanes-per-row access are conflict free.
+__device__ __forceinline__ int stg_index(int row, int unit) { return row * 4 + (unit ^ ((row >> 1) & 3)); }
+
+// registers (thread = row, 32 bf16 packed in w[16]) -> staging tile in the 64B-swizzle layout the TMA store expects
+__device__ __forceinline__ void stage_write(uint4* stg, const uint32_t (&w)[16], int lane) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) stg[stg_index(lane, u)] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+}
+
+// Residual tile of one 32x32 chunk.  Loads are coalesced (4 lanes x 16 B per row) and *issued one chunk ahead*
+// (software pipelining in registers), so their HBM/L2 latency overlaps the previous chunk's math and stores.
+struct ResidualRegs {
+  uint4 h[4], l[4];
+};
+// COHERENT: the residual was written earlier in this same launch by another SM (the chained tail kernel): read it
+// through L2 (ld.global.cg) -- the non-coherent path may serve a stale L1 line of a recycled activation buffer.
+template <bool COHERENT = false>
+__device__ __forceinline__ void residual_issue(ResidualRegs& rr, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int col, int lane,
+                                               int m_base, int M) {
+  const int u = lane & 3;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int row = m_base + pass * 8 + (lane >> 2);
+    rr.h[pass] = make_uint4(0, 0, 0, 0);
+    rr.l[pass] = make_uint4(0, 0, 0, 0);
+    if (row < M) {
+      const int64_t o = (int64_t)row * ld + col + u * 8;
+      rr.h[pass] = COHERENT ? __ldcg(reinterpret_cast<const uint4*>(hi + o)) : __ldg(reinterpret_cast<const uint4*>(hi + o));
+      if (lo != nullptr) rr.l[pass] = COHERENT ? __ldcg(reinterpret_cast<const uint4*>(lo + o)) : __ldg(reinterpret_cast<const uint4*>(lo + o));
+    }
+  }
+}
+// registers (4 lanes per row) -> swizzled staging tile -> registers (thread = row), accumulated into v[32]
+__device__ __forceinline__ void residual_consume(uint4* stg, const ResidualRegs& rr, bool has_lo, int lane, float (&v)[32]) {
+  const int u = lane & 3;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (plane == 1 && !has_lo) break;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) stg[stg_index(pass * 8 + (lane >> 2), u)] = plane ? rr.l[pass] : rr.h[pass];
+    __syncwarp();
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu) {
+      const uint4 val = stg[stg_index(lane, uu)];
+      const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        v[uu * 8 + 2 * j] += f.x;
+        v[uu * 8 + 2 * j + 1] += f.y;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 
 }  // namespace r3d
