@@ -167,7 +167,9 @@ class Run:
         self.dev = torch.device("cuda", local_rank)
         self.B = wl["batch"]
         self.sp, self.st = synth.make_state_dicts(self.spec)
-        self.lifter = Lifter(self.spec, self.sp, self.st, precision=precision, device=local_rank)
+        # plan build options for A/B runs, e.g. R3D_BENCH_OPTIONS="tail_fusion=0" (default: the library's defaults)
+        opts = {k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("R3D_BENCH_OPTIONS", "").split(",") if kv)}
+        self.lifter = Lifter(self.spec, self.sp, self.st, precision=precision, device=local_rank, options=opts)
         self.sets = []
         for i in range(self.NSETS):
             uv, cam = synth.make_inputs(self.spec, self.B, seed=self.seed(i, rank), res=wl["res"])

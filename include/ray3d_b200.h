@@ -188,7 +188,9 @@ R3D_API int r3d_submit_host(r3d_plan* plan, const r3d_input* in_host, float* pos
 
 /* Result-neutral tuning: "graph_max_batch" (CUDA-graph replay for batches <= n, default 64, 0 off), "lanes" (1 or 2,
  * default 2), "side_stream" (0/1, default 1), "host_chunk" (windows per staged chunk of a host-buffer call, 0 = auto),
- * "bottom_fusion" (0/1, default 1: first layer + first tree level as one kernel). */
+ * and, before r3d_plan_finalize only, "tail_fusion" (0/1, default 0: the one-row layers -- top tree level, shrink,
+ * FuseBlocks, Integration -- as ONE persistent kernel with per-row-group dependency counters instead of one launch per
+ * layer; bit-identical results, measured slower on B200, kept for study) and "tail_width" (128/256, its unit width). */
 R3D_API int r3d_plan_set_option(r3d_plan* plan, const char* name, int32_t value);
 
 /* --- forward: replaces nn.Module.forward(x, param) ------------------------------------------------

@@ -84,6 +84,7 @@ EXPORTS = {
 # only in trace builds (R3D_BUILD_TRACE=1): scripts/tile_trace.py
 OPTIONAL_EXPORTS = {
     "r3d_debug_tc_trace": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.c_int32]),
+    "r3d_debug_tail_stats": (C.c_int, [C.POINTER(C.c_uint64)]),      # R3D_BUILD_EXPERIMENTS=1 builds
 }
 
 SRC_RAYS, SRC_UV = 0, 1

@@ -887,6 +887,14 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
       rc = encode_2d(wm + 3, precision == R3D_PREC_BF16X3 ? g.w2_1 : nullptr, (uint64_t)g.K2, 256, (uint64_t)g.K2, 128);
       if (rc) return rc;
     }
+    if (h.n_tile_tail > 0) {   // W half tiles at the chained tail launch's unit width (r3d_tail_tc.cu)
+      if (g.n_pad % h.n_tile_tail) return -7;
+      rc = encode_2d(out + p * kTmapsPerProb + kTmapTailW, g.w0, (uint64_t)g.K, (uint64_t)g.n_pad, (uint64_t)g.K, (uint32_t)h.n_tile_tail / 2);
+      if (rc) return rc;
+      rc = encode_2d(out + p * kTmapsPerProb + kTmapTailW + 1, precision == R3D_PREC_BF16X3 ? g.w1 : nullptr, (uint64_t)g.K, (uint64_t)g.n_pad,
+                     (uint64_t)g.K, (uint32_t)h.n_tile_tail / 2);
+      if (rc) return rc;
+    }
     if (bn >= 32) {   // half-tile W maps for the 2-SM variant
       rc = encode_2d(out + p * kTmapsPerProb + 4, g.w0, (uint64_t)g.K, (uint64_t)g.n_pad, (uint64_t)g.K, (uint32_t)bn / 2);
       if (rc) return rc;

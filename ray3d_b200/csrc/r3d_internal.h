@@ -65,7 +65,7 @@ struct GemmOpDev {
   int32_t fused2;        // 1: every problem carries a second weight matrix (see GemmProb::w2_0)
   int32_t flags;         // experiments: bit 0 fused pair waits for the whole intermediate before the second GEMM;
                          // bit 1 release (instead of relaxed) remote barrier arrivals
-  int32_t _pad;
+  int32_t n_tile_tail;   // unit width of this op inside the chained tail launch (0: not part of it)
   uint32_t* sched;       // work-unit counter of this launch (zeroed before every forward): CTAs claim units with atomicAdd
   GemmProb prob[kMaxProb];
 };
@@ -85,7 +85,8 @@ struct MultiOpDev {
   int32_t unit0[kMaxTailOps + 1];                  // units PER ROW GROUP of the ops before op i; op i's first unit = unit0[i] * row groups
   int32_t op_index[kMaxTailOps];                   // index into the plan's op / tensor-map arrays
   uint8_t nprob[kMaxTailOps];
-  uint8_t ntiles[kMaxTailOps][kMaxProb];           // column tiles per problem
+  uint8_t width[kMaxTailOps];                      // unit width of the op in 128-column steps (1 or 2)
+  uint8_t ntiles[kMaxTailOps][kMaxProb];           // column tiles (units) per problem
   uint8_t ndep[kMaxTailOps][kMaxProb];
   int16_t dep[kMaxTailOps][kMaxProb][kMaxDeps];    // counter rows (local op * kMaxProb + problem) a unit of (op, problem) waits for;
                                                    // a row is complete at ntiles x 2 store threads x CTAs-per-tile arrivals
@@ -163,16 +164,19 @@ cudaError_t launch_gemm_tc(const GemmOpDev* d_op, const GemmOpDev& h_op, const v
 int tc_build_tmaps(const GemmOpDev& h_op, int precision, int64_t cap_rows, void* h_tmaps_out /* kMaxProb*4 maps */);
 cudaError_t tc_configure();
 cudaError_t tail_configure();
+cudaError_t tail_stats_read(unsigned long long* out, int reset);   // experiment builds: cycle accounting of the chained tail launch
 int tc_num_sms();
 // one launch for every op listed in `mo` (device copy d_mo); ops / tensor maps are the plan's arrays
 cudaError_t launch_tail_tc(const GemmOpDev* d_ops, const void* d_tmaps, const MultiOpDev* d_mo, const MultiOpDev& h_mo, int M, int precision,
                            cudaStream_t s);
-inline bool tail_uses_pairs(int M) { return (M + 127) / 128 >= 2; }           // 2-SM (256-row) units whenever there are >= 2 row tiles
-inline int tail_row_groups(int M) { const int t = (M + 127) / 128; return tail_uses_pairs(M) ? (t + 1) / 2 : t; }
+inline bool tail_uses_pairs(int M) { return M >= 256; }                       // the chained launch works on 256-row units (CTA pairs)
+inline int tail_row_groups(int M) { return (M + 255) / 256; }
 void tc_trace_arm(int launches_from_now);              // diagnostics: per-tile clock trace of one GEMM launch
 cudaError_t tc_trace_read(long long* out, int cap);     // 3 roles x 64 tiles x 8 events
-constexpr int kTmapsPerProb = 6 + 2 * kMaxDst + 4;   // A hi/lo, W hi/lo, W hi/lo (half tile), {hi, lo} store maps per destination, W2 hi/lo full + half
+constexpr int kTmapsPerProb = 6 + 2 * kMaxDst + 4 + 2;   // A hi/lo, W hi/lo, W hi/lo (half tile), {hi, lo} store maps per destination, W2 hi/lo full + half,
+                                                         // W hi/lo half tile at the chained tail launch's unit width
 constexpr int kTmapW2 = 6 + 2 * kMaxDst;
+constexpr int kTmapTailW = kTmapW2 + 4;
 constexpr int kTmapBytes = 128;
 
 }  // namespace r3d

@@ -196,12 +196,14 @@ struct r3d_plan {
   bool profiling = false;
   bool use_side_stream = true;
   // chained tail launch (r3d_tail_tc.cu): the ops with one row per window run as ONE kernel
-  bool tail_fusion = true;                            // option "tail_fusion"
+  bool tail_fusion = false;                           // option "tail_fusion" (off: measured slower than one launch per layer)
+  int tail_width = 128;                               // option "tail_width": unit width of the chained launch (128 or 256 columns)
   std::vector<int> tail_ops;                          // plan op indices in unit order (empty: every op is its own launch)
   MultiOpDev tail{};                                  // host copy; the device copy lives in the descriptor slab
   size_t off_tail = 0, off_done = 0, zero_bytes = 0;
   struct Launch { std::string name; std::vector<int> ops; bool tail; };
-  std::vector<Launch> launches;                       // GEMM launches of one forward, in main-stream order (side-stream ops included)
+  std::vector<Launch> launches, launches_flat;        // GEMM launches of one forward (side-stream ops included): with the chained tail / one per op
+  bool prof_tail = false;                             // which of the two the last profiled forward used
   std::vector<int> flip_in, flip_out;                 // joint permutations of the flip augmentation (empty: not set)
   std::vector<cudaEvent_t> prof_ev;                   // [kProfRing][nops + 3]
   int prof_runs = 0;
@@ -765,19 +767,13 @@ static void plan_tail(r3d_plan* p) {
       if (p->ops[i].dev.rows_per_seq != 1 || p->ops[i].dev.fused2) break;
       first = i;
     }
-    std::vector<int> mains, sides;
-    for (int i = 0; i < nops; ++i) {
-      if (p->ops[i].side) { ok = ok && p->ops[i].dev.rows_per_seq == 1; sides.push_back(i); }
-      else if (i >= first) mains.push_back(i);
-    }
-    // the independent GlobalInfo chain is interleaved with the dependent top of the tree; all of it precedes the op that joins
-    size_t a = 0, b = 0;
-    while (a < mains.size() && !p->ops[mains[a]].join_before) {
-      order.push_back(mains[a++]);
-      if (b < sides.size()) order.push_back(sides[b++]);
-    }
-    while (b < sides.size()) order.push_back(sides[b++]);
-    while (a < mains.size()) order.push_back(mains[a++]);
+    // The GlobalInfo chain (side stream) stays one launch per layer: it only depends on the input stage and runs under
+    // the large launches of the tree, off the critical path.  Inside the chained launch its six dependent layers would sit
+    // in front of Integration.fc_1 (measured: 62 % of the tail kernel's cycles spent waiting for inputs).
+    std::vector<int> mains;
+    for (int i = first; i < nops; ++i)
+      if (!p->ops[i].side) mains.push_back(i);
+    order = mains;
     ok = ok && order.size() >= 2 && order.size() <= (size_t)kMaxTailOps && !mains.empty();
     for (size_t li = 0; ok && li < order.size(); ++li) {
       const OpHost& op = p->ops[order[li]];
@@ -794,9 +790,12 @@ static void plan_tail(r3d_plan* p) {
       const OpHost& op = p->ops[order[li]];
       mo.op_index[li] = order[li];
       mo.nprob[li] = (uint8_t)op.dev.nprob;
-      int per_m = 0;
+      int per_m = 0, width = p->tail_width >= 256 ? 2 : 1;          // 256-column units unless some problem of the op is narrower
+      for (int q = 0; q < op.dev.nprob; ++q)
+        if (p->layers.at(op.bind[q].layer).n_pad % (2 * kTailN)) width = 1;
+      mo.width[li] = (uint8_t)width;
       for (int q = 0; q < op.dev.nprob; ++q) {
-        mo.ntiles[li][q] = (uint8_t)(p->layers.at(op.bind[q].layer).n_pad / kTailN);
+        mo.ntiles[li][q] = (uint8_t)(p->layers.at(op.bind[q].layer).n_pad / (kTailN * width));
         per_m += mo.ntiles[li][q];
         // producers: for every matrix this problem reads (operand, residual) and every column offset written into it, the
         // LAST earlier (op, problem) of the launch that writes there (activation buffers are recycled along a chain)
@@ -822,11 +821,13 @@ static void plan_tail(r3d_plan* p) {
   }
   if (ok) p->tail_ops = order;
   else memset(&mo, 0, sizeof(mo));
-  // the GEMM launches of one forward
+  // the GEMM launches of one forward: with the chained tail launch (batches of >= 256 windows) and one launch per op
   std::vector<char> in_tail(nops, 0);
   for (int i : p->tail_ops) in_tail[i] = 1;
   bool tail_listed = false;
+  p->launches_flat.clear();
   for (int i = 0; i < nops; ++i) {
+    p->launches_flat.push_back({p->ops[i].name, {i}, false});
     if (!in_tail[i]) { p->launches.push_back({p->ops[i].name, {i}, false}); continue; }
     if (tail_listed || p->ops[i].side) continue;
     tail_listed = true;
@@ -1238,9 +1239,11 @@ static int bind_workspace(r3d_plan* p, int cap) {
     // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
     bool tile_heuristic = true;
     if (const char* env = exp_env("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
-    const bool in_tail = std::find(p->tail_ops.begin(), p->tail_ops.end(), (int)(&op - p->ops.data())) != p->tail_ops.end();
-    if (in_tail) ntile = kTailN;                 // the chained tail launch works in 128-column units
-    else if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
+    {
+      const auto it = std::find(p->tail_ops.begin(), p->tail_ops.end(), (int)(&op - p->ops.data()));
+      op.dev.n_tile_tail = it == p->tail_ops.end() ? 0 : kTailN * p->tail.width[it - p->tail_ops.begin()];
+    }
+    if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
       const int64_t m_tiles = ((int64_t)cap * op.dev.rows_per_seq + 127) / 128;
       auto cost = [&](int bn) {
         int64_t tiles = 0;
@@ -1373,14 +1376,17 @@ static InputSpec advance(const InputSpec& in, int64_t b0) {
 static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, float* sum, int batch_in, cudaStream_t s, bool tta = false) {
   const int batch = tta ? 2 * batch_in : batch_in;
   const int prec = p->cfg.precision;
-  const int nl = (int)p->launches.size() + 2, nev = 2 * nl;      // start/end event per launch
+  const bool use_tail = !p->tail_ops.empty() && tail_uses_pairs(batch);      // small batches: one launch per op (narrow tiles)
+  const std::vector<r3d_plan::Launch>& launches = use_tail ? p->launches : p->launches_flat;
+  const int nl = (int)launches.size() + 2, nev = 2 * nl;      // start/end event per launch
   cudaEvent_t* ev = nullptr;
   if (p->profiling) {
+    p->prof_tail = use_tail;
     if (p->prof_ev.empty()) {
-      p->prof_ev.resize((size_t)kProfRing * nev);
+      p->prof_ev.resize((size_t)kProfRing * 2 * (p->ops.size() + 2));
       for (auto& e : p->prof_ev) CUDA_TRY(cudaEventCreate(&e));
     }
-    ev = p->prof_ev.data() + (size_t)(p->prof_runs % kProfRing) * nev;
+    ev = p->prof_ev.data() + (size_t)(p->prof_runs % kProfRing) * 2 * (p->ops.size() + 2);
     ++p->prof_runs;
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
@@ -1396,12 +1402,12 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
   const bool use_side = p->use_side_stream && !p->profiling;
   bool forked = false, fork_recorded = false;
   if (use_side) {
-    for (const auto& L : p->launches) fork_recorded |= !L.tail && p->ops[L.ops[0]].side;
+    for (const auto& L : launches) fork_recorded |= !L.tail && p->ops[L.ops[0]].side;
     if (fork_recorded) CUDA_TRY(cudaEventRecord(p->ev_fork, s));   // right after the input stage, before any GEMM is enqueued
   }
   const GemmOpDev* d_ops = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops);
-  for (size_t k = 0; k < p->launches.size(); ++k) {
-    const auto& L = p->launches[k];
+  for (size_t k = 0; k < launches.size(); ++k) {
+    const auto& L = launches[k];
     const size_t i = (size_t)L.ops[0];
     const OpHost& oh = p->ops[i];
     cudaStream_t st = s;
@@ -1895,7 +1901,11 @@ extern "C" R3D_API int r3d_plan_set_option(r3d_plan* p, const char* name, int32_
     if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "tail_fusion must be set before r3d_plan_finalize");
     p->tail_fusion = value != 0;
   }
-  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion)", name);
+  else if (k == "tail_width") {
+    if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "tail_width must be set before r3d_plan_finalize");
+    p->tail_width = value >= 256 ? 256 : 128;
+  }
+  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion, tail_width)", name);
   return R3D_OK;
 }
 
@@ -1910,14 +1920,14 @@ extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
 extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   std::lock_guard<std::mutex> lk(*p->mu);
-  const int nl = (int)p->launches.size() + 2, nev = 2 * nl;
+  const int nl = (int)(p->prof_tail ? p->launches : p->launches_flat).size() + 2, nev = 2 * nl;
   if (n_launches) *n_launches = nl;
   const int runs = std::min(p->prof_runs, kProfRing);
   if (n_runs) *n_runs = runs;
   if (!ms_out || runs == 0) return R3D_OK;
   std::vector<double> acc(nl, 0.0);
   for (int r = 0; r < runs; ++r) {
-    cudaEvent_t* ev = p->prof_ev.data() + (size_t)r * nev;
+    cudaEvent_t* ev = p->prof_ev.data() + (size_t)r * 2 * (p->ops.size() + 2);
     CUDA_TRY(cudaEventSynchronize(ev[nev - 1]));
     for (int i = 0; i < nl; ++i) {
       float ms = 0.f;
@@ -1931,10 +1941,11 @@ extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t
 
 extern "C" R3D_API const char* r3d_plan_launch_name(const r3d_plan* p, int32_t i) {
   if (!p) return "";
-  const int nl = (int)p->launches.size() + 2;
+  const auto& launches = p->prof_tail ? p->launches : p->launches_flat;
+  const int nl = (int)launches.size() + 2;
   if (i == 0) return "input_stage";
   if (i == nl - 1) return "output_stage";
-  if (i > 0 && i < nl - 1) return p->launches[i - 1].name.c_str();
+  if (i > 0 && i < nl - 1) return launches[i - 1].name.c_str();
   return "";
 }
 
@@ -1966,6 +1977,16 @@ extern "C" R3D_API int r3d_eval_metrics(const float* pred, const float* target, 
 }
 
 // ---- on-device self test: tensor-core GEMM vs FP32 FFMA GEMM -----------------------------------------
+#ifdef R3D_EXPERIMENTS
+// Experiment builds: cycle accounting of the chained tail launch (see g_tail_stats in r3d_tail_tc.cu); resets the counters.
+extern "C" R3D_API int r3d_debug_tail_stats(uint64_t* out8) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "stat word");
+  CUDA_TRY(tail_stats_read(reinterpret_cast<unsigned long long*>(out8), 1));
+  return R3D_OK;
+}
+#endif
+
 #ifdef R3D_TC_TRACE
 // Diagnostics of trace builds only (R3D_BUILD_TRACE=1 python -m ray3d_b200.build --force; scripts/tile_trace.py): out == NULL
 // arms a per-tile SM-clock trace for the tensor-core GEMM launch `arm_after_launches` launches from now; out != NULL

@@ -29,6 +29,8 @@ struct TileDesc {
   int32_t p, m0, n0;
   int32_t tmap0;       // first tensor map of (op, problem)
   int32_t done_idx;    // completion counter of (op, problem, row group)
+  int32_t bn;          // unit width of the op: 128 or 256 columns
+  int32_t _pad;
 };
 static_assert(sizeof(TileDesc) % 8 == 0, "TileDesc is copied word-wise into 8-byte aligned shared memory");
 
@@ -36,22 +38,36 @@ constexpr int TAIL_SQ = 4;                                       // queue depth
 constexpr int kTailDescBytes = 2816;                             // TileDesc queue + store barriers (keeps the staging tiles 1024-byte aligned)
 static_assert(TAIL_SQ * sizeof(TileDesc) + (16 + TAIL_SQ) * 8 <= kTailDescBytes, "descriptor block too small");
 __host__ __device__ constexpr int tail_aux_bytes(int cl) { return 256 + kTailDescBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + EPI_WARPS * 512; }
-__host__ __device__ constexpr int tail_stage_bytes(int nsplit, int cl) { return nsplit * (TBM + kTailN / cl) * TBK * 2; }
+constexpr int kTailMaxN = 256;                                    // widest unit; narrower ops (the heads) use 128 of the W slot
+__host__ __device__ constexpr int tail_stage_bytes(int nsplit, int cl) { return nsplit * (TBM + kTailMaxN / cl) * TBK * 2; }
 __host__ __device__ constexpr int tail_num_stages(int nsplit, int cl) {
   int s = (SMEM_LIMIT - tail_aux_bytes(cl)) / tail_stage_bytes(nsplit, cl);
   return s > 6 ? 6 : s;
 }
 
+// Experiment builds: where the leader CTAs' producer / MMA threads spend their cycles (summed over CTAs):
+// [0] dependency spin, [1] unit-queue slot wait, [2] smem ring slot wait, [3] MMA: operands not yet landed, [4] MMA: accumulator
+// not yet drained, [5] MMA: next unit not yet published, [6] units, [7] kernel cycles per CTA
+__device__ unsigned long long g_tail_stats[8];
+#ifdef R3D_EXPERIMENTS
+#define R3D_STAT_T0() const long long _t0 = clock64()
+#define R3D_STAT_ADD(i) st_acc[i] += clock64() - _t0
+#else
+#define R3D_STAT_T0() do { } while (0)
+#define R3D_STAT_ADD(i) do { } while (0)
+#endif
+
 template <int NSPLIT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev* __restrict__ ops, const CUtensorMap* __restrict__ tmaps,
                                                                    const MultiOpDev* __restrict__ mo, int M) {
-  constexpr int BLOCK_N = kTailN;
+  static_assert(CL == 2, "the chained tail launch runs on CTA pairs (batches of >= 256 windows)");
+  constexpr int MAXN = kTailMaxN;
   constexpr int EW = EPI_WARPS;
   constexpr int STAGES = tail_num_stages(NSPLIT, CL);
-  constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = (BLOCK_N / CL) * TBK * 2;
+  constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = (MAXN / CL) * TBK * 2;     // W slot of a stage (a 128-wide unit fills half of it)
   constexpr int STAGE_BYTES = tail_stage_bytes(NSPLIT, CL);
-  constexpr int TMEM_COLS = 2 * BLOCK_N;                           // two accumulator stages
-  constexpr int CH = 32, NCHUNK = BLOCK_N / CH, COL_SPLIT = 2, CHUNKS_PER_WARP = NCHUNK / COL_SPLIT;
+  constexpr int TMEM_COLS = 2 * MAXN;                              // two accumulator stages
+  constexpr int CH = 32, COL_SPLIT = 2, MAX_CPW = MAXN / CH / COL_SPLIT;       // chunks per warp: bn / 64
   constexpr int EPI_BUFS = CL == 2 ? 2 : 1;                        // staging tile sets per column group (hi + lo each)
   constexpr int SQ = TAIL_SQ;
   auto chunk_index = [](int grp, int cc) { return cc * COL_SPLIT + grp; };
@@ -120,6 +136,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  long long st_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long st_begin = clock64();
+  (void)st_acc; (void)st_begin;
   const int nops = __ldg(&mo->nops);
   const int m_groups = ((M + TBM - 1) / TBM + CL - 1) / CL;        // row groups (CL row tiles each)
   const int total = __ldg(&mo->unit0[nops]) * m_groups;
@@ -154,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
       if (lane == 0) {
         if (leader) {
           tile = next_tile;
-          mbar_wait_tag(&sq_empty[slot], qph ^ 1u, 2, (int)qn);                    // every consumer of both CTAs is done with the slot's previous unit
+          { R3D_STAT_T0(); mbar_wait_tag(&sq_empty[slot], qph ^ 1u, 2, (int)qn); R3D_STAT_ADD(1); }   // every consumer of both CTAs is done with the slot's previous unit
         } else {
           mbar_wait_cluster(&idq_full[slot], qph);
           tile = (int)sq_tile[slot];
@@ -175,6 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
           if (leader) {
             // the unit's input rows: wait until every producing unit of this row group has landed
             const int nd = __ldg(&mo->ndep[oi][p]);
+            R3D_STAT_T0();
             for (int d = 0; d < nd; ++d) {
               const int row = __ldg(&mo->dep[oi][p][d]);
               const uint32_t tgt = (uint32_t)__ldg(&mo->ntiles[row / kMaxProb][row % kMaxProb]) * 2u * CL;   // column tiles x store threads x CTAs
@@ -189,6 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
                 }
               }
             }
+            R3D_STAT_ADD(0);
             if (nd) fence_proxy_async_all();                       // the loads below go through the async proxy
           }
         }
@@ -217,7 +238,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
           td.slope = __ldg(&gop->slope);
           td.p = p;
           td.m0 = (mg * CL + crank) * TBM;
-          td.n0 = nt * BLOCK_N;
+          const int bn = kTailN * (int)__ldg(&mo->width[oi]);
+          td.bn = bn;
+          td.n0 = nt * bn;
           td.tmap0 = (opi * kMaxProb + p) * kTmapsPerProb;
           td.done_idx = (oi * kMaxProb + p) * cap + mg;
         }
@@ -229,25 +252,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
       if (lane == 0) {
         const CUtensorMap* tm = tmaps + td.tmap0;
         const int nkb = td.prob.K / TBK;
-        const int m0 = td.m0, n0 = td.n0;
+        const int m0 = td.m0, n0 = td.n0, bn = td.bn;
+        const uint32_t stage_tx = (uint32_t)(NSPLIT * (A_BYTES + (bn / CL) * TBK * 2));     // bytes this CTA receives per K block
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait_tag(&empty_bar[stage], phase ^ 1, 4, kb);
+          { R3D_STAT_T0(); mbar_wait_tag(&empty_bar[stage], phase ^ 1, 4, kb); R3D_STAT_ADD(2); }
           uint8_t* st = smem + stage * STAGE_BYTES;
           // the operand rows are read again by the unit's sibling column tiles: keep them in L2; weights are shared by all row groups
-          if (CL == 1) {
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(st, tm + 0, &full_bar[stage], kb * TBK, m0, kEvictNormal);
-            if (NSPLIT == 2) tma_load_2d(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, m0, kEvictNormal);
-            tma_load_2d(st + NSPLIT * A_BYTES, tm + 2, &full_bar[stage], kb * TBK, n0, kEvictLast);
-            if (NSPLIT == 2) tma_load_2d(st + 2 * A_BYTES + W_BYTES, tm + 3, &full_bar[stage], kb * TBK, n0, kEvictLast);
-          } else {
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-            const int wrow = n0 + crank * (BLOCK_N / CL);
-            tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, m0, kEvictNormal);
-            if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, m0, kEvictNormal);
-            tma_load_2d_2sm(st + NSPLIT * A_BYTES, tm + 4, &full_bar[stage], kb * TBK, wrow, kEvictLast);
-            if (NSPLIT == 2) tma_load_2d_2sm(st + 2 * A_BYTES + W_BYTES, tm + 5, &full_bar[stage], kb * TBK, wrow, kEvictLast);
-          }
+          // both CTAs' loads complete on the leader's barrier, which the (leader-only) MMA thread waits on
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
+          const int wrow = n0 + crank * (bn / CL);
+          tma_load_2d_2sm(st, tm + 0, &full_bar[stage], kb * TBK, m0, kEvictNormal);
+          if (NSPLIT == 2) tma_load_2d_2sm(st + A_BYTES, tm + 1, &full_bar[stage], kb * TBK, m0, kEvictNormal);
+          tma_load_2d_2sm(st + NSPLIT * A_BYTES, tm + kTmapTailW, &full_bar[stage], kb * TBK, wrow, kEvictLast);
+          if (NSPLIT == 2) tma_load_2d_2sm(st + NSPLIT * A_BYTES + W_BYTES, tm + kTmapTailW + 1, &full_bar[stage], kb * TBK, wrow, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (CL == 2 && !leader) sq_release(slot);                   // the peer's producer counts as a consumer of the slot
@@ -257,24 +274,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N, TBM * CL);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (;;) {
         int slot;
+        R3D_STAT_T0();
         const int tile = sq_pop(slot);
+        R3D_STAT_ADD(5);
         if (tile >= total) break;
+        st_acc[6] += 1;
         const int nkb = tq[slot].prob.K / TBK;
+        const uint32_t idesc = make_idesc(tq[slot].bn, TBM * CL);
         sq_release(slot);                                            // (nothing else of the descriptor is needed here)
-        mbar_wait_tag(&tempty_bar[acc], acc_phase ^ 1, 6, tile);                  // epilogue has drained this accumulator
+        { R3D_STAT_T0(); mbar_wait_tag(&tempty_bar[acc], acc_phase ^ 1, 6, tile); R3D_STAT_ADD(4); }   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * MAXN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait_tag(&full_bar[stage], phase, 5, kb);
+          { R3D_STAT_T0(); mbar_wait_tag(&full_bar[stage], phase, 5, kb); R3D_STAT_ADD(3); }
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + NSPLIT * A_BYTES);
-          const uint64_t a_lo = make_smem_desc(st + A_BYTES), w_lo = make_smem_desc(st + 2 * A_BYTES + W_BYTES);
+          const uint64_t a_lo = make_smem_desc(st + A_BYTES), w_lo = make_smem_desc(st + NSPLIT * A_BYTES + W_BYTES);
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -323,7 +343,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
         bool any_bf = false;
         for (int t = 0; t < pr.ndst; ++t) any_bf |= pr.dst[t].f32 == 0;
         if (any_bf) {
-          for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+          const int cpw = td.bn / (CH * COL_SPLIT);
+          for (int cc = 0; cc < cpw; ++cc) {
             const int n = td.n0 + chunk_index(st, cc) * CH;
             if (n >= pr.N) continue;
             const int b = EPI_BUFS == 2 ? (int)(round & 1) : 0;
@@ -361,12 +382,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr bool BIAS_SMEM = CL == 2;
-    constexpr int PB = CHUNKS_PER_WARP;
+    constexpr int PB = MAX_CPW;
     float pb[PB];
     auto prefetch_bias = [&](const TileDesc& t) {
       const float* bp = t.prob.bias + t.n0;
+      const int cpw = t.bn / (CH * COL_SPLIT);
 #pragma unroll
-      for (int i = 0; i < PB; ++i) pb[i] = __ldg(bp + chunk_index(half, i) * CH + lane);
+      for (int i = 0; i < PB; ++i) pb[i] = i < cpw ? __ldg(bp + chunk_index(half, i) * CH + lane) : 0.f;
     };
     // Every lane observes the slot; it is handed back at the end of the unit.  `block` = false only probes: the next unit
     // is published AFTER its inputs have landed, and those may (transitively) depend on the unit this warp is still
@@ -433,10 +455,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
       tc_fence_after();
       {
         uint32_t r[32];
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAXN);
+        const int cpw = td.bn / (CH * COL_SPLIT);
         tmem_ld32(taddr0 + chunk_index(half, 0) * CH, r);
 #pragma unroll 1
-        for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
+        for (int cc = 0; cc < cpw; ++cc) {
           const int n = td.n0 + chunk_index(half, cc) * CH;
           float bb[CH];
           if (BIAS_SMEM) {
@@ -459,7 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
             const float x = __uint_as_float(r[j]) + bb[j];
             v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
           }
-          if (cc + 1 < CHUNKS_PER_WARP) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r);
+          if (cc + 1 < cpw) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r);
           if (cc > 0) look_ahead(false);
           if (n < pr.N) {                        // warp-uniform
             const int sbuf = EPI_BUFS == 2 ? (int)(sround & 1) : 0;
@@ -469,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
               mbar_wait_tag(&sfree_bar[half * 2 + sbuf], (((EPI_BUFS == 2 ? sround >> 1 : sround) & 1) ^ 1), 9, tile);
             if (has_res) {
               residual_consume(stage_hi, rr, res_lo != nullptr, lane, v);
-              if (cc + 1 < CHUNKS_PER_WARP)
+              if (cc + 1 < cpw)
                 residual_issue<true>(rr, res_hi, res_lo, pr.res.ld, pr.res_col + td.n0 + chunk_index(half, cc + 1) * CH, lane, m_base, M);
             }
             if (any_f32 && row_ok) {             // network outputs (tiny): direct masked stores
@@ -517,6 +540,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
     __syncwarp();
   }
 
+#ifdef R3D_EXPERIMENTS
+  if (leader && lane == 0 && (warp == 0 || warp == 1)) {
+    if (warp == 1) st_acc[7] = clock64() - st_begin;
+    for (int i = 0; i < 8; ++i)
+      if (st_acc[i]) atomicAdd(&g_tail_stats[i], (unsigned long long)st_acc[i]);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();
@@ -528,45 +558,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
 }
 
 // ---- host side --------------------------------------------------------------------------------------
+cudaError_t tail_stats_read(unsigned long long* out, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_tail_stats, sizeof(g_tail_stats));
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(g_tail_stats, z, sizeof(z));
+  }
+  return e;
+}
+
 template <int NS, int CL>
 static constexpr int tail_smem_bytes() { return tail_num_stages(NS, CL) * tail_stage_bytes(NS, CL) + tail_aux_bytes(CL); }
 
 cudaError_t tail_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(tail_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes<1, 1>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(tail_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes<1, 2>())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(tail_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes<2, 1>())) != cudaSuccess) return e;
   return cudaFuncSetAttribute(tail_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes<2, 2>());
 }
 
 template <int NS>
-static cudaError_t launch_tail(const GemmOpDev* d_ops, const CUtensorMap* tm, const MultiOpDev* d_mo, int units, int M, bool pair, cudaStream_t s) {
+static cudaError_t launch_tail(const GemmOpDev* d_ops, const CUtensorMap* tm, const MultiOpDev* d_mo, int units, int M, cudaStream_t s) {
   const int sms = tc_num_sms();
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(TC_THREADS);
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
-  int na = 0;
-  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[na].val.programmaticStreamSerializationAllowed = 1;
-  ++na;
-  if (!pair) {
-    cfg.gridDim = dim3(units < sms ? units : sms);
-    cfg.dynamicSmemBytes = tail_smem_bytes<NS, 1>();
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, tail_tc_kernel<NS, 1>, d_ops, tm, d_mo, M);
-  }
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   const int max_clusters = sms / 2;
   cfg.gridDim = dim3(2 * (units < max_clusters ? units : max_clusters));
   cfg.dynamicSmemBytes = tail_smem_bytes<NS, 2>();
-  attr[na].id = cudaLaunchAttributeClusterDimension;
-  attr[na].val.clusterDim.x = 2;
-  attr[na].val.clusterDim.y = 1;
-  attr[na].val.clusterDim.z = 1;
-  ++na;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = na;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, tail_tc_kernel<NS, 2>, d_ops, tm, d_mo, M);
 }
 
@@ -574,10 +601,10 @@ cudaError_t launch_tail_tc(const GemmOpDev* d_ops, const void* d_tmaps, const Mu
                            cudaStream_t s) {
   if (M <= 0 || h_mo.nops <= 0) return cudaSuccess;
   if (tc_num_sms() <= 0) return cudaErrorNotReady;
-  const bool pair = tail_uses_pairs(M);
+  if (!tail_uses_pairs(M)) return cudaErrorInvalidValue;         // small batches keep one launch per op (narrower tiles)
   const int units = h_mo.unit0[h_mo.nops] * tail_row_groups(M);
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(d_tmaps);
-  return precision == R3D_PREC_BF16X3 ? launch_tail<2>(d_ops, tm, d_mo, units, M, pair, s) : launch_tail<1>(d_ops, tm, d_mo, units, M, pair, s);
+  return precision == R3D_PREC_BF16X3 ? launch_tail<2>(d_ops, tm, d_mo, units, M, s) : launch_tail<1>(d_ops, tm, d_mo, units, M, s);
 }
 
 }  // namespace r3d

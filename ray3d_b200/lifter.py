@@ -38,7 +38,7 @@ class Lifter:
     """
 
     def __init__(self, spec: NetSpec, state_pos: Optional[Mapping[str, object]], state_trj: Optional[Mapping[str, object]],
-                 precision: str = DEFAULT_PRECISION, device: Optional[int] = None):
+                 precision: str = DEFAULT_PRECISION, device: Optional[int] = None, options: Optional[Mapping[str, int]] = None):
         nets = (_capi.NET_POS if state_pos is not None else 0) | (_capi.NET_TRJ if state_trj is not None else 0)
         if nets == 0:
             raise ValueError("need at least one state_dict")
@@ -49,6 +49,8 @@ class Lifter:
             self.plan.load_state(_capi.NET_POS, state_pos)
         if state_trj is not None:
             self.plan.load_state(_capi.NET_TRJ, state_trj)
+        for k, v in (options or {}).items():      # build-time tuning (r3d_plan_set_option), e.g. {"tail_fusion": 0}
+            self.plan.set_option(k, v)
         self.plan.finalize()
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: ray3d_b200 computes the lifting path on the GPU only")

@@ -180,3 +180,22 @@ def test_inputs_on_the_wrong_device_or_of_the_wrong_kind_are_refused():
         with pytest.raises(RuntimeError):
             lf.forward_rays(x.to("cuda:1"), torch.zeros(2, 2, device="cuda:1"))
         assert torch.cuda.current_device() == 0                      # the plan never leaves the caller on another device
+
+
+@pytest.mark.parametrize("stage", [1, 3])
+def test_chained_tail_launch_is_bit_identical(stage):
+    """Option tail_fusion: the one-row layers (top tree level, shrink, FuseBlocks, Integration; rie.py:94-105, 388-414) as ONE
+    persistent kernel whose work units wait on per-(op, problem, row group) completion counters.  Same tile code, same
+    arithmetic: outputs must equal the one-launch-per-layer form bit for bit (both unit widths, ragged last row group)."""
+    spec = NetSpec(filter_widths=(3, 3, 3), stage=stage)
+    sp, st = synth.make_state_dicts(spec)
+    base = Lifter(spec, sp, st, precision="bf16x3")
+    for width in (128, 256):
+        lf = Lifter(spec, sp, st, precision="bf16x3", options={"tail_fusion": 1, "tail_width": width})
+        assert any(L["tail"] for L in lf.plan.describe()["launches"])
+        for B in (700, 256, 300, 40):                     # < 256 windows: the plan falls back to one launch per op
+            uv, cam = synth.make_inputs(spec, B, seed=90 + B)
+            uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
+            a, b = lf.forward_uv(uvc, camc), base.forward_uv(uvc, camc)
+            assert all(torch.equal(x, y) for x, y in zip(a, b)), (stage, width, B)
+        del lf
