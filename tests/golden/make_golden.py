@@ -163,6 +163,59 @@ def main():
     except Exception as e:  # pragma: no cover
         print("eval_data_prepare fixture skipped:", e)
 
+    # flip test-time augmentation: the reference's OWN Trainer.evaluate_core(flip_test=True) (trainer.py:283-405) on one
+    # synthetic video -- eval_data_prepare, the mirrored second forward, un-mirroring, torch.mean, pos += trj,
+    # normalized2world and the five metrics.  The trainer object is built without its constructor (it only wires
+    # config/optimizer state evaluate_core never touches); the camera wrapper records what normalized2world receives.
+    try:
+        from lib.train_val.trainer import Trainer  # noqa: E402  (reference)
+        trng = np.random.Generator(np.random.PCG64(4711))
+        spec = NetSpec(num_joints=17, in_features=3, filter_widths=(3, 3, 3), stage=1)
+        sd_pos, sd_trj = synth.make_state_dicts(spec)
+        F, T = 12, spec.receptive_field
+        uvv = (trng.uniform(0.3, 0.7, size=(F + T - 1, 17, 2)) * 1000)
+        pkt = CameraInfoPacket(P=None, K=cams[2]["K"], R=cams[2]["R"], t=cams[2]["t"], dist_coeff=None, res_w=1000, res_h=1002, undistort=False)
+        rays = pkt.get_cam_ray_given_uv(uvv)[None]                       # (1, F+T-1, 17, 3) float64, like the dataset holds it
+        target = trng.standard_normal(size=(1, F, 17, 3))
+        kps_left, kps_right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+
+        class RecordingCamera:
+            def __init__(self, pk):
+                self.pk, self.Rw2c, self.Tw2c, self.cam_pitch_rad, self.seen = pk, pk.Rw2c, pk.Tw2c, pk.cam_pitch_rad, []
+
+            def normalized2world(self, pt):
+                self.seen.append(np.array(pt, copy=True))
+                return self.pk.normalized2world(pt)
+
+        class OneVideo:
+            def __init__(self, cam):
+                self.cam = cam
+
+            def next_epoch(self):
+                yield self.cam, target.copy(), rays.copy()
+
+        out = {}
+        for tag, dtype in (("32", torch.float32), ("64", torch.float64)):
+            pos, trj = build_reference(spec, sd_pos, sd_trj, dtype)
+            if dtype == torch.float64:                                   # evaluate_core feeds float32 tensors: promote them at the module boundary
+                pos.register_forward_pre_hook(lambda m, a: tuple(t.double() for t in a))
+                trj.register_forward_pre_hook(lambda m, a: tuple(t.double() for t in a))
+            tr = Trainer.__new__(Trainer)
+            tr.pos_model_test, tr.trj_model_test = pos, trj
+            tr.model_config, tr.data_config = {"TRAJECTORY_MODEL": True}, {"RAY_ENCODING": True}
+            tr.kps_left, tr.kps_right, tr.receptive_field = kps_left, kps_right, T
+            cam = RecordingCamera(pkt)
+            e = tr.evaluate_core(OneVideo(cam), flip_test=True)
+            out["pred" + tag] = cam.seen[0]                              # pos_tta + trj_tta, normalised frame (trainer.py:353-355)
+            out["metrics" + tag] = np.array(e, dtype=np.float64)         # mm: mpjpe, p_mpjpe, n_mpjpe, mpjve, root
+        np.savez_compressed(os.path.join(HERE, "evaluate_core_tta.npz"), uv=uvv, rays=rays[0].astype(np.float32), target=target[0].astype(np.float32),
+                            param=np.array([(-pkt.Rw2c.T @ pkt.Tw2c)[2][0], pkt.cam_pitch_rad]).astype(np.float32),
+                            kps_left=np.array(kps_left), kps_right=np.array(kps_right), Rn2w=pkt.Rn2w, Tn2w=pkt.Tn2w,
+                            K=cams[2]["K"], R=cams[2]["R"], t=cams[2]["t"], **out)
+    except Exception as e:  # pragma: no cover
+        print("evaluate_core flip-TTA fixture skipped:", repr(e))
+        raise
+
     with open(os.path.join(HERE, "meta.json"), "w") as f:
         json.dump(meta, f, indent=0)
     print("wrote", len(CASES), "cases to", HERE)

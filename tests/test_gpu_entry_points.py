@@ -199,3 +199,27 @@ def test_chained_tail_launch_is_bit_identical(stage):
             a, b = lf.forward_uv(uvc, camc), base.forward_uv(uvc, camc)
             assert all(torch.equal(x, y) for x, y in zip(a, b)), (stage, width, B)
         del lf
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_whole_evaluate_core_step_vs_the_reference(precision):
+    """One video through Lifter.forward_video_tta / forward_video_uv(tta=True) + metrics.evaluate, against what the
+    reference's own Trainer.evaluate_core(flip_test=True) produced for it (tests/golden/evaluate_core_tta.npz: the
+    tensor it hands to normalized2world, computed by the reference modules in float64, and its five metrics)."""
+    import ray3d_b200
+    g = load_golden("evaluate_core_tta")
+    lf = lifter(precision)
+    lf.set_flip(g["kps_left"].tolist(), g["kps_right"].tolist())
+    tol = {"bf16x3": 1e-4, "fp32": 2e-6}[precision]
+    both = lf.forward_video_tta(torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["param"]).cuda())[2]
+    assert relerr(both.cpu().numpy(), g["pred64"]) < tol
+    # from pixels, with the camera the fixture was made with (float64 row): same float32 rays -> same bits
+    cam = RayCamera(g["K"], g["R"], g["t"], res_w=1000, res_h=1002)
+    both_uv = lf.forward_video_uv(torch.from_numpy(g["uv"].astype(np.float32)).cuda(), cam, tta=True)[2]
+    rays32 = cam.get_cam_ray_given_uv(g["uv"].astype(np.float32).astype(np.float64)).astype(np.float32)
+    assert torch.equal(both_uv, lf.forward_video_tta(torch.from_numpy(rays32).cuda(), torch.from_numpy(cam.param).cuda())[2])
+    # evaluate_core's metrics (millimetres) from the device-side evaluation tail
+    m = ray3d_b200.metrics.evaluate(both, torch.from_numpy(g["target"][:, None]).cuda(), g["Rn2w"], g["Tn2w"])
+    e1, e2, e3, ev, er = g["metrics64"]
+    for want, key in ((e1, "mpjpe"), (e2, "p_mpjpe"), (e3, "n_mpjpe"), (ev, "mpjve"), (er, "mrpe")):
+        assert abs(m[key] * 1000 - want) <= 5 * tol * abs(want), (key, m[key] * 1000, want)

@@ -102,3 +102,26 @@ def test_undistort_matches_reference_cv2():
     assert np.array_equal(und, g["und"])
     pp = O.undistort_points(np.array([[g["K"][0, 2], g["K"][1, 2]]]), g["K"], g["dist"])
     assert np.array_equal(pp.reshape(-1), g["pp_cam"].reshape(-1))
+
+
+def test_flip_tta_matches_reference_evaluate_core():
+    """oracle.lift_tta vs the reference's own Trainer.evaluate_core(flip_test=True) (trainer.py:283-405) run on one
+    synthetic video by tests/golden/make_golden.py: the tensor evaluate_core hands to normalized2world (pos_tta + trj_tta)
+    and the five metrics it returns."""
+    g = load_golden("evaluate_core_tta")
+    spec = NetSpec(num_joints=17, in_features=3, filter_widths=(3, 3, 3), stage=1)
+    sp, st = synth.make_state_dicts(spec)
+    win = O.eval_windows(torch.from_numpy(g["rays"]), spec.receptive_field)                    # trainer.py:47-58
+    prm = torch.from_numpy(np.tile(g["param"], (win.shape[0], 1)))                             # trainer.py:324
+    for tag, dtype, tol in (("32", torch.float32, 2e-6), ("64", torch.float64, 1e-12)):
+        got = O.lift_tta(O.to_torch_state(sp, dtype), O.to_torch_state(st, dtype), spec, win.to(dtype), prm.to(dtype),
+                         g["kps_left"].tolist(), g["kps_right"].tolist())[2].numpy()
+        assert got.shape == g["pred" + tag].shape
+        assert relerr(got, g["pred" + tag]) < tol, tag
+    # the metrics of evaluate_core (millimetres): normalized2world on prediction and target, then lib/loss/loss.py
+    pw = O.normalized2world(g["pred32"], g["Rn2w"], g["Tn2w"])
+    tw = O.normalized2world(g["target"][:, None], g["Rn2w"], g["Tn2w"])
+    m = O.eval_metrics(pw, tw)
+    e1, e2, e3, ev, er = g["metrics32"]
+    for want, key in ((e1, "mpjpe"), (e2, "p_mpjpe"), (e3, "n_mpjpe"), (ev, "mpjve"), (er, "mrpe")):
+        assert abs(m[key] * 1000 - want) <= 1e-9 * abs(want), key
