@@ -829,7 +829,9 @@ static void plan_tail(r3d_plan* p) {
   for (int i = 0; i < nops; ++i) {
     p->launches_flat.push_back({p->ops[i].name, {i}, false});
     if (!in_tail[i]) { p->launches.push_back({p->ops[i].name, {i}, false}); continue; }
-    if (tail_listed || p->ops[i].side) continue;
+    // the chained launch goes where its LAST op stood: every launch it reads from (the GlobalInfo chain on the side
+    // stream comes after shrink in plan order) has been enqueued, and joined, before it
+    if (tail_listed || i != *std::max_element(p->tail_ops.begin(), p->tail_ops.end())) continue;
     tail_listed = true;
     p->launches.push_back({"tail[" + p->ops[p->tail_ops.front()].name + " .. " + p->ops[p->tail_ops.back()].name + "]", p->tail_ops, true});
   }
