@@ -352,6 +352,19 @@ def e2e_host(run: Run, steps: int):
     lf, B, spec = run.lifter, run.B, run.spec
     hsets = [(u.pin_memory(), c.pin_memory()) for u, c in run.sets]
     outs = [torch.empty((B, 1, spec.num_joints, 3), dtype=torch.float32).pin_memory() for _ in range(3)]
+    # the host-side ceiling of this path: plain pinned H2D copies of the same buffers, every rank at once (no kernels)
+    dst = torch.empty_like(hsets[0][0], device=run.dev)
+    for i in range(8):
+        dst.copy_(hsets[i % run.NSETS][0], non_blocking=True)
+    run.barrier()
+    w0 = time.perf_counter()
+    for i in range(40):
+        dst.copy_(hsets[i % run.NSETS][0], non_blocking=True)
+    torch.cuda.synchronize()
+    copy_gbs = 40 * hsets[0][0].numel() * 4 / (time.perf_counter() - w0) / 1e9
+    run.barrier()
+    copy_gbs = -run.max_over_ranks(-copy_gbs)                            # slowest rank
+    del dst
     for i in range(3):
         lf.forward_uv_host(*hsets[i % run.NSETS], out=outs[i % 3])
     run.barrier()
@@ -387,7 +400,7 @@ def e2e_host(run: Run, steps: int):
     ms = run.max_over_ranks(own_ms)
     assert checksum == checksum, "NaN in the streamed results"
     h2d = B * (spec.receptive_field * 17 * 2 + 6) * 4
-    return dict(ms=ms, sync_ms=sync_ms, h2d=h2d, d2h=B * 17 * 3 * 4, own_h2d_gbs=h2d / own_ms / 1e6)
+    return dict(ms=ms, sync_ms=sync_ms, h2d=h2d, d2h=B * 17 * 3 * 4, own_h2d_gbs=h2d / own_ms / 1e6, copy_gbs=copy_gbs)
 
 
 def e2e_video(run: Run, steps: int):
@@ -565,7 +578,11 @@ def main():
            "sync_value": B * world / e["sync_ms"] * 1e3, "sync_ms_per_step": e["sync_ms"],
            "sync_api": "Lifter.forward_uv_host -> r3d_forward_host (one blocking call per step; inside it two 512-window chunks "
                        "alternate between the lanes, the second chunk's copy under the first chunk's kernels)",
-           "rank0_h2d_gbs": e["own_h2d_gbs"], "numa_binding": numa}
+           "rank0_h2d_gbs": e["own_h2d_gbs"], "numa_binding": numa,
+           "h2d_ceiling": {"pinned_copy_gbs_per_rank_all_ranks_copying": e["copy_gbs"],
+                           "bound_sequences_per_s": world * e["copy_gbs"] * 1e9 / (e["h2d"] / B),
+                           "note": "plain cudaMemcpyAsync of the same pinned input buffers on every rank at once, slowest rank: what the host's memory "
+                                   "system / PCIe root can feed; the window path ships RF-fold inflated input (33 KB per sequence), e2e.video ships 136 B"}}
     extra = {}
     if not args.no_extra:
         e2e["video"] = e2e_video(run, e2e_steps)

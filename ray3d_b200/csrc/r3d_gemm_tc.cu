@@ -119,15 +119,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint64_t* yready_bar = bars + 2 * STAGES + 4; // [2]  FUSED: channels [0,128) / [128,256) of the intermediate are in tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
-  // Dynamic tile scheduler: the (leader CTA's) TMA producer claims the next work unit with one atomicAdd on the launch's
-  // counter and publishes it through a small queue in shared memory (in both CTAs of a pair) to every other role, so all
-  // roles walk the same sequence.  CTAs that become resident late (a kernel of the plan's other lane still held their SM)
-  // simply claim fewer units: co-running launches share the GPU work-conservingly instead of by static shares.
-  constexpr int SQ = 4;                                           // queue depth (roles are at most ~2 tiles apart)
-  uint64_t* sq_full = bars + 2 * STAGES + 7;                      // [SQ] unit id published
-  uint64_t* sq_empty = sq_full + SQ;                              // [SQ] every consumer (of both CTAs) has read it; leader's is used
-  volatile uint32_t* sq_tile = reinterpret_cast<volatile uint32_t*>(sq_empty + SQ);   // [SQ]
-  static_assert((2 * 6 + 7 + 2 * SQ) * 8 + SQ * 4 <= 256, "barrier block overflows its 256 bytes");
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
   // epilogue warp <-> store thread hand-off, per epilogue warp and staging set: "staged tile ready" / "staging set free"
   static_assert(sizeof(GemmOpDev) % 8 == 0 && 256 + sizeof(GemmOpDev) + 16 * 8 <= 256 + kOpSmemBytes, "no room for the store barriers");
@@ -140,9 +131,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
   const int per_m = total_tiles / m_tiles;                      // tiles per m group (all problems' n tiles)
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  // queue consumers per CTA: MMA thread (leader) or TMA producer (peer), the active store threads, 8 epilogue warps
-  constexpr int SQ_STORE = CH == 32 ? (COL_SPLIT >= 2 ? 2 : 1) : 0;
-  constexpr int SQ_CONSUMERS = (1 + SQ_STORE + EW) * CL;
+  // static round-robin tile schedule (a dynamic, atomically claimed schedule was measured in round 2: no gain with two
+  // lanes sharing the GPU, +10 % small-batch latency from the extra hand-offs; the chained tail kernel keeps one)
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
   constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA stages
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   const bool leader = crank == 0;
@@ -168,10 +159,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       mbar_init(&sready_bar[i], 4);                             // the four epilogue warps (TMEM lane quarters) of a column group
       mbar_init(&sfree_bar[i], 1);
     }
-    for (int i = 0; i < SQ; ++i) {
-      mbar_init(&sq_full[i], 1);
-      mbar_init(&sq_empty[i], SQ_CONSUMERS);                    // CL == 2: the peer's consumers arrive remotely on the leader's
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -193,23 +180,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const GemmOpDev& op = *sop;
-  // consumer side of the scheduler queue; every consuming role pops every unit, in order (qc = pops so far)
-  uint32_t qc = 0;
-  auto sq_pop = [&]() -> int {
-    const int slot = (int)(qc % SQ);
-    const uint32_t ph = (qc / SQ) & 1u;
-    if (CL == 2 && !leader) mbar_wait_cluster(&sq_full[slot], ph);     // written by the leader CTA's scheduler thread
-    else mbar_wait(&sq_full[slot], ph);
-    const int t = (int)sq_tile[slot];
-    ++qc;
-    return t;
-  };
-  auto sq_release = [&](uint32_t popped) {                               // one thread per role, after all its lanes have read the slot
-    const int slot = (int)((popped - 1) % SQ);
-    if (CL == 2 && !leader) mbar_arrive_cluster(&sq_empty[slot], 0);
-    else mbar_arrive(&sq_empty[slot]);
-  };
-
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -218,35 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       int ti = 0;
       bool shared_a = op.nprob > 1 && !R3D_DBG(1024);
       for (int p = 1; p < op.nprob; ++p) shared_a = shared_a && op.prob[p].a.p0 == op.prob[0].a.p0;
-      // scheduler (leader CTA): claim a unit, publish it, claim the next one while this one's loads are issued
-      uint32_t qn = 0;                                            // units published so far
-      // the first unit of every cluster is its own index (no round trip to L2 before the first load of the launch); the
-      // counter hands out the units after those
-      const int n_static = (int)gridDim.x / CL;
-      auto claim = [&]() -> int { return n_static + (int)atomicAdd(op.sched, 1u); };
-      auto publish = [&](int tile) {
-        const int slot = (int)(qn % SQ);
-        mbar_wait(&sq_empty[slot], ((qn / SQ) & 1u) ^ 1u);        // every consumer of both CTAs has read the slot's previous unit
-        sq_tile[slot] = (uint32_t)tile;
-        if (CL == 2) {
-          st_shared_cluster_u32(&sq_tile[slot], 1, (uint32_t)tile);
-          mbar_arrive_cluster(&sq_full[slot], 1, true);           // release.cluster: the peer's roles see the id
-        }
-        mbar_arrive(&sq_full[slot]);
-        ++qn;
-      };
-      int next_tile = (int)blockIdx.x / CL;
-      for (;; ++ti) {
-        int tile;
-        if (leader) {
-          tile = next_tile;
-          publish(tile);
-        } else {
-          tile = sq_pop();
-          sq_release(qc);
-        }
-        if (tile >= total_tiles) break;
-        if (leader) next_tile = claim();
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
@@ -313,10 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       int ti = 0;
-      for (;; ++ti) {
-        const int tile = sq_pop();
-        sq_release(qc);
-        if (tile >= total_tiles) break;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
@@ -439,10 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       uint64_t* prev_free = nullptr;                            // GPS == 2: set handed back one store later (while the next is read)
       int ti = 0;
       const bool strace3 = trace && st == 0;
-      for (;; ++ti) {
-        const int tile = sq_pop();
-        sq_release(qc);
-        if (tile >= total_tiles) break;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const GemmProb& pr = op.prob[tc.p];
         const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
@@ -527,16 +463,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         for (int i = 0; i < 4; ++i) pa[i] = __ldg(g.bias + chunk_of(i) * 32 + lane);
       }
     };
-    // every lane pops (reads the slot), lane 0 hands the slot back once the whole warp has read it
-    auto warp_pop = [&]() -> int {
-      const int t = sq_pop();
-      __syncwarp();
-      if (lane == 0) sq_release(qc);
-      return t;
-    };
-    int tile = warp_pop();
-    TileCoord tc = decode_tile(op, tile < total_tiles ? tile : 0, per_m, BLOCK_N, CL, crank, total_tiles);
-    if (BIAS_SMEM && active && tile < total_tiles) prefetch_bias(tc);
+    TileCoord tc = decode_tile(op, unit0 < total_tiles ? unit0 : 0, per_m, BLOCK_N, CL, crank, total_tiles);
+    if (BIAS_SMEM && active && unit0 < total_tiles) prefetch_bias(tc);
     uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
     for (int p = 0; p < op.nprob; ++p) {
       const GemmProb& g = op.prob[p];
@@ -547,21 +475,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       }
       pflags |= f << (4 * p);
     }
-    for (; tile < total_tiles; ++ti) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
       const GemmProb& pr = op.prob[tc.p];
       if (etrace) R3D_TRACE(2, ti, 0);
+      const bool has_next = tile + unit_step < total_tiles;
       TileCoord tn = tc;
-      int next_tile = total_tiles;
       bool next_ready = false;                                   // next tile decoded + its bias requested (done inside the chunk loop)
       // the next tile's coordinates and bias are fetched behind the first chunk's TMEM load, where the warp would stall anyway
-      // (the scheduler published the next unit long ago: it did so before issuing that unit's loads, and this tile's
-      // accumulator only completed after ITS loads)
       auto look_ahead = [&]() {
         if (next_ready) return;
         next_ready = true;
-        next_tile = warp_pop();
-        if (next_tile >= total_tiles) return;
-        tn = decode_tile(op, next_tile, per_m, BLOCK_N, CL, crank, total_tiles);
+        if (!has_next) return;
+        tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
         if (BIAS_SMEM && active) prefetch_bias(tn);
       };
       const bool ttrace = etrace && R3D_DBG(128);                 // stamps of the per-tile preamble
@@ -770,7 +695,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       look_ahead();                            // (warps without chunks in this tile)
       tc = tn;
-      tile = next_tile;
     }
     __syncwarp();
   }

@@ -66,7 +66,7 @@ struct GemmOpDev {
   int32_t flags;         // experiments: bit 0 fused pair waits for the whole intermediate before the second GEMM;
                          // bit 1 release (instead of relaxed) remote barrier arrivals
   int32_t n_tile_tail;   // unit width of this op inside the chained tail launch (0: not part of it)
-  uint32_t* sched;       // work-unit counter of this launch (zeroed before every forward): CTAs claim units with atomicAdd
+  uint32_t* sched;       // reserved (one counter slot per op in the descriptor slab; the chained tail launch uses its first op's)
   GemmProb prob[kMaxProb];
 };
 

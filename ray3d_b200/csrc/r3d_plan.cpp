@@ -445,7 +445,8 @@ struct Folder {
   // conv weight (n, cin, w) [+ BN]  ->  [n_pad][k_pad] with column = tap*cin + c
   PackedLayer conv(const std::string& wkey, int n, int cin, int w, const std::string& bnpre, const std::string& biaskey) const {
     PackedLayer pl;
-    pl.n = n; pl.k = cin * w; pl.n_pad = n < kTailN ? kTailN : round_up(n, 16); pl.k_pad = round_up(pl.k, kKAlign);   // narrow heads: one 128-column unit
+    pl.n = n; pl.k = cin * w; pl.k_pad = round_up(pl.k, kKAlign);
+    pl.n_pad = (p->tail_fusion && n < kTailN) ? kTailN : round_up(n, 16);   // chained tail launch: narrow heads fill one 128-column unit
     pl.w.assign((size_t)pl.n_pad * pl.k_pad, 0.f); pl.b.assign(pl.n_pad, 0.f);
     std::vector<double> sc(n, 1.0), sh(n, 0.0);
     if (!bnpre.empty()) bn(bnpre, n, sc, sh);
@@ -1392,7 +1393,7 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
     ++p->prof_runs;
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
-  if (prec != R3D_PREC_FP32)   // work-unit counters of the launches below (claimed by their CTAs with atomicAdd) + the tail's completion counters
+  if (use_tail)   // the chained tail launch's work-unit counter and completion counters
     CUDA_TRY(cudaMemsetAsync(p->d_desc + p->off_sched, 0, p->zero_bytes, s));
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, in, batch, tta ? batch_in : batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
@@ -2092,7 +2093,6 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   }
   if (ms_ffma) *ms_ffma = ms;
   for (int rep = 0; rep < 2; ++rep) {
-    CUDA_TRY(cudaMemsetAsync(dSched, 0, 128, 0));
     CUDA_TRY(cudaEventRecord(e0, 0));
     CUDA_TRY(launch_gemm_tc(dT, t, dMaps, m, precision, 0));
     CUDA_TRY(cudaEventRecord(e1, 0));
