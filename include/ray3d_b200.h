@@ -188,9 +188,12 @@ R3D_API int r3d_submit_host(r3d_plan* plan, const r3d_input* in_host, float* pos
 
 /* Result-neutral tuning: "graph_max_batch" (CUDA-graph replay for batches <= n, default 64, 0 off), "lanes" (1 or 2,
  * default 2), "side_stream" (0/1, default 1), "host_chunk" (windows per staged chunk of a host-buffer call, 0 = auto),
- * and, before r3d_plan_finalize only, "tail_fusion" (0/1, default 0: the one-row layers -- top tree level, shrink,
- * FuseBlocks, Integration -- as ONE persistent kernel with per-row-group dependency counters instead of one launch per
- * layer; bit-identical results, measured slower on B200, kept for study) and "tail_width" (128/256, its unit width). */
+ * and, before r3d_plan_finalize only: "side_chain" (0 off / 1 when worth it (default) / 2 always: the GlobalInfo chain,
+ * rie.py:362, as ONE persistent kernel on a few CTA pairs of the side stream, its work units ordered by per-row-group
+ * completion counters, instead of six under-filled launches racing the tree's kernels for SMs), "side_clusters" (CTA
+ * pairs it may hold; 0 = from its flop share), "tail_fusion" (0/1, default 0: the same for the one-row layers of the main
+ * chain -- top tree level, shrink, FuseBlocks, Integration; bit-identical, measured slower on B200, kept for study) and
+ * "tail_width" (128/256, its unit width). */
 R3D_API int r3d_plan_set_option(r3d_plan* plan, const char* name, int32_t value);
 
 /* --- forward: replaces nn.Module.forward(x, param) ------------------------------------------------

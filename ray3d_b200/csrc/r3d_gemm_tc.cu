@@ -82,7 +82,12 @@ constexpr bool kTraceBuilt = false;
 // hi/lo IN PLACE in tensor memory (each 32-column fp32 chunk becomes 16 hi + 16 lo packed columns), acc2 = Y*W2^T with
 // the A operand read from tensor memory (TS-mode tcgen05.mma), then the usual epilogue on acc2.  TMEM: columns
 // [0,256) acc1/Y, [256,512) acc2.  Needs BLOCK_N == 256 == channels.
-template <int BLOCK_N, int NSPLIT, int CL, bool FUSED>
+// DYN: work units after each cluster's first are claimed with atomicAdd on the launch's counter and published to the other
+// roles through a small shared-memory queue, instead of the static round-robin walk.  Used for the multi-wave 2-SM
+// launches (first layer, fused levels): while the GlobalInfo chain holds a few SMs for hundreds of microseconds (chained
+// launch on the side stream) the CTAs of those launches that cannot be resident yet simply take no units -- a static
+// share would make the launch wait for them.  Short launches keep the static walk (the hand-offs cost small-batch latency).
+template <int BLOCK_N, int NSPLIT, int CL, bool FUSED, bool DYN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev* __restrict__ opp, const CUtensorMap* __restrict__ tmaps,
                                                                    int M, int total_tiles, int dbg) {
   constexpr int NTHREADS = TC_THREADS;
@@ -119,6 +124,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint64_t* yready_bar = bars + 2 * STAGES + 4; // [2]  FUSED: channels [0,128) / [128,256) of the intermediate are in tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  constexpr int SQ = 4;                                           // DYN: unit queue depth (roles are at most ~2 tiles apart)
+  uint64_t* sq_full = bars + 2 * STAGES + 7;                      // [SQ] unit id published
+  uint64_t* sq_empty = sq_full + SQ;                              // [SQ] every consumer (of both CTAs) has read it; the leader's is used
+  volatile uint32_t* sq_tile = reinterpret_cast<volatile uint32_t*>(sq_empty + SQ);   // [SQ]
+  static_assert((2 * 6 + 7 + 2 * SQ) * 8 + SQ * 4 <= 256, "barrier block overflows its 256 bytes");
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
   // epilogue warp <-> store thread hand-off, per epilogue warp and staging set: "staged tile ready" / "staging set free"
   static_assert(sizeof(GemmOpDev) % 8 == 0 && 256 + sizeof(GemmOpDev) + 16 * 8 <= 256 + kOpSmemBytes, "no room for the store barriers");
@@ -131,9 +141,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
   const int per_m = total_tiles / m_tiles;                      // tiles per m group (all problems' n tiles)
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  // static round-robin tile schedule (a dynamic, atomically claimed schedule was measured in round 2: no gain with two
-  // lanes sharing the GPU, +10 % small-batch latency from the extra hand-offs; the chained tail kernel keeps one)
-  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;      // static walk; DYN: unit0 = first unit, the rest is claimed
+  // DYN queue consumers per CTA: MMA thread (leader) or TMA producer (peer), the active store threads, 8 epilogue warps
+  constexpr int SQ_STORE = CH == 32 ? (COL_SPLIT >= 2 ? 2 : 1) : 0;
+  constexpr int SQ_CONSUMERS = (1 + SQ_STORE + EW) * CL;
   constexpr int W_PART_ROWS = BLOCK_N / CL;                      // W rows this CTA stages
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   const bool leader = crank == 0;
@@ -159,6 +170,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       mbar_init(&sready_bar[i], 4);                             // the four epilogue warps (TMEM lane quarters) of a column group
       mbar_init(&sfree_bar[i], 1);
     }
+    if (DYN)
+      for (int i = 0; i < SQ; ++i) {
+        mbar_init(&sq_full[i], 1);
+        mbar_init(&sq_empty[i], SQ_CONSUMERS);                  // CL == 2: the peer's consumers arrive remotely on the leader's
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -180,6 +196,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const GemmOpDev& op = *sop;
+  // DYN: consumer side of the unit queue; every consuming role pops every unit, in order (qc = pops so far)
+  uint32_t qc = 0;
+  auto sq_pop = [&]() -> int {
+    const int slot = (int)(qc % SQ);
+    const uint32_t ph = (qc / SQ) & 1u;
+    if (CL == 2 && !leader) mbar_wait_cluster(&sq_full[slot], ph);     // written by the leader CTA's scheduler thread
+    else mbar_wait(&sq_full[slot], ph);
+    const int t = (int)sq_tile[slot];
+    ++qc;
+    return t;
+  };
+  auto sq_release = [&](uint32_t popped) {                               // one thread per role, after all its lanes have read the slot
+    const int slot = (int)((popped - 1) % SQ);
+    if (CL == 2 && !leader) mbar_arrive_cluster(&sq_empty[slot], 0);
+    else mbar_arrive(&sq_empty[slot]);
+  };
+  // next unit of a single-thread role (MMA issuer, store threads, the peer CTA's producer): prev < 0 = first
+  auto next_unit = [&](int prev) -> int {
+    if (!DYN) return prev < 0 ? unit0 : prev + unit_step;
+    const int t = sq_pop();
+    sq_release(qc);
+    return t;
+  };
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -188,7 +227,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       int ti = 0;
       bool shared_a = op.nprob > 1 && !R3D_DBG(1024);
       for (int p = 1; p < op.nprob; ++p) shared_a = shared_a && op.prob[p].a.p0 == op.prob[0].a.p0;
-      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
+      // DYN scheduler (leader CTA): publish a unit, claim the next one (atomicAdd in flight while this unit's loads are issued)
+      uint32_t qn = 0;
+      const int n_static = (int)gridDim.x / CL;
+      auto publish = [&](int tile) {
+        const int slot = (int)(qn % SQ);
+        mbar_wait(&sq_empty[slot], ((qn / SQ) & 1u) ^ 1u);        // every consumer of both CTAs has read the slot's previous unit
+        sq_tile[slot] = (uint32_t)tile;
+        if (CL == 2) {
+          st_shared_cluster_u32(&sq_tile[slot], 1, (uint32_t)tile);
+          mbar_arrive_cluster(&sq_full[slot], 1, true);           // release.cluster: the peer's roles see the id
+        }
+        mbar_arrive(&sq_full[slot]);
+        ++qn;
+      };
+      int claimed = unit0;                                        // (first unit: the cluster's own index, no L2 round trip)
+      for (int tile = DYN && !leader ? next_unit(-1) : unit0;; ++ti) {
+        if (DYN && leader) publish(tile);
+        if (tile >= total_tiles) break;
+        if (DYN && leader) claimed = n_static + (int)atomicAdd(op.sched, 1u);
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
@@ -245,6 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+        tile = !DYN ? tile + unit_step : (leader ? claimed : next_unit(tile));
       }
     }
     __syncwarp();
@@ -255,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       int ti = 0;
-      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
+      for (int tile = next_unit(-1); tile < total_tiles; tile = next_unit(tile), ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
@@ -378,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       uint64_t* prev_free = nullptr;                            // GPS == 2: set handed back one store later (while the next is read)
       int ti = 0;
       const bool strace3 = trace && st == 0;
-      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
+      for (int tile = next_unit(-1); tile < total_tiles; tile = next_unit(tile), ++ti) {
         const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
         const GemmProb& pr = op.prob[tc.p];
         const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
@@ -463,8 +521,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         for (int i = 0; i < 4; ++i) pa[i] = __ldg(g.bias + chunk_of(i) * 32 + lane);
       }
     };
-    TileCoord tc = decode_tile(op, unit0 < total_tiles ? unit0 : 0, per_m, BLOCK_N, CL, crank, total_tiles);
-    if (BIAS_SMEM && active && unit0 < total_tiles) prefetch_bias(tc);
+    // DYN: every lane pops (reads the slot), lane 0 hands the slot back once the whole warp has read it
+    auto warp_pop = [&]() -> int {
+      const int t = sq_pop();
+      __syncwarp();
+      if (lane == 0) sq_release(qc);
+      return t;
+    };
+    int tile = DYN ? warp_pop() : unit0;
+    TileCoord tc = decode_tile(op, tile < total_tiles ? tile : 0, per_m, BLOCK_N, CL, crank, total_tiles);
+    if (BIAS_SMEM && active && tile < total_tiles) prefetch_bias(tc);
     uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
     for (int p = 0; p < op.nprob; ++p) {
       const GemmProb& g = op.prob[p];
@@ -475,18 +541,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       }
       pflags |= f << (4 * p);
     }
-    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++ti) {
+    for (; tile < total_tiles; ++ti) {
       const GemmProb& pr = op.prob[tc.p];
       if (etrace) R3D_TRACE(2, ti, 0);
-      const bool has_next = tile + unit_step < total_tiles;
       TileCoord tn = tc;
+      int next_tile = DYN ? total_tiles : tile + unit_step;
       bool next_ready = false;                                   // next tile decoded + its bias requested (done inside the chunk loop)
       // the next tile's coordinates and bias are fetched behind the first chunk's TMEM load, where the warp would stall anyway
+      // (DYN: the scheduler published the next unit long ago -- before issuing that unit's loads -- so the pop does not wait)
       auto look_ahead = [&]() {
         if (next_ready) return;
         next_ready = true;
-        if (!has_next) return;
-        tn = decode_tile(op, tile + unit_step, per_m, BLOCK_N, CL, crank, total_tiles);
+        if (DYN) next_tile = warp_pop();
+        if (next_tile >= total_tiles) return;
+        tn = decode_tile(op, next_tile, per_m, BLOCK_N, CL, crank, total_tiles);
         if (BIAS_SMEM && active) prefetch_bias(tn);
       };
       const bool ttrace = etrace && R3D_DBG(128);                 // stamps of the per-tile preamble
@@ -695,6 +763,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       look_ahead();                            // (warps without chunks in this tile)
       tc = tn;
+      tile = next_tile;
     }
     __syncwarp();
   }
@@ -840,11 +909,17 @@ static cudaError_t configure_one() {
   constexpr int CL2 = BN >= 32 ? 2 : 1;
   if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, CL2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, CL2>());
   if (e != cudaSuccess) return e;
+  if (BN == 128) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, CL2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, CL2>());
+  if (e != cudaSuccess) return e;
   if (BN == 256) {   // fused conv-pair variants
     constexpr int FB = BN == 256 ? 256 : 256;
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 1>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
   }
   return e;
 }
@@ -929,7 +1004,14 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   ++na;
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (BN == 256 && h.fused2) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, dbg);
+  // multi-wave 256-column launches claim their units dynamically (see DYN); the caller zeroes h.sched before the forward
+  const bool dyn = (BN == 256 || BN == 128) && h.sched != nullptr && units >= 2 * clusters;
+  if (BN == 256 && h.fused2) {
+    if (dyn) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true, true>, d_op, d_tmaps, M, units, dbg);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, dbg);
+  }
+  if (BN == 256 && dyn) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, false, true>, d_op, d_tmaps, M, units, dbg);
+  if (BN == 128 && dyn) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, NS, 2, false, true>, d_op, d_tmaps, M, units, dbg);
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NS, CL2, false>, d_op, d_tmaps, M, units, dbg);
 }
 

@@ -66,7 +66,7 @@ struct GemmOpDev {
   int32_t flags;         // experiments: bit 0 fused pair waits for the whole intermediate before the second GEMM;
                          // bit 1 release (instead of relaxed) remote barrier arrivals
   int32_t n_tile_tail;   // unit width of this op inside the chained tail launch (0: not part of it)
-  uint32_t* sched;       // reserved (one counter slot per op in the descriptor slab; the chained tail launch uses its first op's)
+  uint32_t* sched;       // work-unit counter of this launch (zeroed before every forward): dynamically scheduled launches claim units with atomicAdd
   GemmProb prob[kMaxProb];
 };
 
@@ -168,7 +168,7 @@ cudaError_t tail_stats_read(unsigned long long* out, int reset);   // experiment
 int tc_num_sms();
 // one launch for every op listed in `mo` (device copy d_mo); ops / tensor maps are the plan's arrays
 cudaError_t launch_tail_tc(const GemmOpDev* d_ops, const void* d_tmaps, const MultiOpDev* d_mo, const MultiOpDev& h_mo, int M, int precision,
-                           cudaStream_t s);
+                           int max_clusters, cudaStream_t s);
 inline bool tail_uses_pairs(int M) { return M >= 256; }                       // the chained launch works on 256-row units (CTA pairs)
 inline int tail_row_groups(int M) { return (M + 255) / 256; }
 void tc_trace_arm(int launches_from_now);              // diagnostics: per-tile clock trace of one GEMM launch

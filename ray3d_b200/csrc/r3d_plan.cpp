@@ -195,15 +195,24 @@ struct r3d_plan {
   // optional per-launch timing (r3d_plan_set_profiling): ring of event sets, one per forward chunk
   bool profiling = false;
   bool use_side_stream = true;
-  // chained tail launch (r3d_tail_tc.cu): the ops with one row per window run as ONE kernel
-  bool tail_fusion = false;                           // option "tail_fusion" (off: measured slower than one launch per layer)
-  int tail_width = 128;                               // option "tail_width": unit width of the chained launch (128 or 256 columns)
-  std::vector<int> tail_ops;                          // plan op indices in unit order (empty: every op is its own launch)
-  MultiOpDev tail{};                                  // host copy; the device copy lives in the descriptor slab
-  size_t off_tail = 0, off_done = 0, zero_bytes = 0;
-  struct Launch { std::string name; std::vector<int> ops; bool tail; };
-  std::vector<Launch> launches, launches_flat;        // GEMM launches of one forward (side-stream ops included): with the chained tail / one per op
-  bool prof_tail = false;                             // which of the two the last profiled forward used
+  // chained launches (r3d_tail_tc.cu): a dependency chain of one-row ops as ONE persistent kernel.
+  //   chain 0 (option "tail_fusion", off): top tree level, shrink, FuseBlocks, Integration on the main stream
+  //   chain 1 (option "side_chain", on):   the GlobalInfo chain on the side stream, on a FEW CTA pairs
+  struct Chain {
+    std::vector<int> ops;                             // plan op indices in unit order (empty: every op is its own launch)
+    MultiOpDev mo{};                                  // host copy; the device copy lives in the descriptor slab
+    size_t off_mo = 0, off_done = 0;
+    int max_clusters = 0;                             // 0: the whole GPU
+  };
+  Chain chain[2];
+  bool tail_fusion = false;                           // (off: measured slower than one launch per layer)
+  bool side_chain = true, side_chain_force = false;   // option "side_chain": 0 off, 1 when worth it (default), 2 always
+  int tail_width = 128;                               // option "tail_width": unit width of chain 0 (128 or 256 columns)
+  int side_clusters = 0;                              // option "side_clusters": CTA pairs the GlobalInfo chain may hold (0: from its flop share)
+  size_t zero_bytes = 0;
+  struct Launch { std::string name; std::vector<int> ops; int chain; };     // chain: -1 = one op
+  std::vector<Launch> launches[4];                    // GEMM launches of one forward; variant = (chain 0 used) | (chain 1 used) << 1
+  int prof_variant = 0;                               // variant the last profiled forward used
   std::vector<int> flip_in, flip_out;                 // joint permutations of the flip augmentation (empty: not set)
   std::vector<cudaEvent_t> prof_ev;                   // [kProfRing][nops + 3]
   int prof_runs = 0;
@@ -751,90 +760,125 @@ static void build_graph(r3d_plan* p) {
   }
 }
 
-// Which ops form the chained tail launch (r3d_tail_tc.cu), in which order their units are claimed, and which earlier
-// (op, problem) pairs each (op, problem) reads from.  Host only; pointers are resolved in bind_workspace.
-static void plan_tail(r3d_plan* p) {
-  p->tail_ops.clear();
-  p->launches.clear();
-  memset(&p->tail, 0, sizeof(p->tail));
+// One chained launch (r3d_tail_tc.cu): the ops `order` (plan indices, dependency order), their unit counts, and which
+// earlier (op, problem) pairs each (op, problem) reads from.  Host only; pointers are resolved in bind_workspace.
+static bool build_chain(r3d_plan* p, const std::vector<int>& order, int width_pref, MultiOpDev& mo) {
+  memset(&mo, 0, sizeof(mo));
+  bool ok = order.size() >= 2 && order.size() <= (size_t)kMaxTailOps;
+  for (size_t li = 0; ok && li < order.size(); ++li) {
+    const OpHost& op = p->ops[order[li]];
+    ok = ok && op.dev.rows_per_seq == 1 && !op.dev.fused2;
+    for (int q = 0; ok && q < op.dev.nprob; ++q) {
+      const PackedLayer& l = p->layers.at(op.bind[q].layer);
+      ok = ok && l.n_pad % kTailN == 0 && l.n_pad / kTailN <= 255 && l.k_pad % kKAlign == 0;
+    }
+  }
+  if (!ok) return false;
+  mo.nops = (int)order.size();
+  for (int li = 0; ok && li < mo.nops; ++li) {
+    const OpHost& op = p->ops[order[li]];
+    mo.op_index[li] = order[li];
+    mo.nprob[li] = (uint8_t)op.dev.nprob;
+    int per_m = 0, width = width_pref >= 256 ? 2 : 1;            // 256-column units unless some problem of the op is narrower
+    for (int q = 0; q < op.dev.nprob; ++q)
+      if (p->layers.at(op.bind[q].layer).n_pad % (2 * kTailN)) width = 1;
+    mo.width[li] = (uint8_t)width;
+    for (int q = 0; q < op.dev.nprob; ++q) {
+      mo.ntiles[li][q] = (uint8_t)(p->layers.at(op.bind[q].layer).n_pad / (kTailN * width));
+      per_m += mo.ntiles[li][q];
+      // producers: for every matrix this problem reads (operand, residual) and every column offset written into it, the
+      // LAST earlier (op, problem) of the launch that writes there (activation buffers are recycled along a chain)
+      std::map<std::pair<int, int>, int> writer;                   // (matrix, column) -> counter row
+      for (int lj = 0; lj < li; ++lj) {
+        const OpHost& pj = p->ops[order[lj]];
+        for (int r = 0; r < pj.dev.nprob; ++r)
+          for (auto& d : pj.bind[r].dst)
+            if (d.first == op.bind[q].a || (op.bind[q].res >= 0 && d.first == op.bind[q].res)) writer[{d.first, d.second}] = lj * kMaxProb + r;
+      }
+      std::vector<int> rows;
+      for (auto& kv : writer)
+        if (std::find(rows.begin(), rows.end(), kv.second) == rows.end()) rows.push_back(kv.second);
+      int nd = 0;
+      for (int row : rows) {
+        if (nd == kMaxDeps) { ok = false; break; }
+        mo.dep[li][q][nd++] = (int16_t)row;
+      }
+      mo.ndep[li][q] = (uint8_t)nd;
+    }
+    mo.unit0[li + 1] = mo.unit0[li] + per_m;
+  }
+  if (!ok) memset(&mo, 0, sizeof(mo));
+  return ok;
+}
+
+static void plan_chains(r3d_plan* p) {
   const int nops = (int)p->ops.size();
-  bool ok = p->tail_fusion && p->cfg.precision != R3D_PREC_FP32;
-  std::vector<int> order;
-  if (ok) {
-    // main chain: the maximal suffix of one-row ops (a fused conv pair keeps its own launch); side chain: all of it
+  const bool tc = p->cfg.precision != R3D_PREC_FP32;
+  for (auto& c : p->chain) { c.ops.clear(); memset(&c.mo, 0, sizeof(c.mo)); c.max_clusters = 0; }
+  if (tc && p->tail_fusion) {
+    // main chain: the maximal suffix of one-row ops (a fused conv pair keeps its own launch).  The GlobalInfo chain is NOT
+    // part of it: inside, its six dependent layers would sit in front of Integration.fc_1 (measured: 62 % of the kernel's
+    // cycles spent waiting for inputs).
     int first = nops;
     for (int i = nops - 1; i >= 0; --i) {
       if (p->ops[i].side) continue;
       if (p->ops[i].dev.rows_per_seq != 1 || p->ops[i].dev.fused2) break;
       first = i;
     }
-    // The GlobalInfo chain (side stream) stays one launch per layer: it only depends on the input stage and runs under
-    // the large launches of the tree, off the critical path.  Inside the chained launch its six dependent layers would sit
-    // in front of Integration.fc_1 (measured: 62 % of the tail kernel's cycles spent waiting for inputs).
     std::vector<int> mains;
     for (int i = first; i < nops; ++i)
       if (!p->ops[i].side) mains.push_back(i);
-    order = mains;
-    ok = ok && order.size() >= 2 && order.size() <= (size_t)kMaxTailOps && !mains.empty();
-    for (size_t li = 0; ok && li < order.size(); ++li) {
-      const OpHost& op = p->ops[order[li]];
+    if (build_chain(p, mains, p->tail_width, p->chain[0].mo)) p->chain[0].ops = mains;
+  }
+  if (tc && p->side_chain) {
+    // The GlobalInfo chain only depends on the input stage and has ~600 us of slack before Integration.fc_1 needs it (at
+    // B=1024, T=243).  As six under-filled launches racing the tree's persistent kernels for SMs it costs the step 90 us
+    // (measured by skipping it); as ONE chained launch on a few CTA pairs it takes longer but occupies far fewer SM-microseconds.
+    std::vector<int> sides;
+    for (int i = 0; i < nops; ++i)
+      if (p->ops[i].side) sides.push_back(i);
+    // Only worth it when the chain is a small fraction of the work the tree does before Integration.fc_1 needs its output
+    // (T = 243: 11 %): on few CTA pairs it takes as long as (share x 74 / pairs) of that time.  Short receptive fields keep
+    // one launch per layer.  CTA pairs: 1.5x the flop share unless the option "side_clusters" fixes it.
+    auto op_flops = [&](const OpHost& op) {
+      double f = 0;
       for (int q = 0; q < op.dev.nprob; ++q) {
         const PackedLayer& l = p->layers.at(op.bind[q].layer);
-        ok = ok && l.n_pad % kTailN == 0 && l.n_pad / kTailN <= 255 && l.k_pad % kKAlign == 0;
+        f += (double)op.dev.rows_per_seq * l.n * (l.alg_k ? l.alg_k : l.k);
+        if (!op.bind[q].layer2.empty()) f += (double)op.dev.rows_per_seq * p->layers.at(op.bind[q].layer2).n * p->layers.at(op.bind[q].layer2).k;
       }
+      return f;
+    };
+    double f_side = 0, f_tree = 0;
+    for (const OpHost& op : p->ops) {
+      if (op.side) f_side += op_flops(op);
+      else if (!op.join_before && f_tree >= 0) f_tree += op_flops(op);
+      if (op.join_before) break;                                  // ops from the first consumer on do not hide the chain
+    }
+    const double share = f_tree > 0 ? f_side / f_tree : 1.0;
+    if ((share <= 0.2 || p->side_chain_force) && build_chain(p, sides, 256, p->chain[1].mo)) {
+      p->chain[1].ops = sides;
+      p->chain[1].max_clusters = p->side_clusters > 0 ? p->side_clusters : std::min(24, std::max(4, (int)std::ceil(74.0 * share * 1.5)));
     }
   }
-  MultiOpDev& mo = p->tail;
-  if (ok) {
-    mo.nops = (int)order.size();
-    for (int li = 0; ok && li < mo.nops; ++li) {
-      const OpHost& op = p->ops[order[li]];
-      mo.op_index[li] = order[li];
-      mo.nprob[li] = (uint8_t)op.dev.nprob;
-      int per_m = 0, width = p->tail_width >= 256 ? 2 : 1;          // 256-column units unless some problem of the op is narrower
-      for (int q = 0; q < op.dev.nprob; ++q)
-        if (p->layers.at(op.bind[q].layer).n_pad % (2 * kTailN)) width = 1;
-      mo.width[li] = (uint8_t)width;
-      for (int q = 0; q < op.dev.nprob; ++q) {
-        mo.ntiles[li][q] = (uint8_t)(p->layers.at(op.bind[q].layer).n_pad / (kTailN * width));
-        per_m += mo.ntiles[li][q];
-        // producers: for every matrix this problem reads (operand, residual) and every column offset written into it, the
-        // LAST earlier (op, problem) of the launch that writes there (activation buffers are recycled along a chain)
-        std::map<std::pair<int, int>, int> writer;                   // (matrix, column) -> counter row
-        for (int lj = 0; lj < li; ++lj) {
-          const OpHost& pj = p->ops[order[lj]];
-          for (int r = 0; r < pj.dev.nprob; ++r)
-            for (auto& d : pj.bind[r].dst)
-              if (d.first == op.bind[q].a || (op.bind[q].res >= 0 && d.first == op.bind[q].res)) writer[{d.first, d.second}] = lj * kMaxProb + r;
-        }
-        std::vector<int> rows;
-        for (auto& kv : writer)
-          if (std::find(rows.begin(), rows.end(), kv.second) == rows.end()) rows.push_back(kv.second);
-        int nd = 0;
-        for (int row : rows) {
-          if (nd == kMaxDeps) { ok = false; break; }
-          mo.dep[li][q][nd++] = (int16_t)row;
-        }
-        mo.ndep[li][q] = (uint8_t)nd;
-      }
-      mo.unit0[li + 1] = mo.unit0[li] + per_m;
+  // the GEMM launches of one forward, for every combination of chains in use (a chain needs batches of >= 256 windows)
+  for (int v = 0; v < 4; ++v) {
+    auto& out = p->launches[v];
+    out.clear();
+    std::vector<int> of(nops, -1);
+    for (int c = 0; c < 2; ++c)
+      if ((v >> c) & 1)
+        for (int i : p->chain[c].ops) of[i] = c;
+    bool listed[2] = {false, false};
+    for (int i = 0; i < nops; ++i) {
+      const int c = of[i];
+      if (c < 0) { out.push_back({p->ops[i].name, {i}, -1}); continue; }
+      // a chained launch goes where its LAST op stood: every launch it reads from has been enqueued (and joined) before it
+      const auto& co = p->chain[c].ops;
+      if (listed[c] || i != *std::max_element(co.begin(), co.end())) continue;
+      listed[c] = true;
+      out.push_back({std::string(c ? "side[" : "tail[") + p->ops[co.front()].name + " .. " + p->ops[co.back()].name + "]", co, c});
     }
-  }
-  if (ok) p->tail_ops = order;
-  else memset(&mo, 0, sizeof(mo));
-  // the GEMM launches of one forward: with the chained tail launch (batches of >= 256 windows) and one launch per op
-  std::vector<char> in_tail(nops, 0);
-  for (int i : p->tail_ops) in_tail[i] = 1;
-  bool tail_listed = false;
-  p->launches_flat.clear();
-  for (int i = 0; i < nops; ++i) {
-    p->launches_flat.push_back({p->ops[i].name, {i}, false});
-    if (!in_tail[i]) { p->launches.push_back({p->ops[i].name, {i}, false}); continue; }
-    // the chained launch goes where its LAST op stood: every launch it reads from (the GlobalInfo chain on the side
-    // stream comes after shrink in plan order) has been enqueued, and joined, before it
-    if (tail_listed || i != *std::max_element(p->tail_ops.begin(), p->tail_ops.end())) continue;
-    tail_listed = true;
-    p->launches.push_back({"tail[" + p->ops[p->tail_ops.front()].name + " .. " + p->ops[p->tail_ops.back()].name + "]", p->tail_ops, true});
   }
 }
 
@@ -872,7 +916,7 @@ extern "C" R3D_API int r3d_plan_finalize(r3d_plan* p) {
     pack_fcblock(p, 1, "Integration", p->feat_trj, 3, 1);
   }
   build_graph(p);
-  plan_tail(p);
+  plan_chains(p);
   // weight slab layout
   const int prec = p->cfg.precision;
   size_t off = 0;
@@ -942,21 +986,26 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
       j += std::string(d ? "," : "") + "[" + std::to_string(p->emb_binds[e].dst[d].first) + "," + std::to_string(p->emb_binds[e].dst[d].second) + "]";
     j += "]}";
   }
-  j += "],\"launches\":[";
-  for (size_t k = 0; k < p->launches.size(); ++k) {
-    j += std::string(k ? "," : "") + "{\"name\":\"" + p->launches[k].name + "\",\"tail\":" + (p->launches[k].tail ? "1" : "0") + ",\"ops\":[";
-    for (size_t q = 0; q < p->launches[k].ops.size(); ++q) j += std::string(q ? "," : "") + std::to_string(p->launches[k].ops[q]);
-    j += "]}";
+  j += "],\"launches\":[";                            // the variant with every planned chain in use (batches >= 256)
+  {
+    const int v = (p->chain[0].ops.empty() ? 0 : 1) | (p->chain[1].ops.empty() ? 0 : 2);
+    for (size_t k = 0; k < p->launches[v].size(); ++k) {
+      const auto& L = p->launches[v][k];
+      j += std::string(k ? "," : "") + "{\"name\":\"" + L.name + "\",\"tail\":" + (L.chain >= 0 ? "1" : "0") + ",\"chain\":" + std::to_string(L.chain) + ",\"ops\":[";
+      for (size_t q = 0; q < L.ops.size(); ++q) j += std::string(q ? "," : "") + std::to_string(L.ops[q]);
+      j += "]}";
+    }
   }
   j += "],\"tail\":{\"unit0\":[";
-  for (int i = 0; i <= p->tail.nops && p->tail.nops > 0; ++i) j += std::string(i ? "," : "") + std::to_string(p->tail.unit0[i]);
-  j += "],\"deps\":[";                               // per tail op, per problem: [local producer op, producer problem] pairs
-  for (int i = 0; i < p->tail.nops; ++i) {
+  const MultiOpDev& tmo = p->chain[0].ops.empty() ? p->chain[1].mo : p->chain[0].mo;
+  for (int i = 0; i <= tmo.nops && tmo.nops > 0; ++i) j += std::string(i ? "," : "") + std::to_string(tmo.unit0[i]);
+  j += "],\"deps\":[";                               // per chained op, per problem: [local producer op, producer problem] pairs
+  for (int i = 0; i < tmo.nops; ++i) {
     j += std::string(i ? "," : "") + "[";
-    for (int q = 0; q < p->tail.nprob[i]; ++q) {
+    for (int q = 0; q < tmo.nprob[i]; ++q) {
       j += std::string(q ? "," : "") + "[";
-      for (int d = 0; d < p->tail.ndep[i][q]; ++d)
-        j += std::string(d ? "," : "") + "[" + std::to_string(p->tail.dep[i][q][d] / kMaxProb) + "," + std::to_string(p->tail.dep[i][q][d] % kMaxProb) + "]";
+      for (int d = 0; d < tmo.ndep[i][q]; ++d)
+        j += std::string(d ? "," : "") + "[" + std::to_string(tmo.dep[i][q][d] / kMaxProb) + "," + std::to_string(tmo.dep[i][q][d] % kMaxProb) + "]";
       j += "]";
     }
     j += "]";
@@ -997,7 +1046,9 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
 extern "C" R3D_API int64_t r3d_plan_weight_bytes(const r3d_plan* p) { return p ? (int64_t)p->weight_bytes : 0; }
 extern "C" R3D_API int64_t r3d_plan_workspace_bytes(const r3d_plan* p) { return p ? (int64_t)p->ws_bytes : 0; }
 extern "C" R3D_API int r3d_plan_receptive_field(const r3d_plan* p) { return p ? p->T : 0; }
-extern "C" R3D_API int r3d_plan_kernel_launches(const r3d_plan* p) { return p ? (int)p->launches.size() + 2 : 0; }
+extern "C" R3D_API int r3d_plan_kernel_launches(const r3d_plan* p) {     // at batches >= 256 (chained launches in use)
+  return p ? (int)p->launches[(p->chain[0].ops.empty() ? 0 : 1) | (p->chain[1].ops.empty() ? 0 : 2)].size() + 2 : 0;
+}
 extern "C" R3D_API int64_t r3d_plan_graph_launches(const r3d_plan* p) { return p ? (int64_t)p->graph_launches : 0; }
 
 // ---- device upload -------------------------------------------------------------------------------
@@ -1242,9 +1293,10 @@ static int bind_workspace(r3d_plan* p, int cap) {
     // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
     bool tile_heuristic = true;
     if (const char* env = exp_env("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
-    {
-      const auto it = std::find(p->tail_ops.begin(), p->tail_ops.end(), (int)(&op - p->ops.data()));
-      op.dev.n_tile_tail = it == p->tail_ops.end() ? 0 : kTailN * p->tail.width[it - p->tail_ops.begin()];
+    op.dev.n_tile_tail = 0;
+    for (const auto& c : p->chain) {
+      const auto it = std::find(c.ops.begin(), c.ops.end(), (int)(&op - p->ops.data()));
+      if (it != c.ops.end()) op.dev.n_tile_tail = kTailN * c.mo.width[it - c.ops.begin()];
     }
     if (prec != R3D_PREC_FP32 && ntile > 64 && !op.dev.fused2 && tile_heuristic) {
       const int64_t m_tiles = ((int64_t)cap * op.dev.rows_per_seq + 127) / 128;
@@ -1311,9 +1363,10 @@ static int bind_workspace(r3d_plan* p, int cap) {
   p->off_tmaps = take(nops * kMaxProb * kTmapsPerProb * kTmapBytes);
   p->off_sched = take(nops * r3d_plan::kSchedStride);                    // one work-unit counter per GEMM launch, 128 bytes apart
   const int m_groups_cap = (cap + 127) / 128;
-  p->off_done = take((size_t)std::max(1, p->tail.nops) * kMaxProb * m_groups_cap * sizeof(uint32_t));   // (contiguous with the counters: one memset)
+  for (auto& c : p->chain)                                     // completion counters, contiguous with the work-unit counters: one memset
+    c.off_done = take((size_t)std::max(1, c.mo.nops) * kMaxProb * m_groups_cap * sizeof(uint32_t));
   p->zero_bytes = off - p->off_sched;
-  p->off_tail = take(sizeof(MultiOpDev));
+  for (auto& c : p->chain) c.off_mo = take(sizeof(MultiOpDev));
   const size_t off_map = take(p->a0_src.size() * sizeof(int32_t));
   CUDA_TRY(cudaMalloc(&p->d_desc, off));
   pd.a0_off = reinterpret_cast<const int32_t*>(p->d_desc + off_map);
@@ -1330,11 +1383,12 @@ static int bind_workspace(r3d_plan* p, int cap) {
     p->ops[i].dev.sched = reinterpret_cast<uint32_t*>(p->d_desc + p->off_sched + i * r3d_plan::kSchedStride);
     memcpy(h.data() + p->off_ops + i * sizeof(GemmOpDev), &p->ops[i].dev, sizeof(GemmOpDev));
   }
-  if (p->tail.nops > 0) {
-    p->tail.m_groups_cap = m_groups_cap;
-    p->tail.done = reinterpret_cast<uint32_t*>(p->d_desc + p->off_done);
-    p->tail.sched = reinterpret_cast<uint32_t*>(p->d_desc + p->off_sched + (size_t)p->tail_ops.front() * r3d_plan::kSchedStride);
-    memcpy(h.data() + p->off_tail, &p->tail, sizeof(MultiOpDev));
+  for (auto& c : p->chain) {
+    if (c.mo.nops == 0) continue;
+    c.mo.m_groups_cap = m_groups_cap;
+    c.mo.done = reinterpret_cast<uint32_t*>(p->d_desc + c.off_done);
+    c.mo.sched = reinterpret_cast<uint32_t*>(p->d_desc + p->off_sched + (size_t)c.ops.front() * r3d_plan::kSchedStride);
+    memcpy(h.data() + c.off_mo, &c.mo, sizeof(MultiOpDev));
   }
   memcpy(h.data() + p->off_pro, &pd, sizeof(pd));
   memcpy(h.data() + p->off_asm, &ad, sizeof(ad));
@@ -1379,12 +1433,14 @@ static InputSpec advance(const InputSpec& in, int64_t b0) {
 static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, float* sum, int batch_in, cudaStream_t s, bool tta = false) {
   const int batch = tta ? 2 * batch_in : batch_in;
   const int prec = p->cfg.precision;
-  const bool use_tail = !p->tail_ops.empty() && tail_uses_pairs(batch);      // small batches: one launch per op (narrow tiles)
-  const std::vector<r3d_plan::Launch>& launches = use_tail ? p->launches : p->launches_flat;
+  // chained launches work on 256-row units (CTA pairs); small batches keep one launch per op (narrow tiles)
+  // (the GlobalInfo chain: only while its per-layer launches would under-fill the GPU, i.e. up to 2048 windows)
+  const int variant = tail_uses_pairs(batch) ? ((p->chain[0].ops.empty() ? 0 : 1) | ((p->chain[1].ops.empty() || batch > 2048) ? 0 : 2)) : 0;
+  const std::vector<r3d_plan::Launch>& launches = p->launches[variant];
   const int nl = (int)launches.size() + 2, nev = 2 * nl;      // start/end event per launch
   cudaEvent_t* ev = nullptr;
   if (p->profiling) {
-    p->prof_tail = use_tail;
+    p->prof_variant = variant;
     if (p->prof_ev.empty()) {
       p->prof_ev.resize((size_t)kProfRing * 2 * (p->ops.size() + 2));
       for (auto& e : p->prof_ev) CUDA_TRY(cudaEventCreate(&e));
@@ -1393,7 +1449,9 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
     ++p->prof_runs;
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
-  if (use_tail)   // the chained tail launch's work-unit counter and completion counters
+  // work-unit counters of the dynamically scheduled launches (multi-wave 2-SM GEMMs: never below 64 windows) and the
+  // chained launches' completion counters
+  if (prec != R3D_PREC_FP32 && (variant || batch > 64))
     CUDA_TRY(cudaMemsetAsync(p->d_desc + p->off_sched, 0, p->zero_bytes, s));
   CUDA_TRY(launch_prologue(reinterpret_cast<const PrologueDev*>(p->d_desc + p->off_pro), p->pro, prec, in, batch, tta ? batch_in : batch, s));
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
@@ -1405,7 +1463,7 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
   const bool use_side = p->use_side_stream && !p->profiling;
   bool forked = false, fork_recorded = false;
   if (use_side) {
-    for (const auto& L : launches) fork_recorded |= !L.tail && p->ops[L.ops[0]].side;
+    for (const auto& L : launches) fork_recorded |= p->ops[L.ops[0]].side;
     if (fork_recorded) CUDA_TRY(cudaEventRecord(p->ev_fork, s));   // right after the input stage, before any GEMM is enqueued
   }
   const GemmOpDev* d_ops = reinterpret_cast<const GemmOpDev*>(p->d_desc + p->off_ops);
@@ -1414,7 +1472,7 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
     const size_t i = (size_t)L.ops[0];
     const OpHost& oh = p->ops[i];
     cudaStream_t st = s;
-    if (!L.tail && use_side && oh.side) {
+    if (use_side && oh.side) {
       if (!forked) {
         CUDA_TRY(cudaStreamWaitEvent(p->s_side, p->ev_fork, 0));
         forked = true;
@@ -1429,8 +1487,10 @@ static int run_chunk(r3d_plan* p, const InputSpec& in, float* pos, float* trj, f
       forked = false;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev[2 * (k + 1)], st));
-    if (L.tail)
-      CUDA_TRY(launch_tail_tc(d_ops, p->d_desc + p->off_tmaps, reinterpret_cast<const MultiOpDev*>(p->d_desc + p->off_tail), p->tail, batch, prec, st));
+    if (oh.side && exp_env("R3D_SKIP_SIDE")) {}                        // experiment (wrong results): what the GlobalInfo chain costs the step
+    else if (L.chain >= 0)
+      CUDA_TRY(launch_tail_tc(d_ops, p->d_desc + p->off_tmaps, reinterpret_cast<const MultiOpDev*>(p->d_desc + p->chain[L.chain].off_mo),
+                              p->chain[L.chain].mo, batch, prec, p->chain[L.chain].max_clusters, st));
     else if (prec == R3D_PREC_FP32)
       CUDA_TRY(launch_gemm_ffma(d_ops + i, oh.dev, batch * oh.dev.rows_per_seq, st));
     else
@@ -1900,15 +1960,14 @@ extern "C" R3D_API int r3d_plan_set_option(r3d_plan* p, const char* name, int32_
   else if (k == "lanes") p->use_lanes = value >= 2;
   else if (k == "side_stream") both([&](r3d_plan* q) { q->use_side_stream = value != 0; });
   else if (k == "host_chunk") p->host_chunk = std::max(0, (int)value);
-  else if (k == "tail_fusion") {
-    if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "tail_fusion must be set before r3d_plan_finalize");
-    p->tail_fusion = value != 0;
+  else if (k == "tail_fusion" || k == "tail_width" || k == "side_chain" || k == "side_clusters") {
+    if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "%s must be set before r3d_plan_finalize", name);
+    if (k == "tail_fusion") p->tail_fusion = value != 0;
+    else if (k == "tail_width") p->tail_width = value >= 256 ? 256 : 128;
+    else if (k == "side_chain") { p->side_chain = value != 0; p->side_chain_force = value >= 2; }
+    else p->side_clusters = std::max(0, (int)value);
   }
-  else if (k == "tail_width") {
-    if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "tail_width must be set before r3d_plan_finalize");
-    p->tail_width = value >= 256 ? 256 : 128;
-  }
-  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion, tail_width)", name);
+  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion, tail_width, side_chain, side_clusters)", name);
   return R3D_OK;
 }
 
@@ -1923,7 +1982,7 @@ extern "C" R3D_API int r3d_plan_set_profiling(r3d_plan* p, int enable) {
 extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t cap, int32_t* n_launches, int32_t* n_runs) {
   if (!p) return fail(R3D_ERR_BAD_ARG, "null plan");
   std::lock_guard<std::mutex> lk(*p->mu);
-  const int nl = (int)(p->prof_tail ? p->launches : p->launches_flat).size() + 2, nev = 2 * nl;
+  const int nl = (int)p->launches[p->prof_variant].size() + 2, nev = 2 * nl;
   if (n_launches) *n_launches = nl;
   const int runs = std::min(p->prof_runs, kProfRing);
   if (n_runs) *n_runs = runs;
@@ -1944,7 +2003,7 @@ extern "C" R3D_API int r3d_plan_launch_times(r3d_plan* p, float* ms_out, int32_t
 
 extern "C" R3D_API const char* r3d_plan_launch_name(const r3d_plan* p, int32_t i) {
   if (!p) return "";
-  const auto& launches = p->prof_tail ? p->launches : p->launches_flat;
+  const auto& launches = p->launches[p->prof_variant];
   const int nl = (int)launches.size() + 2;
   if (i == 0) return "input_stage";
   if (i == nl - 1) return "output_stage";
@@ -2093,6 +2152,7 @@ extern "C" R3D_API int r3d_selftest_gemm(int32_t m, int32_t n, int32_t k, int32_
   }
   if (ms_ffma) *ms_ffma = ms;
   for (int rep = 0; rep < 2; ++rep) {
+    CUDA_TRY(cudaMemsetAsync(dSched, 0, 128, 0));
     CUDA_TRY(cudaEventRecord(e0, 0));
     CUDA_TRY(launch_gemm_tc(dT, t, dMaps, m, precision, 0));
     CUDA_TRY(cudaEventRecord(e1, 0));

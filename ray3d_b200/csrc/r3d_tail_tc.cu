@@ -577,7 +577,7 @@ cudaError_t tail_configure() {
 }
 
 template <int NS>
-static cudaError_t launch_tail(const GemmOpDev* d_ops, const CUtensorMap* tm, const MultiOpDev* d_mo, int units, int M, cudaStream_t s) {
+static cudaError_t launch_tail(const GemmOpDev* d_ops, const CUtensorMap* tm, const MultiOpDev* d_mo, int units, int M, int cap, cudaStream_t s) {
   const int sms = tc_num_sms();
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(TC_THREADS);
@@ -585,7 +585,7 @@ static cudaError_t launch_tail(const GemmOpDev* d_ops, const CUtensorMap* tm, co
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const int max_clusters = sms / 2;
+  const int max_clusters = (cap > 0 && cap < sms / 2) ? cap : sms / 2;
   cfg.gridDim = dim3(2 * (units < max_clusters ? units : max_clusters));
   cfg.dynamicSmemBytes = tail_smem_bytes<NS, 2>();
   attr[1].id = cudaLaunchAttributeClusterDimension;
@@ -598,13 +598,13 @@ static cudaError_t launch_tail(const GemmOpDev* d_ops, const CUtensorMap* tm, co
 }
 
 cudaError_t launch_tail_tc(const GemmOpDev* d_ops, const void* d_tmaps, const MultiOpDev* d_mo, const MultiOpDev& h_mo, int M, int precision,
-                           cudaStream_t s) {
+                           int max_clusters, cudaStream_t s) {
   if (M <= 0 || h_mo.nops <= 0) return cudaSuccess;
   if (tc_num_sms() <= 0) return cudaErrorNotReady;
   if (!tail_uses_pairs(M)) return cudaErrorInvalidValue;         // small batches keep one launch per op (narrower tiles)
   const int units = h_mo.unit0[h_mo.nops] * tail_row_groups(M);
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(d_tmaps);
-  return precision == R3D_PREC_BF16X3 ? launch_tail<2>(d_ops, tm, d_mo, units, M, s) : launch_tail<1>(d_ops, tm, d_mo, units, M, s);
+  return precision == R3D_PREC_BF16X3 ? launch_tail<2>(d_ops, tm, d_mo, units, M, max_clusters, s) : launch_tail<1>(d_ops, tm, d_mo, units, M, max_clusters, s);
 }
 
 }  // namespace r3d

@@ -184,14 +184,20 @@ def test_inputs_on_the_wrong_device_or_of_the_wrong_kind_are_refused():
 
 @pytest.mark.parametrize("stage", [1, 3])
 def test_chained_tail_launch_is_bit_identical(stage):
-    """Option tail_fusion: the one-row layers (top tree level, shrink, FuseBlocks, Integration; rie.py:94-105, 388-414) as ONE
-    persistent kernel whose work units wait on per-(op, problem, row group) completion counters.  Same tile code, same
-    arithmetic: outputs must equal the one-launch-per-layer form bit for bit (both unit widths, ragged last row group)."""
+    """Chained launches: the GlobalInfo chain (default, on a few CTA pairs of the side stream; rie.py:362) and -- option
+    tail_fusion -- the one-row layers of the main chain (top tree level, shrink, FuseBlocks, Integration; rie.py:94-105,
+    388-414) as ONE persistent kernel each, whose work units wait on per-(op, problem, row group) completion counters.
+    Same tile code, same arithmetic: outputs must equal the one-launch-per-layer form bit for bit (both unit widths,
+    ragged last row group, fewer CTA pairs than dependency chains)."""
     spec = NetSpec(filter_widths=(3, 3, 3), stage=stage)
     sp, st = synth.make_state_dicts(spec)
-    base = Lifter(spec, sp, st, precision="bf16x3")
-    for width in (128, 256):
-        lf = Lifter(spec, sp, st, precision="bf16x3", options={"tail_fusion": 1, "tail_width": width})
+    base = Lifter(spec, sp, st, precision="bf16x3", options={"side_chain": 0})        # every op its own launch
+    assert not any(L["tail"] for L in base.plan.describe()["launches"])
+    # (side_chain=2 forces the chained GlobalInfo launch: by default it is only planned for long receptive fields)
+    for opts in ({"side_chain": 2}, {"side_chain": 2, "side_clusters": 3}, {"tail_fusion": 1, "tail_width": 128, "side_chain": 2},
+                 {"tail_fusion": 1, "tail_width": 256, "side_chain": 0}):
+        lf = Lifter(spec, sp, st, precision="bf16x3", options=opts)
+        width = opts
         assert any(L["tail"] for L in lf.plan.describe()["launches"])
         for B in (700, 256, 300, 40):                     # < 256 windows: the plan falls back to one launch per op
             uv, cam = synth.make_inputs(spec, B, seed=90 + B)
