@@ -31,12 +31,17 @@ namespace r3d {
 
 constexpr int kOpSmemBytes = (sizeof(GemmOpDev) + 256 + 1023) / 1024 * 1024 - 256;   // keeps the staging tiles 1024-byte aligned
 // barriers, descriptor, per-warp hi/lo store staging tiles (double buffered in 2-SM mode, where the W half-tiles leave room)
-__host__ __device__ constexpr int tc_aux_bytes(int cl) { return 256 + kOpSmemBytes + 8 * 4096 * (cl == 2 ? 2 : 1) + (cl == 2 ? EPI_WARPS * 512 : 0); }
+// lean (the fused conv pair in 2-SM mode): ONE staging set per column half and the folded bias broadcast from registers
+// (warp shuffles) instead of a shared-memory copy -- its tiles are MMA-bound, the epilogue has slack -- which frees
+// exactly the 36 KB a third operand stage needs (3 x 64 KB + 35 KB = 227 KB)
+__host__ __device__ constexpr int tc_aux_bytes(int cl, bool lean = false) {
+  return 256 + kOpSmemBytes + 8 * 4096 * ((cl == 2 && !lean) ? 2 : 1) + ((cl == 2 && !lean) ? EPI_WARPS * 512 : 0);
+}
 
 // per-CTA bytes of one K block: A tile (128 rows) + this CTA's share of the W tile (all of it, or half in 2-SM mode)
 __host__ __device__ constexpr int tc_stage_bytes(int block_n, int nsplit, int cl = 1) { return nsplit * (TBM + block_n / cl) * TBK * 2; }
-__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1) {
-  int s = (SMEM_LIMIT - tc_aux_bytes(cl)) / tc_stage_bytes(block_n, nsplit, cl);
+__host__ __device__ constexpr int tc_num_stages(int block_n, int nsplit, int cl = 1, bool lean = false) {
+  int s = (SMEM_LIMIT - tc_aux_bytes(cl, lean)) / tc_stage_bytes(block_n, nsplit, cl);
   return s > 6 ? 6 : s;
 }
 __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
@@ -96,7 +101,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   // HALF of the W tile (the tensor cores read the other half from the peer's shared memory), which cuts the bytes
   // every SM has to receive per MMA by a third -- the measured limiter (~74 GB/s per SM from L2) -- and buys a third
   // pipeline stage.
-  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL);
+  constexpr bool LEAN = FUSED && CL == 2;
+  constexpr int STAGES = tc_num_stages(BLOCK_N, NSPLIT, CL, LEAN);
   constexpr int A_BYTES = TBM * TBK * 2, W_BYTES = (BLOCK_N / CL) * TBK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N, NSPLIT, CL);
   constexpr int TMEM_COLS = tc_tmem_cols(BLOCK_N);
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* sready_bar = reinterpret_cast<uint64_t*>(aux + 256 + sizeof(GemmOpDev));   // [column half][staging set], 4 arrivals
   uint64_t* sfree_bar = sready_bar + 8;                                                 // [column group][staging set]
   uint4* stage_s = reinterpret_cast<uint4*>(aux + 256 + kOpSmemBytes);            // [EPI_WARPS][sets][2 planes][32 rows x 64 B]
-  float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes + 8 * 4096 * (CL == 2 ? 2 : 1));   // CL == 2: [EPI_WARPS][128]
+  float* bias_s = reinterpret_cast<float*>(aux + 256 + kOpSmemBytes + 8 * 4096 * (CL == 2 ? 2 : 1));   // CL == 2 && !LEAN: [EPI_WARPS][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = ((M + TBM - 1) / TBM + CL - 1) / CL;      // m-tile groups (CL tiles each)
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     // plane moves all of it (4x fewer store instructions), and the epilogue warps convert the next chunk meanwhile.
     // Protocol per (column half, staging set): the four warps fill their slices, fence, arrive on sready (count 4);
     // this thread issues the stores, commits, and arrives on sfree once the store engine has read the set.
-    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;
+    constexpr int EPI_BUFS = (CL == 2 && !LEAN) ? 2 : 1;
     constexpr int GPS = COL_SPLIT > 2 ? COL_SPLIT / 2 : 1;      // column groups per store thread (1 with 8 epilogue warps)
     const int st = warp - 2;
     if (CH == 32 && lane == 0 && st >= 0 && st * GPS < COL_SPLIT) {
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
     const int half = ew >> 2;                                 // column group (half of the columns with 8 epilogue warps)
     const bool active = half < COL_SPLIT;
-    constexpr int EPI_BUFS = CL == 2 ? 2 : 1;    // staging tile sets per column group (hi + lo each)
+    constexpr int EPI_BUFS = (CL == 2 && !LEAN) ? 2 : 1;    // staging tile sets per column group (hi + lo each)
     // staging: [column group][set][plane] tiles of 128 rows x 64 B (64B-swizzled): the smem image of a (32 columns, 128 rows,
     // 2 planes) box, so ONE 3-D TMA store writes both planes; this warp owns rows [32 q, 32 q + 32)
     uint4* const stage_base = stage_s + half * EPI_BUFS * 1024;
@@ -505,7 +511,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     const float slope = op.slope;
     const bool etrace = trace && ew == 0;
     int ti = 0;
-    constexpr bool BIAS_SMEM = CL == 2;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
+    constexpr bool BIAS_SMEM = CL == 2 && !LEAN;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
+    constexpr bool BIAS_REG = LEAN;                   // ... LEAN: this tile's bias words stay in registers (lane = column) and are broadcast by shuffles
     constexpr int PB = CHUNKS_PER_WARP;                           // bias words per lane: one per chunk of this warp
     auto chunk_of = [&](int cc) { return (cc >> 1) * 4 + half * 2 + (cc & 1); };     // FUSED: first-GEMM chunk order
     // The epilogue warps are the critical path of the short-K launches: the coordinates and the folded bias of the NEXT
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     };
     int tile = DYN ? warp_pop() : unit0;
     TileCoord tc = decode_tile(op, tile < total_tiles ? tile : 0, per_m, BLOCK_N, CL, crank, total_tiles);
-    if (BIAS_SMEM && active && tile < total_tiles) prefetch_bias(tc);
+    if ((BIAS_SMEM || BIAS_REG) && active && tile < total_tiles) prefetch_bias(tc);
     uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
     for (int p = 0; p < op.nprob; ++p) {
       const GemmProb& g = op.prob[p];
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         if (DYN) next_tile = warp_pop();
         if (next_tile >= total_tiles) return;
         tn = decode_tile(op, next_tile, per_m, BLOCK_N, CL, crank, total_tiles);
-        if (BIAS_SMEM && active) prefetch_bias(tn);
+        if ((BIAS_SMEM || BIAS_REG) && active) prefetch_bias(tn);
       };
       const bool ttrace = etrace && R3D_DBG(128);                 // stamps of the per-tile preamble
       if (ttrace) R3D_TRACE(2, ti, 1);
@@ -582,6 +589,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           for (int i = 0; i < 4; ++i) my_bias[lane + 32 * i] = pa[i];
           __syncwarp();
         }
+        const float pa0 = pa[0], pa1 = pa[1], pa2 = pa[2], pa3 = pa[3];   // BIAS_REG: this tile's words (pa is refilled for the next tile)
         mbar_wait(&tfull_bar[0], acc_phase);
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -591,11 +599,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         for (int cc = 0; cc < 4; ++cc) {
           const int g = chunk_of(cc);
           float bb[32];
+          if (BIAS_REG) {
+            const float mine = cc == 0 ? pa0 : cc == 1 ? pa1 : cc == 2 ? pa2 : pa3;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = BIAS_SMEM ? *reinterpret_cast<const float4*>(my_bias + cc * 32 + j4 * 4)
-                                        : __ldg(reinterpret_cast<const float4*>(pr.bias + g * 32) + j4);
-            bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+            for (int j = 0; j < 32; ++j) bb[j] = __shfl_sync(0xffffffffu, mine, j);
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = BIAS_SMEM ? *reinterpret_cast<const float4*>(my_bias + cc * 32 + j4 * 4)
+                                          : __ldg(reinterpret_cast<const float4*>(pr.bias + g * 32) + j4);
+              bb[j4 * 4 + 0] = b4.x; bb[j4 * 4 + 1] = b4.y; bb[j4 * 4 + 2] = b4.z; bb[j4 * 4 + 3] = b4.w;
+            }
           }
           tmem_ld_wait();
           uint32_t yh[16], yl[16];
@@ -627,6 +641,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       const float* const bias_ptr = FUSED ? pr.bias2 : pr.bias;
       const int acc_col = FUSED ? BLOCK_N : acc * BLOCK_N;
       const int fb = FUSED ? 1 : acc;                          // accumulator-full / -empty barrier of this tile
+      float pbc[PB];                          // BIAS_REG: this tile's words
+#pragma unroll
+      for (int i = 0; i < PB; ++i) pbc[i] = pb[i];
       if (BIAS_SMEM && active) {              // this warp's slice of the folded bias (prefetched during the previous tile)
         __syncwarp();
 #pragma unroll
@@ -649,7 +666,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
           const int n = tc.n0 + chunk_index(half, cc) * CH;
           float bb[CH];
-          if (BIAS_SMEM) {
+          if (BIAS_REG) {
+            float mine = pbc[0];
+#pragma unroll
+            for (int i = 1; i < PB; ++i) mine = cc == i ? pbc[i] : mine;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) bb[j] = __shfl_sync(0xffffffffu, mine, j);
+          } else if (BIAS_SMEM) {
 #pragma unroll
             for (int j4 = 0; j4 < CH / 4; ++j4) {
               const float4 b4 = *reinterpret_cast<const float4*>(my_bias + cc * CH + j4 * 4);
@@ -899,8 +922,8 @@ int tc_build_tmaps(const GemmOpDev& h, int precision, int64_t cap_rows, void* ou
   return 0;
 }
 
-template <int BN, int NS, int CL = 1>
-static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL) * tc_stage_bytes(BN, NS, CL) + tc_aux_bytes(CL); }
+template <int BN, int NS, int CL = 1, bool LEAN = false>
+static constexpr int tc_smem_bytes() { return tc_num_stages(BN, NS, CL, LEAN) * tc_stage_bytes(BN, NS, CL) + tc_aux_bytes(CL, LEAN); }
 
 template <int BN, int NS>
 static cudaError_t configure_one() {
@@ -915,9 +938,9 @@ static cudaError_t configure_one() {
     constexpr int FB = BN == 256 ? 256 : 256;
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 1>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
+    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2, true>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
+    e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2, true>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<FB, NS, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<FB, NS, 2>());
   }
@@ -1007,6 +1030,7 @@ static cudaError_t launch_one(const GemmOpDev* d_op, const CUtensorMap* d_tmaps,
   // multi-wave 256-column launches claim their units dynamically (see DYN); the caller zeroes h.sched before the forward
   const bool dyn = (BN == 256 || BN == 128) && h.sched != nullptr && units >= 2 * clusters;
   if (BN == 256 && h.fused2) {
+    cfg.dynamicSmemBytes = tc_smem_bytes<256, NS, 2, true>();
     if (dyn) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true, true>, d_op, d_tmaps, M, units, dbg);
     return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, NS, 2, true>, d_op, d_tmaps, M, units, dbg);
   }

@@ -208,6 +208,7 @@ struct r3d_plan {
   bool tail_fusion = false;                           // (off: measured slower than one launch per layer)
   bool side_chain = true, side_chain_force = false;   // option "side_chain": 0 off, 1 when worth it (default), 2 always
   int tail_width = 128;                               // option "tail_width": unit width of chain 0 (128 or 256 columns)
+  int tail_clusters = 0;                              // option "tail_clusters": CTA pairs chain 0 may hold (0: the whole GPU)
   int side_clusters = 0;                              // option "side_clusters": CTA pairs the GlobalInfo chain may hold (0: from its flop share)
   size_t zero_bytes = 0;
   struct Launch { std::string name; std::vector<int> ops; int chain; };     // chain: -1 = one op
@@ -828,7 +829,10 @@ static void plan_chains(r3d_plan* p) {
     std::vector<int> mains;
     for (int i = first; i < nops; ++i)
       if (!p->ops[i].side) mains.push_back(i);
-    if (build_chain(p, mains, p->tail_width, p->chain[0].mo)) p->chain[0].ops = mains;
+    if (build_chain(p, mains, p->tail_width, p->chain[0].mo)) {
+      p->chain[0].ops = mains;
+      p->chain[0].max_clusters = p->tail_clusters;
+    }
   }
   if (tc && p->side_chain) {
     // The GlobalInfo chain only depends on the input stage and has ~600 us of slack before Integration.fc_1 needs it (at
@@ -1960,10 +1964,11 @@ extern "C" R3D_API int r3d_plan_set_option(r3d_plan* p, const char* name, int32_
   else if (k == "lanes") p->use_lanes = value >= 2;
   else if (k == "side_stream") both([&](r3d_plan* q) { q->use_side_stream = value != 0; });
   else if (k == "host_chunk") p->host_chunk = std::max(0, (int)value);
-  else if (k == "tail_fusion" || k == "tail_width" || k == "side_chain" || k == "side_clusters") {
+  else if (k == "tail_fusion" || k == "tail_width" || k == "tail_clusters" || k == "side_chain" || k == "side_clusters") {
     if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "%s must be set before r3d_plan_finalize", name);
     if (k == "tail_fusion") p->tail_fusion = value != 0;
     else if (k == "tail_width") p->tail_width = value >= 256 ? 256 : 128;
+    else if (k == "tail_clusters") p->tail_clusters = std::max(0, (int)value);
     else if (k == "side_chain") { p->side_chain = value != 0; p->side_chain_force = value >= 2; }
     else p->side_clusters = std::max(0, (int)value);
   }
