@@ -128,13 +128,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-  uint64_t* yready_bar = bars + 2 * STAGES + 4; // [2]  FUSED: channels [0,128) / [128,256) of the intermediate are in tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint64_t* yready_bar = bars + 2 * STAGES + 4; // [4]  FUSED: channels [64 k, 64 k + 64) of the intermediate (K block k of the second GEMM) are in tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
   constexpr int SQ = 4;                                           // DYN: unit queue depth (roles are at most ~2 tiles apart)
-  uint64_t* sq_full = bars + 2 * STAGES + 7;                      // [SQ] unit id published
+  uint64_t* sq_full = bars + 2 * STAGES + 9;                      // [SQ] unit id published
   uint64_t* sq_empty = sq_full + SQ;                              // [SQ] every consumer (of both CTAs) has read it; the leader's is used
   volatile uint32_t* sq_tile = reinterpret_cast<volatile uint32_t*>(sq_empty + SQ);   // [SQ]
-  static_assert((2 * 6 + 7 + 2 * SQ) * 8 + SQ * 4 <= 256, "barrier block overflows its 256 bytes");
+  static_assert((2 * 6 + 9 + 2 * SQ) * 8 + SQ * 4 <= 256, "barrier block overflows its 256 bytes");
   GemmOpDev* sop = reinterpret_cast<GemmOpDev*>(aux + 256);                        // op descriptor, smem resident
   // epilogue warp <-> store thread hand-off, per epilogue warp and staging set: "staged tile ready" / "staging set free"
   static_assert(sizeof(GemmOpDev) % 8 == 0 && 256 + sizeof(GemmOpDev) + 16 * 8 <= 256 + kOpSmemBytes, "no room for the store barriers");
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EW * CL);                // CL == 2: the peer's epilogue warps arrive remotely
-      mbar_init(&yready_bar[a], EW * CL);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&yready_bar[a], EW * CL);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&sready_bar[i], 4);                             // the four epilogue warps (TMEM lane quarters) of a column group
       mbar_init(&sfree_bar[i], 1);
@@ -374,19 +374,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         R3D_TRACE(1, ti, 3);
         if (FUSED) {
           // second GEMM: Y (bf16 hi/lo, written in place over acc1 by the epilogue warps) x W2^T -> acc2
-          // The epilogue warps convert Y in two halves; the K blocks over channels [0,128) start while the second
-          // half is still being converted.
-          mbar_wait(&yready_bar[0], acc_phase);               // first half of Y complete in both CTAs
-          if (op.flags & 1) mbar_wait(&yready_bar[1], acc_phase);
+          // The epilogue warps convert Y K block by K block (64 channels: the two warps of a TMEM lane quarter take one
+          // 32-channel chunk each): K block k of this GEMM starts as soon as its channels are there, while the later ones
+          // are still being converted.
+          if (op.flags & 1)
+            for (int k = 0; k < 4; ++k) mbar_wait(&yready_bar[k], acc_phase);
           mbar_wait(&tempty_bar[1], acc_phase ^ 1);           // previous tile's epilogue has drained acc2
           tc_fence_after();
           const uint32_t d2 = tmem_base + BLOCK_N;
           const int nkb2 = op.prob[tc.p].K2 / TBK;
           for (int kb = 0; kb < nkb2; ++kb) {
-            if (kb == nkb2 / 2) {
-              mbar_wait(&yready_bar[1], acc_phase);           // second half of Y
-              tc_fence_after();
-            }
+            mbar_wait(&yready_bar[kb & 3], acc_phase);        // channels [64 kb, 64 kb + 64) of Y complete in both CTAs
+            tc_fence_after();
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     constexpr bool BIAS_SMEM = CL == 2 && !LEAN;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
     constexpr bool BIAS_REG = LEAN;                   // ... LEAN: this tile's bias words stay in registers (lane = column) and are broadcast by shuffles
     constexpr int PB = CHUNKS_PER_WARP;                           // bias words per lane: one per chunk of this warp
-    auto chunk_of = [&](int cc) { return (cc >> 1) * 4 + half * 2 + (cc & 1); };     // FUSED: first-GEMM chunk order
+    auto chunk_of = [&](int cc) { return 2 * cc + half; };     // FUSED: this warp's cc-th chunk of the first GEMM = half of K block cc of the second
     // The epilogue warps are the critical path of the short-K launches: the coordinates and the folded bias of the NEXT
     // tile are fetched while the current tile is processed (registers), so no tile starts with an L2 round trip.
     float pb[PB], pa[4];
@@ -581,8 +580,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       float* my_bias = bias_s + ew * 128;
       if (FUSED) {
         // ---- epilogue of the first GEMM: acc1 -> Y = lrelu(acc1 + bias) as bf16 hi/lo, in place in tensor memory
-        // This warp converts chunks {2*half, 2*half+1} of the first 128 channels, signals, then the same two chunks of
-        // the second 128 channels: the MMA thread starts the second GEMM on the first half meanwhile.
+        // This warp converts chunk `half` of every 64-channel K block in turn and signals after each: the MMA thread
+        // starts the second GEMM on K block 0 while blocks 1..3 are still being converted.
         if (BIAS_SMEM) {
           __syncwarp();
 #pragma unroll
@@ -627,13 +626,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           if (cc + 1 < 4) tmem_ld32(ta + chunk_of(cc + 1) * 32, r1);
           tmem_st16(ta + g * 32, yh);                        // channels [32g, 32g+32) -> 16 packed columns
           if (NSPLIT == 2) tmem_st16(ta + g * 32 + 16, yl);
-          if (cc & 1) {                                      // a 128-channel half of Y is complete for this warp's rows
+          {                                                  // this warp's part of K block cc of Y is complete for its rows
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (CL == 1) mbar_arrive(&yready_bar[cc >> 1]);
-              else mbar_arrive_cluster(&yready_bar[cc >> 1], 0, (op.flags & 2) != 0);
+              if (CL == 1) mbar_arrive(&yready_bar[cc]);
+              else mbar_arrive_cluster(&yready_bar[cc], 0, (op.flags & 2) != 0);
             }
           }
         }
