@@ -192,8 +192,10 @@ R3D_API int r3d_submit_host(r3d_plan* plan, const r3d_input* in_host, float* pos
  * rie.py:362, as ONE persistent kernel on a few CTA pairs of the side stream, its work units ordered by per-row-group
  * completion counters, instead of six under-filled launches racing the tree's kernels for SMs), "side_clusters" (CTA
  * pairs it may hold; 0 = from its flop share), "tail_fusion" (0/1, default 0: the same for the one-row layers of the main
- * chain -- top tree level, shrink, FuseBlocks, Integration; bit-identical, measured slower on B200, kept for study) and
- * "tail_width" (128/256, its unit width). */
+ * chain -- top tree level, shrink, FuseBlocks, Integration; bit-identical, measured slower on B200, kept for study),
+ * "tail_width" (128/256, its unit width) and "tile_policy" (GEMM tile width of the narrow launches: 1 = latency, the
+ * shortest launch for a forward that has the GPU to itself; 2 = throughput, the widest tile, least SM time per flop
+ * when two batches are in flight; 0 = auto (default): throughput for plans of >= 256 windows capacity). */
 R3D_API int r3d_plan_set_option(r3d_plan* plan, const char* name, int32_t value);
 
 /* --- forward: replaces nn.Module.forward(x, param) ------------------------------------------------

@@ -210,6 +210,7 @@ struct r3d_plan {
   int tail_width = 128;                               // option "tail_width": unit width of chain 0 (128 or 256 columns)
   int tail_clusters = 0;                              // option "tail_clusters": CTA pairs chain 0 may hold (0: the whole GPU)
   int side_clusters = 0;                              // option "side_clusters": CTA pairs the GlobalInfo chain may hold (0: from its flop share)
+  int tile_policy = 0;                                // option "tile_policy": 0 auto, 1 latency (wave-count model), 2 throughput (widest tiles)
   size_t zero_bytes = 0;
   struct Launch { std::string name; std::vector<int> ops; int chain; };     // chain: -1 = one op
   std::vector<Launch> launches[4];                    // GEMM launches of one forward; variant = (chain 0 used) | (chain 1 used) << 1
@@ -1020,7 +1021,7 @@ extern "C" R3D_API int r3d_plan_describe(const r3d_plan* p, char* out, int64_t c
     char sl[32];
     snprintf(sl, sizeof(sl), "%.9g", op.dev.slope);
     j += std::string(i ? "," : "") + "{\"name\":\"" + op.name + "\",\"rows_per_seq\":" + std::to_string(op.dev.rows_per_seq) +
-         ",\"slope\":" + sl + ",\"prob\":[";
+         ",\"slope\":" + sl + ",\"n_tile\":" + std::to_string(op.dev.n_tile) + ",\"prob\":[";
     for (int q = 0; q < op.dev.nprob; ++q) {
       const auto& b = op.bind[q];
       const PackedLayer& pl = p->layers.at(b.layer);
@@ -1292,10 +1293,15 @@ static int bind_workspace(r3d_plan* p, int cap) {
         g.N = l2.n;
       }
     }
-    // Tile-width heuristic for the tensor path: the widest tile maximises operand reuse, but the small-M launches
-    // (upper tree levels, FC chains) then occupy a fraction of the 148 SMs.  Minimise waves x (tile cost) with a
-    // fixed per-tile overhead; wave count is taken at the plan's capacity batch.
-    bool tile_heuristic = true;
+    // Tile width for the tensor path.  The widest tile maximises operand reuse (least L2->SM traffic per flop), but the
+    // small-M launches (upper tree levels, FC chains) then occupy a fraction of the 148 SMs.
+    //  * latency policy: minimise waves x (tile cost) with a fixed per-tile overhead, wave count at the plan's capacity
+    //    batch -- the shortest launch when the forward has the GPU to itself (small batches);
+    //  * throughput policy: keep the widest tile -- with two batches in flight (lanes) the SMs a narrow-grid launch leaves
+    //    free run the other batch's kernels, so SM-seconds per flop decide, not the launch's own duration (measured at
+    //    B=1024: every one of these launches 8-25 % longer in isolation, the step 1-2 % shorter).
+    // auto: throughput from 256 windows of capacity (where the chained launches start as well).
+    bool tile_heuristic = p->tile_policy == 1 || (p->tile_policy == 0 && !tail_uses_pairs(cap));
     if (const char* env = exp_env("R3D_TC_TILE_HEUR")) tile_heuristic = atoi(env) != 0;
     op.dev.n_tile_tail = 0;
     for (const auto& c : p->chain) {
@@ -1964,15 +1970,16 @@ extern "C" R3D_API int r3d_plan_set_option(r3d_plan* p, const char* name, int32_
   else if (k == "lanes") p->use_lanes = value >= 2;
   else if (k == "side_stream") both([&](r3d_plan* q) { q->use_side_stream = value != 0; });
   else if (k == "host_chunk") p->host_chunk = std::max(0, (int)value);
-  else if (k == "tail_fusion" || k == "tail_width" || k == "tail_clusters" || k == "side_chain" || k == "side_clusters") {
+  else if (k == "tail_fusion" || k == "tail_width" || k == "tail_clusters" || k == "side_chain" || k == "side_clusters" || k == "tile_policy") {
     if (p->uploaded || p->finalized) return fail(R3D_ERR_STATE, "%s must be set before r3d_plan_finalize", name);
     if (k == "tail_fusion") p->tail_fusion = value != 0;
     else if (k == "tail_width") p->tail_width = value >= 256 ? 256 : 128;
     else if (k == "tail_clusters") p->tail_clusters = std::max(0, (int)value);
     else if (k == "side_chain") { p->side_chain = value != 0; p->side_chain_force = value >= 2; }
+    else if (k == "tile_policy") p->tile_policy = std::min(2, std::max(0, (int)value));
     else p->side_clusters = std::max(0, (int)value);
   }
-  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion, tail_width, side_chain, side_clusters)", name);
+  else return fail(R3D_ERR_BAD_ARG, "unknown option '%s' (graph_max_batch, lanes, side_stream, host_chunk, tail_fusion, tail_width, side_chain, side_clusters, tile_policy)", name);
   return R3D_OK;
 }
 

@@ -207,6 +207,23 @@ def test_chained_tail_launch_is_bit_identical(stage):
         del lf
 
 
+def test_tile_policy_is_result_neutral():
+    """Option tile_policy picks the GEMM tile width of the narrow launches (latency: wave-count model; throughput: widest
+    tile; auto switches at 256 windows of capacity).  The K order of every dot product is the same: bit-identical."""
+    spec = NetSpec(filter_widths=(3, 3, 3), stage=1)
+    sp, st = synth.make_state_dicts(spec)
+    lat = Lifter(spec, sp, st, precision="bf16x3", options={"tile_policy": 1})
+    thr = Lifter(spec, sp, st, precision="bf16x3", options={"tile_policy": 2})
+    auto = Lifter(spec, sp, st, precision="bf16x3")
+    for B in (40, 600):
+        uv, cam = synth.make_inputs(spec, B, seed=70 + B)
+        uvc, camc = torch.from_numpy(uv).cuda(), torch.from_numpy(cam).cuda()
+        a, b, c = lat.forward_uv(uvc, camc), thr.forward_uv(uvc, camc), auto.forward_uv(uvc, camc)
+        assert all(torch.equal(x, y) and torch.equal(x, z) for x, y, z in zip(a, b, c)), B
+    tiles = lambda lf: [o["n_tile"] for o in lf.plan.describe()["ops"]]
+    assert tiles(auto) == tiles(thr) and all(x <= y for x, y in zip(tiles(lat), tiles(thr)))   # capacity grew to 600 windows
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
 def test_whole_evaluate_core_step_vs_the_reference(precision):
     """One video through Lifter.forward_video_tta / forward_video_uv(tta=True) + metrics.evaluate, against what the
