@@ -57,18 +57,41 @@ struct TileCoord {
 // from L2 instead of streaming it from HBM once per problem (measured: 575 MB -> DRAM reads for an 85 MB operand when
 // the walk was problem-major, because the 510 MB output stream flushes L2 in between).  With clusters a unit covers
 // `cl` consecutive m tiles (one per CTA of the pair).
-__device__ __forceinline__ TileCoord decode_tile(const GemmOpDev& op, int unit, int per_m, int block_n, int cl, int rank, int total) {
-  if (op.reverse) unit = total - 1 - unit;       // per_m = total / m_groups: sum over problems of their n tiles
-  const int mg = unit / per_m;
-  int rem = unit - mg * per_m;
-  int p = 0, n_tiles = 1;
-  for (;; ++p) {
-    n_tiles = op.prob[p].n_pad / block_n;
-    if (rem < n_tiles) break;
-    rem -= n_tiles;
+// The decode runs on the epilogue warps' critical path once per tile (next-tile look-ahead), so it is division- and
+// branch-free: per_m is inverted once per thread (exact for unit * per_m < 2^32), and the problem of a unit is found by
+// comparing against the packed prefix sums of the problems' n-tile counts (one byte each; <= 16 tiles x 6 problems).
+struct TileDecoder {
+  uint32_t magic;       // ceil(2^32 / per_m) (0: per_m == 1)
+  uint32_t per_m;
+  uint64_t cum;         // byte p: n tiles of problems [0, p); bytes >= nprob: 255
+  int flip;             // reversed walk: total - 1, else -1
+  __device__ __forceinline__ void init(const GemmOpDev& op, int per_m_, int block_n, int total) {
+    per_m = (uint32_t)per_m_; magic = per_m_ >= 2 ? 0xFFFFFFFFu / (uint32_t)per_m_ + 1u : 0u;
+    flip = op.reverse ? total - 1 : -1;
+    cum = 0;
+    uint32_t c = 0;
+    static_assert(kMaxProb <= 8, "prefix bytes");
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      cum |= (uint64_t)(p < op.nprob ? c : 255u) << (8 * p);
+      if (p < kMaxProb && p < op.nprob) c += (uint32_t)(op.prob[p].n_pad / block_n);
+    }
   }
-  return TileCoord{p, (mg * cl + rank) * TBM, rem * block_n};
-}
+  template <int BLOCK_N, int CL>
+  __device__ __forceinline__ TileCoord get(int unit, int rank) const {
+    if (flip >= 0) unit = flip - unit;           // per_m = total / m_groups: sum over problems of their n tiles
+    const uint32_t mg = magic ? __umulhi((uint32_t)unit, magic) : (uint32_t)unit;
+    const uint32_t rem = (uint32_t)unit - mg * per_m;
+    const uint32_t lo = (uint32_t)cum, hi = (uint32_t)(cum >> 32);
+    int p = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) p += rem >= ((lo >> (8 * i)) & 0xFFu) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p += rem >= ((hi >> (8 * i)) & 0xFFu) ? 1 : 0;
+    const uint32_t base = (uint32_t)(cum >> (8 * p)) & 0xFFu;
+    return TileCoord{p, (int)(mg * CL + rank) * TBM, (int)(rem - base) * BLOCK_N};
+  }
+};
 
 // Diagnostics (R3D_TC_DEBUG bit 32 / r3d_debug_tc_trace): CTA 0 records SM clock stamps per tile for its producer (role 0),
 // MMA thread (role 1) and first epilogue warp (role 2): [role][tile index < 64][event < 8].
@@ -148,6 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   const int per_m = total_tiles / m_tiles;                      // tiles per m group (all problems' n tiles)
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;      // static walk; DYN: unit0 = first unit, the rest is claimed
+  TileDecoder decode_unit;                                             // initialised once the descriptor is in shared memory
   // DYN queue consumers per CTA: MMA thread (leader) or TMA producer (peer), the active store threads, 8 epilogue warps
   constexpr int SQ_STORE = CH == 32 ? (COL_SPLIT >= 2 ? 2 : 1) : 0;
   constexpr int SQ_CONSUMERS = (1 + SQ_STORE + EW) * CL;
@@ -202,6 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const GemmOpDev& op = *sop;
+  decode_unit.init(op, per_m, BLOCK_N, total_tiles);
   // DYN: consumer side of the unit queue; every consuming role pops every unit, in order (qc = pops so far)
   uint32_t qc = 0;
   auto sq_pop = [&]() -> int {
@@ -252,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         if (DYN && leader) publish(tile);
         if (tile >= total_tiles) break;
         if (DYN && leader) claimed = n_static + (int)atomicAdd(op.sched, 1u);
-        const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord tc = decode_unit.get<BLOCK_N, CL>(tile, crank);
         const CUtensorMap* tm = tmaps + tc.p * kTmapsPerProb;
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
@@ -320,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       uint32_t phase = 0, acc_phase = 0;
       int ti = 0;
       for (int tile = next_unit(-1); tile < total_tiles; tile = next_unit(tile), ++ti) {
-        const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord tc = decode_unit.get<BLOCK_N, CL>(tile, crank);
         const int nkb = op.prob[tc.p].K / TBK;
         const uint64_t kmask = op.prob[tc.p].kmask ? op.prob[tc.p].kmask : ~0ull;
         R3D_TRACE(1, ti, 0);
@@ -442,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       int ti = 0;
       const bool strace3 = trace && st == 0;
       for (int tile = next_unit(-1); tile < total_tiles; tile = next_unit(tile), ++ti) {
-        const TileCoord tc = decode_tile(op, tile, per_m, BLOCK_N, CL, crank, total_tiles);
+        const TileCoord tc = decode_unit.get<BLOCK_N, CL>(tile, crank);
         const GemmProb& pr = op.prob[tc.p];
         const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
         bool any_bf = false;
@@ -459,6 +484,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             any = true;
             mbar_wait(&sready_bar[grp * 2 + b], uses & 1);
             if (strace3 && gi == 0 && cc < 4) R3D_TRACE(3, ti, 2 * cc);
+            if (GPS == 1 && EPI_BUFS == 2 && !R3D_DBG(16384) && prev_free != nullptr) {
+              // the previous store was issued a whole chunk ago: the engine has read its set long since -- hand it back
+              // BEFORE this chunk's fence/issue (~600 cycles), the client warps are about to ask for it
+              bulk_wait_read0();
+              mbar_arrive(prev_free);
+              prev_free = nullptr;
+            }
             // generic-proxy writes of the four client warps (ordered before this point by their mbarrier arrivals) ->
             // async proxy: ONE proxy fence here, on the causality path between the writes and the tensor stores, instead
             // of one per writing warp (the fence drains the SM's shared-memory pipe: 32 of them per tile serialised the
@@ -478,12 +510,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             bulk_commit();
             // The set is handed back as soon as the store engine has read it (a few hundred cycles), not one round later:
             // the client warps then never wait for their slowest peer's NEXT chunk before reusing a set.
-            if (GPS == 1) {
+            if (GPS == 1 && (EPI_BUFS == 1 || R3D_DBG(16384))) {
               bulk_wait_read0();
               if (strace3 && cc < 4) R3D_TRACE(3, ti, 2 * cc + 1);
               mbar_arrive(&sfree_bar[grp * 2 + b]);
-            } else {                                            // two groups alternate: wait for the previous group's store only
+            } else {                                            // two sets (or two groups) alternate: TWO stores in flight, wait for the previous one only
               bulk_wait_read1();
+              if (strace3 && cc < 4) R3D_TRACE(3, ti, 2 * cc + 1);
               if (prev_free != nullptr) mbar_arrive(prev_free);
               prev_free = &sfree_bar[grp * 2 + b];
             }
@@ -507,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
     uint32_t sround = 0;                                      // chunks this warp has handed to its store thread
     int acc = 0;
     uint32_t acc_phase = 0;
-    const float slope = op.slope;
+    const float2 slope2 = make_float2(op.slope, op.slope);
     const bool etrace = trace && ew == 0;
     int ti = 0;
     constexpr bool BIAS_SMEM = CL == 2 && !LEAN;     // with (almost) all of L1 carved out as smem every bias LDG is an L2 round trip
@@ -535,7 +568,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
       return t;
     };
     int tile = DYN ? warp_pop() : unit0;
-    TileCoord tc = decode_tile(op, tile < total_tiles ? tile : 0, per_m, BLOCK_N, CL, crank, total_tiles);
+    TileCoord tc = decode_unit.get<BLOCK_N, CL>(tile < total_tiles ? tile : 0, crank);
     if ((BIAS_SMEM || BIAS_REG) && active && tile < total_tiles) prefetch_bias(tc);
     uint32_t pflags = 0;          // per problem: bit 0 any fp32 destination, 1 any bf16 destination, 2 any lo plane, 3 residual
     for (int p = 0; p < op.nprob; ++p) {
@@ -560,12 +593,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
         next_ready = true;
         if (DYN) next_tile = warp_pop();
         if (next_tile >= total_tiles) return;
-        tn = decode_tile(op, next_tile, per_m, BLOCK_N, CL, crank, total_tiles);
+        tn = decode_unit.get<BLOCK_N, CL>(next_tile, crank);
         if ((BIAS_SMEM || BIAS_REG) && active) prefetch_bias(tn);
       };
       const bool ttrace = etrace && R3D_DBG(128);                 // stamps of the per-tile preamble
       if (ttrace) R3D_TRACE(2, ti, 1);
-      const CUtensorMap* dmaps = tmaps + tc.p * kTmapsPerProb + 6;      // [dst][hi, lo] store maps
       const int m_base = tc.m0 + q * 32;
       const int row = m_base + lane;
       const bool row_ok = row < M;
@@ -613,16 +645,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
           tmem_ld_wait();
           uint32_t yh[16], yl[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x0 = __uint_as_float(r1[2 * j]) + bb[2 * j], x1 = __uint_as_float(r1[2 * j + 1]) + bb[2 * j + 1];
-            x0 = fmaxf(x0, slope * x0);
-            x1 = fmaxf(x1, slope * x1);
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-            yh[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            const float2 hf = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-            yl[j] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
+          for (int j = 0; j < 16; ++j)
+            split_bf16x2(bias_lrelu2(r1[2 * j], r1[2 * j + 1], bb[2 * j], bb[2 * j + 1], slope2), yh[j], yl[j]);
           if (cc + 1 < 4) tmem_ld32(ta + chunk_of(cc + 1) * 32, r1);
           tmem_st16(ta + g * 32, yh);                        // channels [32g, 32g+32) -> 16 packed columns
           if (NSPLIT == 2) tmem_st16(ta + g * 32 + 16, yl);
@@ -664,6 +688,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS_PER_WARP; ++cc) {
           const int n = tc.n0 + chunk_index(half, cc) * CH;
+          const bool strace = etrace && R3D_DBG(64) && !R3D_DBG(128) && cc == ((dbg >> 16) & 3);     // sub-step stamps of one chunk (bits 16-17)
+          if (strace) R3D_TRACE(2, ti, 1);
           float bb[CH];
           if (BIAS_REG) {
             float mine = pbc[0];
@@ -685,26 +711,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             }
           }
           tmem_ld_wait();
-          const bool strace = etrace && R3D_DBG(64) && !R3D_DBG(128) && cc == 1;     // sub-step stamps of one steady-state chunk
           if (strace) R3D_TRACE(2, ti, 3);
+          // staging set of this chunk: probe its "free" barrier now, the answer (a ~150-cycle shared-memory round trip on
+          // this warp's in-order critical path) arrives behind the activation math
+          const int sbuf = EPI_BUFS == 2 ? (int)(sround & 1) : 0;
+          const uint32_t sfree_parity = ((EPI_BUFS == 2 ? sround >> 1 : sround) & 1) ^ 1;
+          const bool set_free = CH == 32 && mbar_try_wait(&sfree_bar[half * 2 + sbuf], sfree_parity);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const float x = __uint_as_float(r[j]) + bb[j];
-            v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
+          for (int j = 0; j < CH / 2; ++j) {
+            const float2 a = bias_lrelu2(r[2 * j], r[2 * j + 1], bb[2 * j], bb[2 * j + 1], slope2);
+            v[2 * j] = a.x;
+            v[2 * j + 1] = a.y;
           }
           if (cc + 1 < CHUNKS_PER_WARP) {        // next chunk's accumulator columns: in flight during this chunk's stores
             if (CH == 32) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r); else tmem_ld16(taddr0 + chunk_index(half, cc + 1) * CH, r);
           }
+          if (strace) R3D_TRACE(2, ti, 0);
           if (cc > 0) look_ahead();              // not in chunk 0: the store thread is waiting for that one
+          if (strace) R3D_TRACE(2, ti, 2);
           if (n < pr.N && !R3D_DBG(4)) {          // warp-uniform
             // the TMA stores that last used this staging set must have finished reading it (with two sets the store
             // of the previous chunk may still be in flight)
-            const int sbuf = EPI_BUFS == 2 ? (int)(sround & 1) : 0;
             uint4* const stage_hi = stage_base + sbuf * 1024 + q * 128;   // this warp's rows of the hi-plane tile (also its residual scratch)
             uint4* const stage_lo = stage_hi + 512;                        // lo-plane tile: the next 8 KB
             if (CH == 32) {    // the store thread has released this staging set (its previous stores have read it)
-              mbar_wait(&sfree_bar[half * 2 + sbuf], (((EPI_BUFS == 2 ? sround >> 1 : sround) & 1) ^ 1));
+              if (!set_free) mbar_wait(&sfree_bar[half * 2 + sbuf], sfree_parity);
               if (strace) R3D_TRACE(2, ti, 4);
             }
             if (has_res) {
@@ -733,13 +765,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
             if (any_bf) {
               uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int j = 0; j < CH / 2; ++j) {
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-                lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
-              }
+              for (int j = 0; j < CH / 2; ++j) split_bf16x2(make_float2(v[2 * j], v[2 * j + 1]), hi[j], lo[j]);
               if (CH == 32) {
                 // thread = row -> swizzled staging tiles -> one TMA store per destination plane (the TMA engine does
                 // the address generation / coalescing; rows past the buffer capacity are clipped by the tensor map,

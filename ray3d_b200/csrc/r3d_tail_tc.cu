@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
         any_lo |= pr.dst[t].f32 == 0 && pr.dst[t].m.p1 != nullptr;
       }
       const bool has_res = pr.res.p0 != nullptr;
-      const float slope = td.slope;
+      const float2 slope2 = make_float2(td.slope, td.slope);
       const __nv_bfloat16* res_hi = reinterpret_cast<const __nv_bfloat16*>(pr.res.p0);
       const __nv_bfloat16* res_lo = reinterpret_cast<const __nv_bfloat16*>(pr.res.p1);
       ResidualRegs rr;
@@ -478,9 +478,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
           tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const float x = __uint_as_float(r[j]) + bb[j];
-            v[j] = fmaxf(x, slope * x);          // LeakyReLU for 0 < slope <= 1 (slope == 1: identity)
+          for (int j = 0; j < CH / 2; ++j) {
+            const float2 a = bias_lrelu2(r[2 * j], r[2 * j + 1], bb[2 * j], bb[2 * j + 1], slope2);
+            v[2 * j] = a.x;
+            v[2 * j + 1] = a.y;
           }
           if (cc + 1 < cpw) tmem_ld32(taddr0 + chunk_index(half, cc + 1) * CH, r);
           if (cc > 0) look_ahead(false);
@@ -508,13 +509,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tail_tc_kernel(const GemmOpDev*
             if (any_bf) {
               uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int j = 0; j < CH / 2; ++j) {
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-                lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
-              }
+              for (int j = 0; j < CH / 2; ++j) split_bf16x2(make_float2(v[2 * j], v[2 * j + 1]), hi[j], lo[j]);
               stage_write(stage_hi, hi, lane);
               if (any_lo) stage_write(stage_lo, lo, lane);
               __syncwarp();
