@@ -957,7 +957,7 @@ static cudaError_t configure_one() {
   constexpr int CL2 = BN >= 32 ? 2 : 1;
   if (BN >= 32) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, CL2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, CL2>());
   if (e != cudaSuccess) return e;
-  if (BN == 128) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, CL2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, CL2>());
+  if constexpr (BN == 128) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NS, CL2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<BN, NS, CL2>());
   if (e != cudaSuccess) return e;
   if (BN == 256) {   // fused conv-pair variants
     constexpr int FB = BN == 256 ? 256 : 256;
