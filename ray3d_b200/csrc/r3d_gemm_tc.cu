@@ -8,8 +8,8 @@
 // as hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory (R3D_PREC_BF16X3, ~1e-5 normwise
 // end to end), or hi*hi only (R3D_PREC_BF16).
 //
-// Structure (one persistent CTA per SM -- a CTA pair per tile in 2-SM mode --, 384 threads, static round-robin tile
-// schedule):
+// Structure (one persistent CTA per SM -- a CTA pair per tile in 2-SM mode --, 384 threads; static round-robin unit
+// walk, or -- DYN, multi-wave 2-SM launches -- units claimed with atomicAdd and published through a shared-memory queue):
 //   warp 0       TMA producer: cp.async.bulk.tensor 2D loads of the A / W planes of one 64-wide K block into a ring of
 //                128B-swizzled smem stages, completion on "full" mbarriers; K blocks whose 16-column steps all carry
 //                zero weights (GemmProb::kmask) are never staged; L2 hints per operand class
@@ -19,8 +19,8 @@
 //   warp 2       allocates / frees the TMEM columns (two accumulator stages; acc1/Y + acc2 in the fused conv pair)
 //   warps 2, 3   lane 0: store threads -- one TMA tensor store per destination for the 128-row staging tile that the four
 //                epilogue warps of a column group have filled (sready / sfree mbarriers)
-//   warps 4..11  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and chunk), bias + LeakyReLU + residual in registers,
-//                re-split to bf16 hi/lo, 64B-swizzled staging tiles in shared memory
+//   warps 4..11  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and chunk), bias + LeakyReLU + residual in registers
+//                (packed fp32x2 ALU operations), re-split to bf16 hi/lo, 64B-swizzled staging tiles in shared memory
 // so the epilogue of tile i overlaps the main loop of tile i+1.  FUSED: see gemm_tc_kernel below.
 #include <cstdlib>
 #include <cstring>
@@ -223,10 +223,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmOpDev*
   // Programmatic dependent launch: everything above (descriptor copy, barrier init, TMEM allocation) only touches
   // launch-invariant data and overlaps the tail of the previous kernel in the stream; activations written by that
   // kernel are first touched below.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
   const GemmOpDev& op = *sop;
   decode_unit.init(op, per_m, BLOCK_N, total_tiles);
+  if (lane == 0 && warp < 4 && warp != 1 && !R3D_DBG(32768)) {
+    // tensor maps of this CTA's first unit (operand loads: warp 0, stores: warps 2/3) into the descriptor cache while the
+    // previous kernel drains -- their first use sits on the first tile's critical path otherwise
+    const TileCoord t0 = decode_unit.get<BLOCK_N, CL>(unit0 < total_tiles ? unit0 : 0, crank);
+    const CUtensorMap* tm = tmaps + t0.p * kTmapsPerProb;
+    if (warp == 0) {
+      for (int i = 0; i < 6; ++i) tmap_prefetch(tm + i);
+    } else {
+      for (int t = warp - 2; t < 2 * op.prob[t0.p].ndst; t += 2) tmap_prefetch(tm + 6 + t);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
   // DYN: consumer side of the unit queue; every consuming role pops every unit, in order (qc = pops so far)
   uint32_t qc = 0;
   auto sq_pop = [&]() -> int {
