@@ -159,8 +159,12 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * blockDim.x;
         if (i < T * J) {
-          const int jj = i % J;
-          pv[u] = __ldg(uv + (flip ? i - jj + d.flip_perm[jj] : i));
+          int is = i;
+          if (flip) {                                   // (the modulo costs three XU operations: mirrored windows only)
+            const int jj = i % J;
+            is = i - jj + d.flip_perm[jj];
+          }
+          pv[u] = __ldg(uv + is);
         }
       }
 #pragma unroll
