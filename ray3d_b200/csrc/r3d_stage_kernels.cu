@@ -124,6 +124,18 @@ __device__ __forceinline__ float3 encode_keypoint(float2 p, const CamRow& c) {
   return make_float3((float)xn, (float)__dadd_rn(__dmul_rn(c.cp, yn), c.sp), (float)__dadd_rn(__dmul_rn(-c.sp, yn), c.cp));
 }
 
+// Hidden layer of the camera embedding (embedding.py:15-16, BN folded, fp32 FFMA): one thread per hidden unit of every net.
+__device__ __forceinline__ void embed_hidden(const PrologueDev& d, const float (&prm)[8], float* scratch) {
+  const int mid = d.emb_mid;
+  for (int t = threadIdx.x; t < d.n_embed * mid; t += blockDim.x) {
+    const EmbedDev& em = d.embed[t / mid];
+    const int j = t % mid;
+    float acc = __ldg(em.b1 + j);
+    for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(__ldg(em.w1 + j * d.ext_dim + i), prm[i], acc);
+    scratch[t] = acc > 0.f ? acc : 0.01f * acc;
+  }
+}
+
 // One CTA per sequence (window).  Dynamic smem: T*J*Cin floats (+ embed scratch).
 // src_kind R3D_SRC_UV: pixel keypoints, camera rows per cam_kind; R3D_SRC_RAYS: encoded input, `cam` = param rows (float).
 template <bool UNDIST>
@@ -132,7 +144,15 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
                                                        int src_is_uv, const void* __restrict__ cam, int64_t cam_stride,
                                                        int cam_kind, int batch, int flip_from) {
   extern __shared__ float smem[];
-  const PrologueDev& d = *dp;
+  // The descriptor (~600 bytes: shapes, destination pointers, embedder pointers) goes to shared memory first: read through
+  // `dp` its fields are L2 round trips whenever the streamed keypoints have pushed them out of the small L1, and the
+  // camera embedding at the end of the CTA chained three of those (pointer -> pointer -> value) with nothing to hide them.
+  __shared__ PrologueDev sd;
+  static_assert(sizeof(PrologueDev) % 4 == 0, "word copy");
+  for (int i = threadIdx.x; i < (int)(sizeof(PrologueDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sd)[i] = __ldg(reinterpret_cast<const uint32_t*>(dp) + i);
+  __syncthreads();
+  const PrologueDev& d = sd;
   const int b = blockIdx.x;
   // flip test-time augmentation (trainer.py:299-302): windows [flip_from, batch) are the mirrored copies of
   // windows [0, batch - flip_from): x component negated, left/right joints swapped, same camera parameters
@@ -150,6 +170,7 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     const CamRow c = load_cam(cam, cam_stride, cam_kind, bs);
     prm[0] = c.height;
     prm[1] = c.pitch;
+    embed_hidden(d, prm, scratch);       // (its two loads fly while the keypoints are fetched; published by the barrier below)
     const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
     // keypoints are fetched in batches of 8 independent loads per thread before any float64 math touches them
     // (one HBM round trip per batch instead of one per keypoint)
@@ -179,6 +200,8 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       }
     }
   } else {
+    for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = reinterpret_cast<const float*>(cam)[(int64_t)bs * cam_stride + i];
+    embed_hidden(d, prm, scratch);
     const float* x = src + (int64_t)bs * src_batch_stride;
     if (!flip) {
       for (int i = threadIdx.x; i < T * JC; i += blockDim.x) xs[i] = __ldg(x + i);
@@ -292,17 +315,7 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
 
   // ---- 4. camera embedding (embedding.py:15-19), BN folded, fp32 FFMA; both nets' embedders side by side ----------
   if (d.n_embed > 0) {
-    const int mid = d.emb_mid, ne = d.n_embed;
-    if (!src_is_uv)
-      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = reinterpret_cast<const float*>(cam)[(int64_t)bs * cam_stride + i];
-    for (int t = threadIdx.x; t < ne * mid; t += blockDim.x) {           // hidden layer
-      const EmbedDev& em = d.embed[t / mid];
-      const int j = t % mid;
-      float acc = em.b1[j];
-      for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(em.w1[j * d.ext_dim + i], prm[i], acc);
-      scratch[t] = acc > 0.f ? acc : 0.01f * acc;
-    }
-    __syncthreads();
+    const int mid = d.emb_mid, ne = d.n_embed;     // (hidden layer: embed_hidden at the top of the kernel)
     for (int t = threadIdx.x; t < ne * d.emb_dim; t += blockDim.x) {     // output layer: 8 independent loads per step
       const int e = t / d.emb_dim, j = t % d.emb_dim;
       const EmbedDev& em = d.embed[e];
