@@ -125,14 +125,43 @@ __device__ __forceinline__ float3 encode_keypoint(float2 p, const CamRow& c) {
 }
 
 // Hidden layer of the camera embedding (embedding.py:15-16, BN folded, fp32 FFMA): one thread per hidden unit of every net.
-__device__ __forceinline__ void embed_hidden(const PrologueDev& d, const float (&prm)[8], float* scratch) {
+__device__ __forceinline__ void embed_hidden(const PrologueDev& d, const float (&prm)[8], float* scratch, int tid, int nthr) {
   const int mid = d.emb_mid;
-  for (int t = threadIdx.x; t < d.n_embed * mid; t += blockDim.x) {
+  for (int t = tid; t < d.n_embed * mid; t += nthr) {
     const EmbedDev& em = d.embed[t / mid];
     const int j = t % mid;
     float acc = __ldg(em.b1 + j);
     for (int i = 0; i < d.ext_dim; ++i) acc = fmaf(__ldg(em.w1 + j * d.ext_dim + i), prm[i], acc);
     scratch[t] = acc > 0.f ? acc : 0.01f * acc;
+  }
+}
+
+// Output layer of the camera embedding (embedding.py:17-19) by the thread group [0, nthr): one thread per output of every net.
+__device__ __forceinline__ void embed_output(const PrologueDev& d, int precision, int b, const float* scratch, int tid, int nthr) {
+  const int mid = d.emb_mid;
+  for (int t = tid; t < d.n_embed * d.emb_dim; t += nthr) {
+    const int e = t / d.emb_dim, j = t % d.emb_dim;
+    const EmbedDev& em = d.embed[e];
+    const float* w = em.w2 + j * mid;
+    const float* h = scratch + e * mid;
+    float acc = __ldg(em.b2 + j);
+    int i = 0;
+    // the weight row is fetched 16 floats (four 16-byte loads) per L2 round trip
+    for (; i + 16 <= mid; i += 16) {
+      float4 wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const float4*>(w + i) + u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                                       // same summation order as the scalar loop
+        acc = fmaf(wv[u].x, h[i + 4 * u], acc);
+        acc = fmaf(wv[u].y, h[i + 4 * u + 1], acc);
+        acc = fmaf(wv[u].z, h[i + 4 * u + 2], acc);
+        acc = fmaf(wv[u].w, h[i + 4 * u + 3], acc);
+      }
+    }
+    for (; i < mid; ++i) acc = fmaf(__ldg(w + i), h[i], acc);
+    acc = acc > 0.f ? acc : 0.01f * acc;
+    for (int q = 0; q < em.ndst; ++q) store_act(em.dst[q].m, precision, b, em.dst[q].col + j, acc);
   }
 }
 
@@ -148,6 +177,8 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   // `dp` its fields are L2 round trips whenever the streamed keypoints have pushed them out of the small L1, and the
   // camera embedding at the end of the CTA chained three of those (pointer -> pointer -> value) with nothing to hide them.
   __shared__ PrologueDev sd;
+  __shared__ int kp_next;                  // next 256-keypoint chunk of the window (claimed warp by warp)
+  if (threadIdx.x == 0) kp_next = 0;
   static_assert(sizeof(PrologueDev) % 4 == 0, "word copy");
   for (int i = threadIdx.x; i < (int)(sizeof(PrologueDev) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&sd)[i] = __ldg(reinterpret_cast<const uint32_t*>(dp) + i);
@@ -170,16 +201,31 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     const CamRow c = load_cam(cam, cam_stride, cam_kind, bs);
     prm[0] = c.height;
     prm[1] = c.pitch;
-    embed_hidden(d, prm, scratch);       // (its two loads fly while the keypoints are fetched; published by the barrier below)
+    // The camera embedding first, by warps 0-3 only (own named barrier between its two layers): its dependent L2 round
+    // trips (bias / weight rows) are then hidden by the other warps' keypoint work instead of sitting at the end of the
+    // CTA with nothing beside them (7 of the stage's 44 us).  The keypoints are claimed in chunks of 256 by whichever
+    // warp is free, so the embedding warps simply encode fewer of them.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d.n_embed > 0 && warp < 4) {
+      embed_hidden(d, prm, scratch, threadIdx.x, 128);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      embed_output(d, precision, b, scratch, threadIdx.x, 128);
+    }
     const float2* uv = reinterpret_cast<const float2*>(src + (int64_t)bs * src_batch_stride);
     // keypoints are fetched in batches of 8 independent loads per thread before any float64 math touches them
     // (one HBM round trip per batch instead of one per keypoint)
-    for (int i0 = threadIdx.x; i0 < T * J; i0 += 8 * blockDim.x) {
+    const int nkp = T * J;
+    for (;;) {
+      int chunk = 0;
+      if (lane == 0) chunk = atomicAdd(&kp_next, 1);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      const int i0 = chunk * 256 + lane;
+      if (chunk * 256 >= nkp) break;
       float2 pv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (i < T * J) {
+        const int i = i0 + u * 32;
+        if (i < nkp) {
           int is = i;
           if (flip) {                                   // (the modulo costs three XU operations: mirrored windows only)
             const int jj = i % J;
@@ -190,8 +236,8 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (i < T * J) {
+        const int i = i0 + u * 32;
+        if (i < nkp) {
           const float3 r = encode_keypoint<UNDIST>(pv[u], c);
           xs[i * 3 + 0] = flip ? -r.x : r.x;
           xs[i * 3 + 1] = r.y;
@@ -200,8 +246,12 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
       }
     }
   } else {
-    for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = reinterpret_cast<const float*>(cam)[(int64_t)bs * cam_stride + i];
-    embed_hidden(d, prm, scratch);
+    if (d.n_embed > 0 && threadIdx.x < 128) {
+      for (int i = 0; i < d.ext_dim && i < 8; ++i) prm[i] = reinterpret_cast<const float*>(cam)[(int64_t)bs * cam_stride + i];
+      embed_hidden(d, prm, scratch, threadIdx.x, 128);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      embed_output(d, precision, b, scratch, threadIdx.x, 128);
+    }
     const float* x = src + (int64_t)bs * src_batch_stride;
     if (!flip) {
       for (int i = threadIdx.x; i < T * JC; i += blockDim.x) xs[i] = __ldg(x + i);
@@ -313,35 +363,6 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   for (int i = threadIdx.x; i < d.inc.ld; i += blockDim.x)
     store_act(d.inc, precision, b, i, i < JC ? xs[d.tc * JC + i] : 0.f);
 
-  // ---- 4. camera embedding (embedding.py:15-19), BN folded, fp32 FFMA; both nets' embedders side by side ----------
-  if (d.n_embed > 0) {
-    const int mid = d.emb_mid, ne = d.n_embed;     // (hidden layer: embed_hidden at the top of the kernel)
-    for (int t = threadIdx.x; t < ne * d.emb_dim; t += blockDim.x) {     // output layer: 8 independent loads per step
-      const int e = t / d.emb_dim, j = t % d.emb_dim;
-      const EmbedDev& em = d.embed[e];
-      const float* w = em.w2 + j * mid;
-      const float* h = scratch + e * mid;
-      float acc = em.b2[j];
-      int i = 0;
-      // the weight row is fetched 16 floats (four 16-byte loads) per round trip: this loop runs at the end of the CTA with
-      // nothing else to hide the L2 latency (ncu: a third of the stage's warp samples sat here with four 8-float rounds)
-      for (; i + 16 <= mid; i += 16) {
-        float4 wv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const float4*>(w + i) + u);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                                       // same summation order as the scalar loop
-          acc = fmaf(wv[u].x, h[i + 4 * u], acc);
-          acc = fmaf(wv[u].y, h[i + 4 * u + 1], acc);
-          acc = fmaf(wv[u].z, h[i + 4 * u + 2], acc);
-          acc = fmaf(wv[u].w, h[i + 4 * u + 3], acc);
-        }
-      }
-      for (; i < mid; ++i) acc = fmaf(w[i], h[i], acc);
-      acc = acc > 0.f ? acc : 0.01f * acc;
-      for (int q = 0; q < em.ndst; ++q) store_act(em.dst[q].m, precision, b, em.dst[q].col + j, acc);
-    }
-  }
 }
 
 static int g_prologue_smem_cap = 48 * 1024;
