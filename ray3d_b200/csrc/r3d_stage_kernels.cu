@@ -180,15 +180,28 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
   __shared__ int kp_next;                  // next 256-keypoint chunk of the window (claimed warp by warp)
   if (threadIdx.x == 0) kp_next = 0;
   static_assert(sizeof(PrologueDev) % 4 == 0, "word copy");
-  for (int i = threadIdx.x; i < (int)(sizeof(PrologueDev) / 4); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(&sd)[i] = __ldg(reinterpret_cast<const uint32_t*>(dp) + i);
-  __syncthreads();
-  const PrologueDev& d = sd;
   const int b = blockIdx.x;
   // flip test-time augmentation (trainer.py:299-302): windows [flip_from, batch) are the mirrored copies of
   // windows [0, batch - flip_from): x component negated, left/right joints swapped, same camera parameters
   const bool flip = b >= flip_from;
   const int bs = flip ? b - flip_from : b;
+  // descriptor words and the camera row are requested together (two independent L2 round trips at the head of every CTA)
+  constexpr int kDescWords = (int)(sizeof(PrologueDev) / 4), kDescPerThread = (kDescWords + 255) / 256;
+  uint32_t dw[kDescPerThread];
+#pragma unroll
+  for (int k = 0; k < kDescPerThread; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    dw[k] = i < kDescWords ? __ldg(reinterpret_cast<const uint32_t*>(dp) + i) : 0u;
+  }
+  CamRow c{};
+  if (src_is_uv) c = load_cam(cam, cam_stride, cam_kind, bs);      // camera.py:438-439,471 in float64
+#pragma unroll
+  for (int k = 0; k < kDescPerThread; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    if (i < kDescWords) reinterpret_cast<uint32_t*>(&sd)[i] = dw[k];
+  }
+  __syncthreads();
+  const PrologueDev& d = sd;
   const int T = d.T, J = d.J, JC = d.JC;
   float* xs = smem;                    // [T][JC]
   float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
@@ -197,8 +210,7 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
 
   // ---- 1. stage the (ray-encoded) window in shared memory -----------------------------------
   if (src_is_uv) {
-    // camera.py:438-439,471 in float64, then .astype(float32) (trainer.py:298)
-    const CamRow c = load_cam(cam, cam_stride, cam_kind, bs);
+    // ray encode in float64, then .astype(float32) (trainer.py:298)
     prm[0] = c.height;
     prm[1] = c.pitch;
     // The camera embedding first, by warps 0-3 only (own named barrier between its two layers): its dependent L2 round
