@@ -313,27 +313,27 @@ __global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __rest
     if (kp == 256 && precision != R3D_PREC_FP32) {
       // the shipped configurations on the tensor path: a lane owns 8 ADJACENT columns -- one 16-byte store per plane and
       // row (512 contiguous bytes per warp), the hi/lo split on packed fp32x2 operations
-      int off[8];
-      uint32_t relbits = 0;
+      int cur[8], step[8];        // source offset of this lane's 8 columns for the warp's current row / its advance per row
       {
         const int4 e0 = __ldg(reinterpret_cast<const int4*>(d.a0_off + lane * 8)), e1 = __ldg(reinterpret_cast<const int4*>(d.a0_off + lane * 8) + 1);
         const int e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          off[j] = e[j] & ~kRowRel;
-          relbits |= (e[j] & kRowRel ? 1u : 0u) << j;
+          const int rel = (e[j] & kRowRel) ? 1 : 0;                 // relative to the row's first frame, or fixed (frame tc, zero word)
+          cur[j] = (e[j] & ~kRowRel) + rel * warp * k_frames;
+          step[j] = rel * nwarp * k_frames;
         }
       }
       __nv_bfloat16* const oh = reinterpret_cast<__nv_bfloat16*>(d.a0.p0);
       __nv_bfloat16* const ol = reinterpret_cast<__nv_bfloat16*>(d.a0.p1);
       const bool x3 = precision == R3D_PREC_BF16X3;
       for (int tq = warp; tq < d.L0; tq += nwarp) {
-        const int base = tq * k_frames;
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 v = make_float2(xs[off[2 * j] + base * (int)((relbits >> (2 * j)) & 1u)],
-                                       xs[off[2 * j + 1] + base * (int)((relbits >> (2 * j + 1)) & 1u)]);
+          const float2 v = make_float2(xs[cur[2 * j]], xs[cur[2 * j + 1]]);
+          cur[2 * j] += step[2 * j];
+          cur[2 * j + 1] += step[2 * j + 1];
           const __nv_bfloat162 hh = __floats2bfloat162_rn(v.x, v.y);
           hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
           const float2 dlt = __ffma2_rn(__bfloat1622float2(hh), make_float2(-1.f, -1.f), v);      // v - hi, one rounding
