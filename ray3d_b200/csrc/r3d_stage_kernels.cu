@@ -168,40 +168,24 @@ __device__ __forceinline__ void embed_output(const PrologueDev& d, int precision
 // One CTA per sequence (window).  Dynamic smem: T*J*Cin floats (+ embed scratch).
 // src_kind R3D_SRC_UV: pixel keypoints, camera rows per cam_kind; R3D_SRC_RAYS: encoded input, `cam` = param rows (float).
 template <bool UNDIST>
-__global__ void __launch_bounds__(320) prologue_kernel(const PrologueDev* __restrict__ dp, int precision,
+__global__ void __launch_bounds__(320) prologue_kernel(const __grid_constant__ PrologueDev d, int precision,
                                                        const float* __restrict__ src, int64_t src_batch_stride,
                                                        int src_is_uv, const void* __restrict__ cam, int64_t cam_stride,
                                                        int cam_kind, int batch, int flip_from) {
   extern __shared__ float smem[];
-  // The descriptor (~600 bytes: shapes, destination pointers, embedder pointers) goes to shared memory first: read through
-  // `dp` its fields are L2 round trips whenever the streamed keypoints have pushed them out of the small L1, and the
-  // camera embedding at the end of the CTA chained three of those (pointer -> pointer -> value) with nothing to hide them.
-  __shared__ PrologueDev sd;
+  // The descriptor (1.6 KB: shapes, destination pointers, embedder pointers) is a kernel PARAMETER (constant bank): read
+  // through a pointer its fields were L2 round trips whenever the streamed keypoints had pushed them out of the small L1,
+  // and the camera embedding chained three of those (pointer -> pointer -> value).
   __shared__ int kp_next;                  // next 256-keypoint chunk of the window (claimed warp by warp)
   if (threadIdx.x == 0) kp_next = 0;
-  static_assert(sizeof(PrologueDev) % 4 == 0, "word copy");
   const int b = blockIdx.x;
   // flip test-time augmentation (trainer.py:299-302): windows [flip_from, batch) are the mirrored copies of
   // windows [0, batch - flip_from): x component negated, left/right joints swapped, same camera parameters
   const bool flip = b >= flip_from;
   const int bs = flip ? b - flip_from : b;
-  // descriptor words and the camera row are requested together (two independent L2 round trips at the head of every CTA)
-  constexpr int kDescWords = (int)(sizeof(PrologueDev) / 4), kDescPerThread = (kDescWords + 255) / 256;
-  uint32_t dw[kDescPerThread];
-#pragma unroll
-  for (int k = 0; k < kDescPerThread; ++k) {
-    const int i = threadIdx.x + k * blockDim.x;
-    dw[k] = i < kDescWords ? __ldg(reinterpret_cast<const uint32_t*>(dp) + i) : 0u;
-  }
   CamRow c{};
   if (src_is_uv) c = load_cam(cam, cam_stride, cam_kind, bs);      // camera.py:438-439,471 in float64
-#pragma unroll
-  for (int k = 0; k < kDescPerThread; ++k) {
-    const int i = threadIdx.x + k * blockDim.x;
-    if (i < kDescWords) reinterpret_cast<uint32_t*>(&sd)[i] = dw[k];
-  }
-  __syncthreads();
-  const PrologueDev& d = sd;
+  __syncthreads();                                                 // kp_next
   const int T = d.T, J = d.J, JC = d.JC;
   float* xs = smem;                    // [T][JC]
   float* scratch = smem + T * JC + 8;  // [emb_mid] embed hidden
@@ -398,10 +382,10 @@ cudaError_t launch_prologue(const PrologueDev* d_desc, const PrologueDev& h, int
   const int threads = 256;   // measured: 4 CTAs x 256 threads per SM (register-limited) beat 3 x 320 (57 vs 64 us at B=1024, T=243)
   const int is_uv = in.src_kind == R3D_SRC_UV;
   if (is_uv && in.undistort)   // lens undistortion inside the encode: a separate instantiation keeps the common path's registers
-    prologue_kernel<true><<<batch, threads, smem, s>>>(d_desc, precision, in.src, in.src_stride, is_uv, in.cam, in.cam_stride, in.cam_kind,
+    prologue_kernel<true><<<batch, threads, smem, s>>>(h, precision, in.src, in.src_stride, is_uv, in.cam, in.cam_stride, in.cam_kind,
                                                      batch, flip_from);
   else
-    prologue_kernel<false><<<batch, threads, smem, s>>>(d_desc, precision, in.src, in.src_stride, is_uv, in.cam, in.cam_stride, in.cam_kind,
+    prologue_kernel<false><<<batch, threads, smem, s>>>(h, precision, in.src, in.src_stride, is_uv, in.cam, in.cam_stride, in.cam_kind,
                                                       batch, flip_from);
   return cudaGetLastError();
 }
