@@ -418,9 +418,10 @@ cudaError_t launch_video_encode(const float* uv, float* rays, float* param, int6
 // ---- output stage ------------------------------------------------------------------------------
 // flip != 0: head rows [batch, 2*batch) hold the predictions for the mirrored windows; un-mirror them (negate x,
 // swap left/right slots) and average with the direct prediction (trainer.py:338-353; torch.mean of two values).
-__global__ void assemble_kernel(const AssembleDev* __restrict__ dp, float* __restrict__ pos, float* __restrict__ trj,
+// (descriptor as a kernel parameter: the kernel is the last link of every forward's dependency chain, and reading the head
+// pointers through a descriptor pointer added a dependent L2 round trip to it)
+__global__ void assemble_kernel(const __grid_constant__ AssembleDev d, float* __restrict__ pos, float* __restrict__ trj,
                                 float* __restrict__ sum, int batch, int flip) {
-  const AssembleDev& d = *dp;
   const int per = d.J * 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)batch * per) return;
@@ -447,7 +448,7 @@ __global__ void assemble_kernel(const AssembleDev* __restrict__ dp, float* __res
 cudaError_t launch_assemble(const AssembleDev* d_desc, const AssembleDev& h, float* pos, float* trj, float* sum,
                             int batch, int flip, cudaStream_t s) {
   const int64_t n = (int64_t)batch * h.J * 3;
-  assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_desc, pos, trj, sum, batch, flip);
+  assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h, pos, trj, sum, batch, flip);
   return cudaGetLastError();
 }
 
