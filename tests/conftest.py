@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is git-ignored (it travels to the GPU box as a built file): a fresh checkout builds it once here
+    (nvcc cross-compiles sm_100a without a GPU).  The product path itself never builds or falls back -- it fails loudly."""
+    lib = os.path.join(ROOT, "ray3d_b200", "libray3d_b200.so")
+    if not os.path.exists(lib):
+        from ray3d_b200 import build
+        build.build_library()
+
+
 @pytest.fixture(scope="session")
 def golden_meta():
     with open(os.path.join(GOLDEN, "meta.json")) as f:
