@@ -348,7 +348,8 @@ def gemm_roofline(run: Run, ms_step: float, timed_seconds: float, peaks, profile
                                   note="runs on a few CTA pairs beside the per-layer launches; excluded from achieved/frac, "
                                        "included in achieved_timed_region") for p in chained],
         "top_launch": {"name": top["name"], "ms": top["ms"], "gflop": top["gflop"], "achieved": top["gflop"] / top["ms"],
-                       "frac": top["gflop"] / top["ms"] / peak, "share_of_step": top["ms"] / ms_prof, "traffic": top_traffic},
+                       "frac": top["gflop"] / top["ms"] / peak, "tensor_issue_frac": top["gflop"] / top["ms"] * issue / peak if tc else None,
+                       "share_of_step": top["ms"] / ms_prof, "traffic": top_traffic},
         "ms_per_step_with_launch_events": ms_prof,
         "hbm": {"algorithmic_bytes_per_seq": alg_bytes, "achieved_gbs": B * 1e3 / ms_step * alg_bytes / 1e9, "peak_gbs": peaks["hbm_gbs"],
                 "frac": B * 1e3 / ms_step * alg_bytes / 1e9 / peaks["hbm_gbs"],
